@@ -1,0 +1,94 @@
+// Builds the device scan image from a validated host automaton.
+//
+// Results of a scan depend only on the automaton's transition/output structure, never on
+// where the builder placed a state, so the image is free to carry
+// derived fields next to the reference's BASE / CHECK / FAIL / OUTPUT_POS values.
+#include "dev_image.h"
+
+namespace dach {
+
+namespace {
+
+// Every failure chain must end at ROOT (or at DEAD where DEAD is a terminal).  O(n).
+bool fail_chains_terminate(const dach_pma* p, bool dead_is_terminal) {
+    const size_t n = p->slots();
+    std::vector<uint8_t> color(n, 0);  // 0 new, 1 on the current path, 2 proven
+    std::vector<uint32_t> path;
+    for (size_t start = 0; start < n; ++start) {
+        if (color[start]) continue;
+        path.clear();
+        uint32_t s = uint32_t(start);
+        for (;;) {
+            if (s == kRoot || (dead_is_terminal && s == kDead) || color[s] == 2) break;
+            if (color[s] == 1) return false;  // cycle
+            color[s] = 1;
+            path.push_back(s);
+            s = p->fail[s];
+        }
+        for (uint32_t v : path) color[v] = 2;
+    }
+    return true;
+}
+
+}  // namespace
+
+int build_image(const dach_pma* p, HostImage* img) {
+    const size_t n = p->slots();
+    const bool lm = is_leftmost(p->match_kind);
+    img->charwise = p->charwise;
+    img->match_kind = p->match_kind;
+    img->n_slots = uint32_t(n);
+    img->root_opos = n ? p->state_output_pos(kRoot) : 0;
+    img->max_pattern_len = 0;
+    for (const OutputRec& o : p->outputs)
+        if (o.length > img->max_pattern_len) img->max_pattern_len = o.length;
+
+    if (!fail_chains_terminate(p, p->charwise || lm)) {
+        set_error("invalid automaton: a failure chain never reaches the root");
+        return DACH_INVALID_AUTOMATON;
+    }
+
+    img->rec.resize(n * 4);
+    if (!p->charwise) {
+        for (size_t s = 0; s < n; ++s) {
+            // failure target with child-less states skipped
+            uint32_t f = p->fail[s];
+            while (f != kRoot && !(lm && f == kDead) && p->base[f] == 0) f = p->fail[f];
+            uint32_t* r = &img->rec[s * 4];
+            r[0] = p->base[s];
+            r[1] = f;
+            r[2] = (f == kRoot || (lm && f == kDead)) ? 0 : p->base[f];
+            r[3] = p->opos_ch[s];
+        }
+        // dense ROOT row; also valid for the leftmost automaton, whose ROOT transition is
+        // "child or stay" (src/bytewise.rs:1102-1117)
+        img->root_table.assign(256, kRoot);
+        if (n && p->base[kRoot] != 0) {
+            const uint32_t b = p->base[kRoot];
+            for (uint32_t c = 0; c < 256; ++c) {
+                const uint32_t ci = b ^ c;
+                if (ci < n && (p->opos_ch[ci] & 0xff) == c) img->root_table[c] = ci;
+            }
+        }
+    } else {
+        for (size_t s = 0; s < n; ++s) {
+            uint32_t* r = &img->rec[s * 4];
+            r[0] = p->base[s];
+            r[1] = p->check[s];
+            r[2] = p->fail[s];
+            r[3] = p->output_pos[s];
+        }
+        img->root_table.assign(256, kRoot);  // unused by the charwise kernels
+        img->mapper = p->mapper_table;
+    }
+    img->outputs.resize(p->outputs.size() * 4);
+    for (size_t i = 0; i < p->outputs.size(); ++i) {
+        img->outputs[i * 4 + 0] = p->outputs[i].value;
+        img->outputs[i * 4 + 1] = p->outputs[i].length;
+        img->outputs[i * 4 + 2] = p->outputs[i].parent;
+        img->outputs[i * 4 + 3] = 0;
+    }
+    return DACH_OK;
+}
+
+}  // namespace dach

@@ -1,0 +1,27 @@
+// Host-side builder of the device scan image (see scan_lane.cuh for the layouts).
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+#include "host.h"
+
+namespace dach {
+
+struct HostImage {
+    bool charwise = false;
+    uint8_t match_kind = 0;
+    uint32_t n_slots = 0;
+    uint32_t root_opos = 0;
+    uint32_t max_pattern_len = 0;
+    std::vector<uint32_t> rec;         // 4 words per slot
+    std::vector<uint32_t> outputs;     // 4 words per output
+    std::vector<uint32_t> root_table;  // 256 words (bytewise)
+    std::vector<uint32_t> mapper;      // charwise code table
+};
+
+// Returns DACH_OK or DACH_INVALID_AUTOMATON (a failure chain that never reaches ROOT would
+// spin a kernel forever; the crate documents the same hazard at src/bytewise.rs:824-830).
+int build_image(const dach_pma* p, HostImage* img);
+
+}  // namespace dach

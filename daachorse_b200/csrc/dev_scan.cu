@@ -1,0 +1,524 @@
+// CUDA kernels (sm_100a) and the device half of the C ABI of libdaachorse_b200.
+//
+// Pipeline of one dach_dev_scan_batch():
+//   1. k_scan<CHARWISE, MODE>   persistent grid (CTAs = SMs x ctas_per_sm); lanes pull items from
+//                               one atomic counter; each lane walks its haystack through the
+//                               automaton image (hot records + root row in shared memory, the
+//                               rest through L1/L2) and appends matches to pooled 256-byte blocks.
+//   2. k_offsets_*              exclusive scan of the per-item match counts -> d_out_offs (u64).
+//   3. k_gather                 copies every pooled block to its final place, which makes the
+//                               output dense and ordered exactly like the crate's iterators.
+// No CPU fallback exists: every entry point here fails with DACH_CUDA_ERROR without a device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+
+#include "dev_image.h"
+#include "host.h"
+#include "scan_lane.cuh"
+
+namespace dach {
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+
+constexpr int kMaxThreads = 1024;
+constexpr uint32_t kRootBytes = 1024;  // 256 x u32 at the front of dynamic shared memory
+
+template <bool CHARWISE, int MODE>
+__global__ void __launch_bounds__(kMaxThreads, 1) k_scan(ScanParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* s_root = reinterpret_cast<uint32_t*>(smem_raw);
+    uint4* s_hot = reinterpret_cast<uint4*>(smem_raw + kRootBytes);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_root[i] = P.root_table[i];
+    for (uint32_t i = threadIdx.x; i < P.hot_n; i += blockDim.x) s_hot[i] = P.rec[i];
+    __syncthreads();
+
+    RecView V{P.rec, s_hot, P.hot_n, s_root};
+    TextWin T;
+    Emitter E;
+    for (;;) {
+        const unsigned long long item = atomicAdd(&P.ctrl->next_item, 1ull);
+        if (item >= P.n_items) break;
+        const uint64_t o0 = P.offs[item], o1 = P.offs[item + 1];
+        const uint32_t len = (uint32_t)(o1 - o0);
+        T.open(P.text + o0);
+        E.begin((uint32_t)item);
+        if (MODE == M_LEFTMOST)
+            scan_leftmost<CHARWISE>(P, V, T, E, len);
+        else
+            scan_standard<CHARWISE, MODE>(P, V, T, E, len);
+        E.finish(P);
+    }
+}
+
+// ---- exclusive scan of counts (u32) into offsets (u64) -----------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 8;
+constexpr int kScanTile = kScanThreads * kScanPerThread;
+
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long* total) {
+    __shared__ unsigned long long warp_sums[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long w = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += t;
+        }
+        if (lane < kScanThreads / 32) warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const unsigned long long before = wid ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[kScanThreads / 32 - 1];
+    __syncthreads();
+    return before + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_offsets_tile_sums(const uint32_t* counts, uint64_t n,
+                                                                      unsigned long long* tile_sums) {
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+    unsigned long long s = 0;
+    for (int k = 0; k < kScanPerThread; ++k) {
+        const uint64_t i = base + (uint64_t)k * kScanThreads + threadIdx.x;
+        if (i < n) s += counts[i];
+    }
+    unsigned long long total;
+    (void)block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// one CTA turns the tile sums into exclusive tile offsets (in place)
+__global__ void __launch_bounds__(kScanThreads) k_offsets_scan_tiles(unsigned long long* tile_sums, uint64_t n_tiles) {
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < n_tiles; base += kScanThreads) {
+        const uint64_t i = base + threadIdx.x;
+        const unsigned long long v = i < n_tiles ? tile_sums[i] : 0;
+        unsigned long long total;
+        const unsigned long long ex = block_exclusive_scan(v, &total);
+        if (i < n_tiles) tile_sums[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_offsets_apply(const uint32_t* counts, uint64_t n,
+                                                                  const unsigned long long* tile_offs,
+                                                                  unsigned long long* out_offs) {
+    // thread t owns kScanPerThread consecutive items so that one block scan suffices
+    const uint64_t first = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPerThread;
+    uint32_t c[kScanPerThread];
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) {
+        const uint64_t i = first + k;
+        c[k] = i < n ? counts[i] : 0;
+        s += c[k];
+    }
+    unsigned long long total;
+    unsigned long long run = tile_offs[blockIdx.x] + block_exclusive_scan(s, &total);
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) {
+        const uint64_t i = first + k;
+        if (i < n) out_offs[i] = run;
+        run += c[k];
+        if (i + 1 == n) out_offs[n] = run;
+    }
+}
+
+// ---- gather pooled blocks into the final, ordered match array ----------------------------
+// One warp per block.  Skipped entirely when the batch overflowed the pool or out_cap.
+__global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const ScanCtrl* ctrl, uint32_t pool_blocks,
+                                                 const uint32_t* counts, const unsigned long long* out_offs,
+                                                 uint64_t n_items, unsigned long long out_cap, uint32_t* out_words) {
+    if (ctrl->overflow) return;
+    if (out_offs[n_items] > out_cap) return;
+    const uint32_t used = min(ctrl->blk_cursor, pool_blocks);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps_per_cta = blockDim.x >> 5;
+    for (uint64_t b = (uint64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); b < used;
+         b += (uint64_t)gridDim.x * warps_per_cta) {
+        const uint32_t* blk = pool + b * BLK_WORDS;
+        const uint32_t item = blk[0], seq = blk[1];
+        const uint32_t cnt = counts[item];
+        const uint32_t first = seq * BLK_MATCHES;
+        const uint32_t nm = min(BLK_MATCHES, cnt - first);
+        uint32_t* dst = out_words + (out_offs[item] + first) * 3ull;
+        const uint32_t nw = nm * 3;
+        if (lane < nw) dst[lane] = blk[2 + lane];
+        if (lane + 32 < nw) dst[lane + 32] = blk[2 + lane + 32];
+    }
+}
+
+__global__ void k_zero_offsets(unsigned long long* out_offs) { out_offs[0] = 0; }
+
+}  // namespace dach
+
+// ------------------------------------------------------------------------------------------
+// device handle
+// ------------------------------------------------------------------------------------------
+
+using namespace dach;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+bool cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return false;
+}
+
+bool ensure(DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return true;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+    const size_t want = std::max<size_t>(bytes, 256);
+    if (!cuda_ok(cudaMalloc(&b.p, want), "cudaMalloc")) return false;
+    b.bytes = want;
+    return true;
+}
+
+struct HostPinned {
+    unsigned long long total;
+    ScanCtrl ctrl;
+};
+
+}  // namespace
+
+struct dach_dev {
+    int device = 0;
+    bool charwise = false;
+    uint8_t match_kind = 0;
+    uint32_t n_slots = 0, root_opos = 0, mapper_len = 0, max_pattern_len = 0;
+    size_t image_bytes = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    // image
+    uint4* d_rec = nullptr;
+    uint4* d_outputs = nullptr;
+    uint32_t* d_root = nullptr;
+    uint32_t* d_mapper = nullptr;
+    // workspace (guarded by mu)
+    std::mutex mu;
+    DevBuf counts, tiles, ctrl, pool;
+    DevBuf h_text, h_offs, h_out, h_out_offs;  // device staging for dach_scan_batch_host
+    HostPinned* pinned = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // options
+    int64_t opt_hot_records = -1;  // -1: as many as fit
+    int64_t opt_threads = 1024;
+    int64_t opt_ctas_per_sm = 1;
+    // stats
+    uint64_t launches = 0;
+    double last_scan_ms = 0, last_total_ms = 0;
+    uint64_t last_h2d = 0, last_d2h = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cuda_ok(cudaSetDevice(dev), "cudaSetDevice");
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <bool CW, int MODE>
+cudaError_t launch_scan_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
+    static bool attr_done = false;  // per instantiation
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_scan<CW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    k_scan<CW, MODE><<<grid, threads, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan(bool cw, int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
+    switch ((cw ? 4 : 0) + mode) {
+        case 0: return launch_scan_t<false, M_FIND>(P, grid, threads, smem, st);
+        case 1: return launch_scan_t<false, M_OVERLAPPING>(P, grid, threads, smem, st);
+        case 2: return launch_scan_t<false, M_NO_SUFFIX>(P, grid, threads, smem, st);
+        case 3: return launch_scan_t<false, M_LEFTMOST>(P, grid, threads, smem, st);
+        case 4: return launch_scan_t<true, M_FIND>(P, grid, threads, smem, st);
+        case 5: return launch_scan_t<true, M_OVERLAPPING>(P, grid, threads, smem, st);
+        case 6: return launch_scan_t<true, M_NO_SUFFIX>(P, grid, threads, smem, st);
+        case 7: return launch_scan_t<true, M_LEFTMOST>(P, grid, threads, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+int check_mode(const dach_dev* d, int mode) {
+    if (mode < DACH_FIND || mode > DACH_LEFTMOST_FIND) {
+        set_error("unknown scan mode");
+        return DACH_INVALID_ARGUMENT;
+    }
+    const bool lm = is_leftmost(d->match_kind);
+    if ((mode == DACH_LEFTMOST_FIND) != lm) {
+        set_error(lm ? "Error: match_kind must be standard." : "Error: match_kind must be leftmost.");
+        return DACH_MATCH_KIND_MISMATCH;
+    }
+    return DACH_OK;
+}
+
+// the device-side pipeline; caller holds d->mu and has set the device
+int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, const uint64_t* d_offs, uint64_t n,
+                dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs, uint64_t* needed, cudaStream_t st) {
+    if (n > 0xfffffff0ull) {
+        set_error("too many haystacks in one batch (max 2^32-16)");
+        return DACH_INVALID_ARGUMENT;
+    }
+    if (n == 0) {
+        k_zero_offsets<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(d_out_offs));
+        ++d->launches;
+        if (!cuda_ok(cudaStreamSynchronize(st), "sync")) return DACH_CUDA_ERROR;
+        if (needed) *needed = 0;
+        return DACH_OK;
+    }
+    const uint64_t n_tiles = (n + kScanTile - 1) / kScanTile;
+    uint64_t pool_blocks64 = out_cap / BLK_MATCHES + n + 1024;
+    if (pool_blocks64 > 0xffffff00ull) pool_blocks64 = 0xffffff00ull;
+    const uint32_t pool_blocks = (uint32_t)pool_blocks64;
+    if (!ensure(d->counts, n * 4) || !ensure(d->tiles, n_tiles * 8) || !ensure(d->ctrl, sizeof(ScanCtrl)) ||
+        !ensure(d->pool, (size_t)pool_blocks * BLK_WORDS * 4))
+        return DACH_CUDA_ERROR;
+
+    ScanParams P;
+    memset(&P, 0, sizeof(P));
+    P.rec = d->d_rec;
+    P.outputs = d->d_outputs;
+    P.root_table = d->d_root;
+    P.mapper = d->d_mapper;
+    P.mapper_len = d->mapper_len;
+    P.n_slots = d->n_slots;
+    P.root_opos = d->root_opos;
+    P.text = d_text;
+    P.offs = d_offs;
+    P.n_items = n;
+    P.counts = static_cast<uint32_t*>(d->counts.p);
+    P.pool = static_cast<uint32_t*>(d->pool.p);
+    P.pool_blocks = pool_blocks;
+    P.ctrl = static_cast<ScanCtrl*>(d->ctrl.p);
+
+    int threads = (int)std::min<int64_t>(std::max<int64_t>(d->opt_threads, 32), kMaxThreads);
+    threads = (threads / 32) * 32;
+    int ctas_per_sm = (int)std::min<int64_t>(std::max<int64_t>(d->opt_ctas_per_sm, 1), 2048 / threads);
+    const size_t smem_budget = std::min<size_t>(d->smem_optin, 227 * 1024) / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
+    uint64_t hot = smem_budget > kRootBytes ? (smem_budget - kRootBytes) / 16 : 0;
+    if (d->opt_hot_records >= 0) hot = std::min<uint64_t>(hot, (uint64_t)d->opt_hot_records);
+    hot = std::min<uint64_t>(hot, d->n_slots);
+    P.hot_n = (uint32_t)hot;
+    const size_t smem = kRootBytes + (size_t)hot * 16;
+    const int grid = d->sm_count * ctas_per_sm;
+
+    if (!cuda_ok(cudaMemsetAsync(d->ctrl.p, 0, sizeof(ScanCtrl), st), "memset ctrl")) return DACH_CUDA_ERROR;
+    cudaEventRecord(d->ev[0], st);
+    if (!cuda_ok(launch_scan(d->charwise, mode, P, grid, threads, smem, st), "k_scan launch")) return DACH_CUDA_ERROR;
+    cudaEventRecord(d->ev[1], st);
+    unsigned long long* offs64 = reinterpret_cast<unsigned long long*>(d_out_offs);
+    unsigned long long* tiles = static_cast<unsigned long long*>(d->tiles.p);
+    k_offsets_tile_sums<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n, tiles);
+    k_offsets_scan_tiles<<<1, kScanThreads, 0, st>>>(tiles, n_tiles);
+    k_offsets_apply<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n, tiles, offs64);
+    const int gather_grid = d->sm_count * 8;
+    k_gather<<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, offs64, n, out_cap,
+                                         reinterpret_cast<uint32_t*>(d_out));
+    d->launches += 5;
+    if (!cuda_ok(cudaGetLastError(), "kernel launch")) return DACH_CUDA_ERROR;
+    cudaEventRecord(d->ev[2], st);
+    cudaMemcpyAsync(&d->pinned->total, offs64 + n, 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&d->pinned->ctrl, d->ctrl.p, sizeof(ScanCtrl), cudaMemcpyDeviceToHost, st);
+    if (!cuda_ok(cudaStreamSynchronize(st), "scan pipeline")) return DACH_CUDA_ERROR;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]) == cudaSuccess) d->last_scan_ms = ms;
+    if (cudaEventElapsedTime(&ms, d->ev[0], d->ev[2]) == cudaSuccess) d->last_total_ms = ms;
+    const uint64_t total = d->pinned->total;
+    if (needed) *needed = total;
+    if (d->pinned->ctrl.overflow || total > out_cap) {
+        set_error("output capacity too small");
+        return DACH_OUTPUT_OVERFLOW;
+    }
+    return DACH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
+    if (!out) return DACH_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!pma) {
+        set_error("null automaton");
+        return DACH_INVALID_ARGUMENT;
+    }
+    HostImage img;
+    const int rc = build_image(pma, &img);
+    if (rc) return rc;
+    int ndev = 0;
+    if (!cuda_ok(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount")) return DACH_CUDA_ERROR;
+    if (device < 0 || device >= ndev) {
+        set_error("no such CUDA device");
+        return DACH_CUDA_ERROR;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) return DACH_CUDA_ERROR;
+    std::unique_ptr<dach_dev> d(new dach_dev());
+    d->device = device;
+    d->charwise = img.charwise;
+    d->match_kind = img.match_kind;
+    d->n_slots = img.n_slots;
+    d->root_opos = img.root_opos;
+    d->max_pattern_len = img.max_pattern_len;
+    d->mapper_len = (uint32_t)img.mapper.size();
+    cudaDeviceProp prop;
+    if (!cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return DACH_CUDA_ERROR;
+    d->sm_count = prop.multiProcessorCount;
+    d->smem_optin = prop.sharedMemPerBlockOptin;
+    auto up = [&](const std::vector<uint32_t>& v, void** dst) -> bool {
+        const size_t bytes = std::max<size_t>(v.size() * 4, 16);
+        if (!cuda_ok(cudaMalloc(dst, bytes), "cudaMalloc image")) return false;
+        if (!v.empty() && !cuda_ok(cudaMemcpy(*dst, v.data(), v.size() * 4, cudaMemcpyHostToDevice), "upload image"))
+            return false;
+        d->image_bytes += v.size() * 4;
+        return true;
+    };
+    bool ok = up(img.rec, reinterpret_cast<void**>(&d->d_rec)) && up(img.outputs, reinterpret_cast<void**>(&d->d_outputs)) &&
+              up(img.root_table, reinterpret_cast<void**>(&d->d_root)) && up(img.mapper, reinterpret_cast<void**>(&d->d_mapper));
+    ok = ok && cuda_ok(cudaMallocHost(reinterpret_cast<void**>(&d->pinned), sizeof(HostPinned)), "cudaMallocHost");
+    for (int i = 0; ok && i < 4; ++i) ok = cuda_ok(cudaEventCreate(&d->ev[i]), "cudaEventCreate");
+    if (!ok) {
+        dach_dev_free(d.release());
+        return DACH_CUDA_ERROR;
+    }
+    *out = d.release();
+    return DACH_OK;
+}
+
+void dach_dev_free(dach_dev* d) {
+    if (!d) return;
+    DeviceGuard g(d->device);
+    cudaFree(d->d_rec);
+    cudaFree(d->d_outputs);
+    cudaFree(d->d_root);
+    cudaFree(d->d_mapper);
+    for (DevBuf* b : {&d->counts, &d->tiles, &d->ctrl, &d->pool, &d->h_text, &d->h_offs, &d->h_out, &d->h_out_offs})
+        if (b->p) cudaFree(b->p);
+    if (d->pinned) cudaFreeHost(d->pinned);
+    for (int i = 0; i < 4; ++i)
+        if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+    delete d;
+}
+
+size_t dach_dev_image_bytes(const dach_dev* d) { return d ? d->image_bytes : 0; }
+
+int dach_dev_scan_batch(dach_dev* d, int mode, const uint8_t* d_text, const uint64_t* d_offs, uint64_t n,
+                        uint64_t text_bytes, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs,
+                        uint64_t* needed, void* stream) {
+    (void)text_bytes;
+    if (!d || !d_offs || !d_out_offs || (out_cap && !d_out)) {
+        set_error("null argument");
+        return DACH_INVALID_ARGUMENT;
+    }
+    const int rc = check_mode(d, mode);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(d->mu);
+    DeviceGuard g(d->device);
+    if (!g.ok) return DACH_CUDA_ERROR;
+    return scan_locked(d, mode, d_text, d_offs, n, d_out, out_cap, d_out_offs, needed, static_cast<cudaStream_t>(stream));
+}
+
+int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint64_t* offs, uint64_t n,
+                         dach_match* out, uint64_t out_cap, uint64_t* out_offs, uint64_t* needed) {
+    if (!d || !offs || !out_offs || (out_cap && !out)) {
+        set_error("null argument");
+        return DACH_INVALID_ARGUMENT;
+    }
+    int rc = check_mode(d, mode);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(d->mu);
+    DeviceGuard g(d->device);
+    if (!g.ok) return DACH_CUDA_ERROR;
+    const uint64_t text_bytes = offs[n] - offs[0];
+    if (!ensure(d->h_text, text_bytes + 16) || !ensure(d->h_offs, (n + 1) * 8) || !ensure(d->h_out, out_cap * 12 + 16) ||
+        !ensure(d->h_out_offs, (n + 1) * 8))
+        return DACH_CUDA_ERROR;
+    cudaStream_t st = nullptr;
+    // offsets are passed through unchanged: the text is copied from its first used byte so
+    // that offs[0] may be non-zero
+    const uint8_t* src = text ? text + offs[0] : nullptr;
+    if (text_bytes && !cuda_ok(cudaMemcpyAsync(d->h_text.p, src, text_bytes, cudaMemcpyHostToDevice, st), "H2D text"))
+        return DACH_CUDA_ERROR;
+    if (!cuda_ok(cudaMemcpyAsync(d->h_offs.p, offs, (n + 1) * 8, cudaMemcpyHostToDevice, st), "H2D offsets"))
+        return DACH_CUDA_ERROR;
+    const uint8_t* d_text = static_cast<const uint8_t*>(d->h_text.p) - offs[0];
+    uint64_t total = 0;
+    rc = scan_locked(d, mode, d_text, static_cast<const uint64_t*>(d->h_offs.p), n,
+                     static_cast<dach_match*>(d->h_out.p), out_cap, static_cast<uint64_t*>(d->h_out_offs.p), &total, st);
+    if (needed) *needed = total;
+    d->last_h2d = text_bytes + (n + 1) * 8;
+    d->last_d2h = 0;
+    if (rc) return rc;
+    if (!cuda_ok(cudaMemcpyAsync(out_offs, d->h_out_offs.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H offsets"))
+        return DACH_CUDA_ERROR;
+    if (total && !cuda_ok(cudaMemcpyAsync(out, d->h_out.p, total * 12, cudaMemcpyDeviceToHost, st), "D2H matches"))
+        return DACH_CUDA_ERROR;
+    if (!cuda_ok(cudaStreamSynchronize(st), "D2H")) return DACH_CUDA_ERROR;
+    d->last_d2h = (n + 1) * 8 + total * 12;
+    return DACH_OK;
+}
+
+uint64_t dach_dev_kernel_launches(const dach_dev* d) { return d ? d->launches : 0; }
+double dach_dev_last_scan_kernel_ms(const dach_dev* d) { return d ? d->last_scan_ms : 0; }
+double dach_dev_last_total_ms(const dach_dev* d) { return d ? d->last_total_ms : 0; }
+uint64_t dach_dev_last_h2d_bytes(const dach_dev* d) { return d ? d->last_h2d : 0; }
+uint64_t dach_dev_last_d2h_bytes(const dach_dev* d) { return d ? d->last_d2h : 0; }
+
+int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
+    if (!d || !name) return DACH_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(d->mu);
+    const std::string k(name);
+    if (k == "hot_records")
+        d->opt_hot_records = value;
+    else if (k == "threads")
+        d->opt_threads = value;
+    else if (k == "ctas_per_sm")
+        d->opt_ctas_per_sm = value;
+    else {
+        set_error("unknown option " + k);
+        return DACH_INVALID_ARGUMENT;
+    }
+    return DACH_OK;
+}
+
+}  // extern "C"

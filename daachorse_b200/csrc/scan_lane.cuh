@@ -1,0 +1,450 @@
+// Per-lane scan logic of libdaachorse_b200 (sm_100a).
+//
+// Everything here is __host__ __device__ so that tests/emu can compile the SAME lane logic
+// with g++ (-DDACH_EMU) and step it on the CPU against the oracle while no GPU is attached.
+// That harness is test infrastructure; the product only ever runs this code inside the
+// CUDA kernels of dev_scan.cu.
+//
+// Device image (built by dev_image.cpp from the validated host automaton):
+//   bytewise record  uint4 {base, efail, fbase, opos<<8 | check}           16 B / slot
+//       base    BASE of the slot (0 = no children)            src/bytewise.rs:1131-1137
+//       efail   failure target with child-less states skipped (a state without children can
+//               never satisfy a probe, src/bytewise.rs:1075-1083); kRoot ends the chase in the
+//               dense root table, kDead (leftmost only) ends it at ROOT without a probe
+//               (src/bytewise.rs:1120-1123)
+//       fbase   BASE of efail, so a missed probe is followed by the next probe without first
+//               loading the failure state's record
+//   charwise record  uint4 {base, check(parent), fail, output_pos}         src/charwise.rs:1096-1101
+//   output           uint4 {value, length, parent, 0}                      src/lib.rs:213-218
+//   root table       256 x u32                                             src/bytewise.rs:1040-1056
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DACH_HD __host__ __device__ __forceinline__
+#else
+#define DACH_HD inline
+#ifndef DACH_EMU_TYPES
+#define DACH_EMU_TYPES
+struct uint4 {
+    uint32_t x, y, z, w;
+};
+#endif
+#endif
+
+namespace dach {
+
+constexpr uint32_t D_ROOT = 0;
+constexpr uint32_t D_DEAD = 1;
+constexpr uint32_t D_INVALID_CODE = 0xffffffffu;
+
+// scan modes == dach_scan_mode
+constexpr int M_FIND = 0, M_OVERLAPPING = 1, M_NO_SUFFIX = 2, M_LEFTMOST = 3;
+
+// Match staging: every lane appends its matches to 256-byte blocks taken from one pool with an
+// atomic bump allocator.  Block layout (64 words): [0] item id, [1] sequence number of the
+// block inside the item, [2..61] up to 20 matches (start, end, value), [62..63] unused.
+constexpr uint32_t BLK_WORDS = 64;
+constexpr uint32_t BLK_MATCHES = 20;
+
+struct ScanCtrl {
+    unsigned long long next_item;  // dynamic work counter
+    unsigned int blk_cursor;       // bump allocator
+    unsigned int overflow;         // pool exhausted
+};
+
+struct ScanParams {
+    // automaton image
+    const uint4* rec;
+    const uint4* outputs;
+    const uint32_t* root_table;  // global copy (kernels stage it in shared memory)
+    const uint32_t* mapper;
+    uint32_t mapper_len;
+    uint32_t n_slots;
+    uint32_t root_opos;  // output_pos of ROOT (empty pattern), 0 = none
+    uint32_t hot_n;      // leading records staged in shared memory
+    // batch
+    const uint8_t* text;
+    const uint64_t* offs;
+    uint64_t n_items;
+    // results
+    uint32_t* counts;  // matches per item
+    uint32_t* pool;
+    uint32_t pool_blocks;
+    ScanCtrl* ctrl;
+};
+
+DACH_HD uint4 ld_u4(const uint4* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+DACH_HD uint32_t ld_u32(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// ---- haystack bytes through a 16-byte register window ---------------------------------
+// Text is read with aligned 16-byte vector loads; an aligned 16-byte load never crosses a
+// page, so the window may cover a few bytes outside the haystack but never faults.
+struct TextWin {
+    const uint8_t* hay;  // first byte of the haystack
+    uint64_t cur;        // address>>4 of the cached window
+    uint4 w;
+
+    DACH_HD void open(const uint8_t* h) {
+        hay = h;
+        cur = ~0ull;
+    }
+    DACH_HD uint32_t at(uint32_t pos) {
+        const uint64_t a = (uint64_t)(uintptr_t)hay + pos;
+        const uint64_t blk = a >> 4;
+        if (blk != cur) {
+            cur = blk;
+#if defined(__CUDA_ARCH__)
+            const uint4* q = reinterpret_cast<const uint4*>((uintptr_t)(blk << 4));
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                         : "l"(q));
+#elif defined(DACH_EMU)
+            // CPU emulation (tests/emu): gather only bytes inside [emu_lo, emu_hi)
+            const uint8_t* q = reinterpret_cast<const uint8_t*>((uintptr_t)(blk << 4));
+            uint32_t v[4] = {0, 0, 0, 0};
+            for (int i = 0; i < 16; ++i) {
+                const uint8_t* qi = q + i;
+                uint32_t b = (qi >= emu_lo && qi < emu_hi) ? *qi : 0;
+                v[i >> 2] |= b << ((i & 3) * 8);
+            }
+            w.x = v[0], w.y = v[1], w.z = v[2], w.w = v[3];
+#else
+            w.x = w.y = w.z = w.w = 0;  // host pass of nvcc: never executed
+#endif
+        }
+        const uint32_t o = (uint32_t)a & 15u;
+        const uint32_t lo = (o & 8u) ? w.z : w.x;
+        const uint32_t hi = (o & 8u) ? w.w : w.y;
+        const uint32_t word = (o & 4u) ? hi : lo;
+        return (word >> ((o & 3u) * 8u)) & 0xffu;
+    }
+#if defined(DACH_EMU)
+    const uint8_t* emu_lo = nullptr;
+    const uint8_t* emu_hi = nullptr;
+#endif
+};
+
+// ---- match emission --------------------------------------------------------------------
+struct Emitter {
+    uint32_t* blk;   // current block (nullptr when the pool is exhausted or nothing emitted yet)
+    uint32_t fill;   // matches in the current block
+    uint32_t count;  // matches of the current item
+    uint32_t item;
+
+    DACH_HD void begin(uint32_t item_id) {
+        blk = nullptr;
+        fill = 0;
+        count = 0;
+        item = item_id;
+    }
+    DACH_HD void emit(const ScanParams& P, uint32_t start, uint32_t end, uint32_t value) {
+        if (fill == 0) {
+#if defined(__CUDA_ARCH__)
+            const uint32_t b = atomicAdd(&P.ctrl->blk_cursor, 1u);
+#else
+            const uint32_t b = P.ctrl->blk_cursor++;
+#endif
+            if (b < P.pool_blocks) {
+                blk = P.pool + (size_t)b * BLK_WORDS;
+                blk[0] = item;
+                blk[1] = count / BLK_MATCHES;
+            } else {
+                blk = nullptr;
+                P.ctrl->overflow = 1u;
+            }
+        }
+        if (blk) {
+            uint32_t* q = blk + 2 + 3 * fill;
+            q[0] = start;
+            q[1] = end;
+            q[2] = value;
+        }
+        fill = (fill + 1 == BLK_MATCHES) ? 0 : fill + 1;
+        ++count;
+    }
+    DACH_HD void finish(const ScanParams& P) { P.counts[item] = count; }
+};
+
+// Walk a merged output list from `opos` (1-based, 0 = end), emitting every pattern ending
+// at `end` (src/bytewise/iter.rs:134-148).
+DACH_HD void emit_chain(const ScanParams& P, Emitter& E, uint32_t opos, uint32_t end) {
+    while (opos != 0) {
+        const uint4 o = ld_u4(P.outputs + (opos - 1));
+        E.emit(P, end - o.y, end, o.x);
+        opos = o.z;
+    }
+}
+DACH_HD void emit_head(const ScanParams& P, Emitter& E, uint32_t opos, uint32_t end) {
+    const uint4 o = ld_u4(P.outputs + (opos - 1));
+    E.emit(P, end - o.y, end, o.x);
+}
+
+// ---- record access: leading `hot_n` records come from shared memory --------------------
+struct RecView {
+    const uint4* glob;
+    const uint4* hot;  // shared-memory copy of glob[0 .. hot_n)
+    uint32_t hot_n;
+    const uint32_t* root;  // root table (shared memory on the device)
+    DACH_HD uint4 get(uint32_t i) const { return i < hot_n ? hot[i] : ld_u4(glob + i); }
+};
+
+// ---- bytewise transitions ---------------------------------------------------------------
+// delta(s, c) for the Standard automaton (src/bytewise.rs:1063-1088) on the device image.
+// `r` is the record of the current state s (unused when s == ROOT); returns the new state
+// and leaves its record in `r`.
+DACH_HD uint32_t bw_step(const RecView& V, uint32_t s, uint4& r, uint32_t c) {
+    if (s != D_ROOT) {
+        if (r.x != 0) {  // own children
+            const uint32_t ci = r.x ^ c;
+            const uint4 x = V.get(ci);
+            if ((x.w & 0xffu) == c) {
+                r = x;
+                return ci;
+            }
+        }
+        uint32_t f = r.y, fb = r.z;
+        while (f != D_ROOT) {  // failure chase; every visited state has children
+            const uint32_t ci = fb ^ c;
+            const uint4 x = V.get(ci);
+            if ((x.w & 0xffu) == c) {
+                r = x;
+                return ci;
+            }
+            const uint4 fr = V.get(f);
+            f = fr.y;
+            fb = fr.z;
+        }
+    }
+    const uint32_t n = V.root[c];
+    if (n != D_ROOT) r = V.get(n);
+    return n;
+}
+
+// delta for the leftmost automaton (src/bytewise.rs:1094-1128): as above, but a failure
+// link to DEAD ends at ROOT without probing ROOT's children.
+DACH_HD uint32_t bw_step_leftmost(const RecView& V, uint32_t s, uint4& r, uint32_t c) {
+    if (s != D_ROOT) {
+        if (r.x != 0) {
+            const uint32_t ci = r.x ^ c;
+            const uint4 x = V.get(ci);
+            if ((x.w & 0xffu) == c) {
+                r = x;
+                return ci;
+            }
+        }
+        uint32_t f = r.y, fb = r.z;
+        while (f != D_ROOT) {
+            if (f == D_DEAD) return D_ROOT;
+            const uint32_t ci = fb ^ c;
+            const uint4 x = V.get(ci);
+            if ((x.w & 0xffu) == c) {
+                r = x;
+                return ci;
+            }
+            const uint4 fr = V.get(f);
+            f = fr.y;
+            fb = fr.z;
+        }
+    }
+    const uint32_t n = V.root[c];
+    if (n != D_ROOT) r = V.get(n);
+    return n;
+}
+
+// ---- charwise ----------------------------------------------------------------------------
+// UTF-8 decode of one char at `pos` (src/charwise/iter.rs:71-97); input is valid UTF-8.
+DACH_HD uint32_t utf8_at(TextWin& T, uint32_t& pos) {
+    const uint32_t first = T.at(pos++);
+    if (first < 0x80u) return first;
+    uint32_t c = T.at(pos++) & 0x3fu;
+    if (first < 0xe0u) return ((first & 0x1fu) << 6) | c;
+    c = (c << 6) | (T.at(pos++) & 0x3fu);
+    if (first < 0xf0u) return ((first & 0x0fu) << 12) | c;
+    c = (c << 6) | (T.at(pos++) & 0x3fu);
+    return ((first & 0x07u) << 18) | c;
+}
+
+DACH_HD uint32_t map_code(const ScanParams& P, uint32_t cp) {  // src/charwise/mapper.rs:36-42
+    return cp < P.mapper_len ? ld_u32(P.mapper + cp) : D_INVALID_CODE;
+}
+
+// src/charwise.rs:1022-1051 (leftmost == false) and :1057-1092 (leftmost == true)
+template <bool LEFTMOST>
+DACH_HD uint32_t cw_step(const ScanParams& P, const RecView& V, uint32_t s, uint4& r, uint32_t cp) {
+    const uint32_t mc = map_code(P, cp);
+    if (mc == D_INVALID_CODE) return D_ROOT;
+    for (;;) {
+        if (r.x != 0) {
+            const uint32_t ci = r.x ^ mc;
+            const uint4 x = V.get(ci);
+            if (x.y == s) {
+                r = x;
+                return ci;
+            }
+        }
+        if (s == D_ROOT) return D_ROOT;
+        const uint32_t f = r.z;
+        // DEAD ends the chase (src/charwise.rs:1081-1084).  A valid Standard automaton never links a
+        // live state to DEAD; stopping there too keeps a malformed one from spinning the kernel.
+        if (f == D_DEAD) return D_ROOT;
+        s = f;
+        r = V.get(s);
+    }
+}
+
+// ---- one haystack, Standard modes --------------------------------------------------------
+// FindIterator / FindOverlappingIterator / FindOverlappingNoSuffixIterator
+// (src/bytewise/iter.rs:58-113, 133-176, 195-243; src/charwise/iter.rs:115-170, 190-235, 254-302)
+template <bool CHARWISE, int MODE>
+DACH_HD void scan_standard(const ScanParams& P, const RecView& V, TextWin& T, Emitter& E, uint32_t len) {
+    const uint32_t root_opos = P.root_opos;
+    uint4 root_rec = {0, 0, 0, 0};
+    if (CHARWISE) root_rec = V.get(D_ROOT);
+    if (MODE == M_OVERLAPPING) emit_chain(P, E, root_opos, 0);
+    if (MODE == M_NO_SUFFIX && root_opos) {
+        const uint4 o = ld_u4(P.outputs + (root_opos - 1));
+        E.emit(P, 0, 0, o.x);  // length 0, end 0 (iter.rs:210-214)
+    }
+    if (MODE == M_FIND && root_opos) {
+        // an empty pattern exists: only zero-length matches, one per boundary (iter.rs:60-85)
+        const uint32_t v = ld_u4(P.outputs + (root_opos - 1)).x;
+        E.emit(P, 0, 0, v);
+        uint32_t pos = 0;
+        while (pos < len) {
+            if (CHARWISE)
+                (void)utf8_at(T, pos);
+            else
+                ++pos;
+            E.emit(P, pos, pos, v);
+        }
+        return;
+    }
+    uint32_t s = D_ROOT;
+    uint4 r = root_rec;
+    uint32_t pos = 0;
+    while (pos < len) {
+        if (CHARWISE) {
+            const uint32_t cp = utf8_at(T, pos);
+            if (s == D_ROOT) r = root_rec;
+            s = cw_step<false>(P, V, s, r, cp);
+        } else {
+            const uint32_t c = T.at(pos++);
+            s = bw_step(V, s, r, c);
+        }
+        if (s != D_ROOT) {
+            const uint32_t op = CHARWISE ? r.w : (r.w >> 8);
+            if (op != 0) {
+                if (MODE == M_OVERLAPPING) {
+                    emit_chain(P, E, op, pos);
+                } else {
+                    emit_head(P, E, op, pos);
+                    if (MODE == M_FIND) s = D_ROOT;  // every next() restarts at ROOT (iter.rs:87)
+                }
+            }
+        } else if (MODE == M_OVERLAPPING && root_opos) {
+            // ROOT carries the empty pattern: it ends at every position the scan is in ROOT
+            emit_chain(P, E, root_opos, pos);
+        } else if (MODE == M_NO_SUFFIX && root_opos) {
+            emit_head(P, E, root_opos, pos);
+        }
+    }
+}
+
+// ---- one haystack, leftmost --------------------------------------------------------------
+// LeftmostFindIterator (src/bytewise/iter.rs:272-340; src/charwise/iter.rs:328-399).  The
+// iterator fields (pos, init_output_pos, skip_empty) persist across next() calls; one turn of
+// the outer loop is one next().
+template <bool CHARWISE>
+DACH_HD void scan_leftmost(const ScanParams& P, const RecView& V, TextWin& T, Emitter& E, uint32_t len) {
+    uint32_t self_pos = 0;
+    uint32_t init_opos = P.root_opos;
+    bool skip_empty = false;
+    uint4 root_rec = {0, 0, 0, 0};
+    if (CHARWISE) root_rec = V.get(D_ROOT);
+    for (;;) {
+        uint32_t s = D_ROOT;
+        uint4 r = root_rec;
+        uint32_t last = init_opos;
+        bool yielded = false;
+        uint32_t i = self_pos;
+        while (i < len) {
+            const uint32_t unit_start = i;
+            if (CHARWISE) {
+                const uint32_t cp = utf8_at(T, i);
+                if (s == D_ROOT) r = root_rec;
+                s = cw_step<true>(P, V, s, r, cp);
+            } else {
+                const uint32_t c = T.at(i++);
+                s = bw_step_leftmost(V, s, r, c);
+            }
+            if (s == D_ROOT) {
+                if (last != 0) {
+                    const uint32_t end = self_pos;
+                    if (last == init_opos) {
+                        self_pos += i - unit_start;  // one byte / one char
+                        if (skip_empty) {
+                            skip_empty = false;
+                            i = self_pos;  // continue 'a: rescan from the new self.pos
+                            continue;
+                        }
+                    } else {
+                        skip_empty = true;
+                    }
+                    emit_head(P, E, last, end);
+                    yielded = true;
+                    break;
+                }
+            } else {
+                const uint32_t op = CHARWISE ? r.w : (r.w >> 8);
+                if (op != 0) {
+                    last = op;
+                    self_pos = i;
+                }
+            }
+        }
+        if (yielded) continue;
+        if (self_pos == len) init_opos = 0;
+        if (last != 0) {
+            if (self_pos < len && last == init_opos) {
+                // The input ended inside a partial match with only the empty pattern pending.  The
+                // crate's iterator returns that empty match without advancing (iter.rs:320-335) and
+                // therefore never terminates on such input; a kernel must.  End-of-input is treated
+                // like the fall-back-to-ROOT branch (iter.rs:283-293): consume one unit at self.pos
+                // and honour skip_empty ("Reference divergences").
+                const uint32_t end = self_pos;
+                if (CHARWISE) {
+                    uint32_t t = self_pos;
+                    (void)utf8_at(T, t);
+                    self_pos = t;
+                } else {
+                    self_pos += 1;
+                }
+                if (skip_empty) {
+                    skip_empty = false;
+                    continue;
+                }
+                emit_head(P, E, last, end);
+                continue;
+            }
+            emit_head(P, E, last, self_pos);
+            continue;
+        }
+        return;
+    }
+}
+
+}  // namespace dach

@@ -1,0 +1,176 @@
+/*
+ * daachorse_b200.h -- C ABI of libdaachorse_b200.so
+ *
+ * A B200-native (sm_100a) double-array Aho-Corasick matcher that is a drop-in for the
+ * scan path of the Rust crate daac-tools/daachorse 4.0.0.  The reference has no FFI of
+ * its own: its boundary is the crate's public Rust API.  Each entry point below names the
+ * reference item it replaces (file:line relative to the crate root) -- INTEGRATION.md
+ * shows the `extern "C"` block and the thin Rust wrappers a crate maintainer would add.
+ *
+ * Conventions
+ *   - every function returns a dach_status (0 = OK) unless documented otherwise;
+ *   - handles are opaque, created/destroyed by the library; all data buffers are
+ *     caller-owned; no torch / C++ types cross the boundary;
+ *   - V (the pattern value type of the crate) is fixed to u32;
+ *   - match positions are u32 byte offsets inside one haystack (haystacks <= 4 GiB - 1);
+ *     per-haystack result ranges are u64 offsets into the match array;
+ *   - there is NO CPU scan path in this library: scanning requires a CUDA device and
+ *     fails with DACH_CUDA_ERROR otherwise.
+ */
+#ifndef DAACHORSE_B200_H
+#define DAACHORSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DACH_ABI_VERSION 1
+
+/* Status codes.  1-4 mirror DaachorseError (src/errors.rs:10-22); 5 stands for the
+ * `assert!(self.match_kind.is_standard())` / `is_leftmost()` panics of
+ * src/bytewise.rs:194-197,299-302,551-554 and src/charwise.rs:188-191,297-300,557-560
+ * (a Rust shim turns it back into a panic). */
+typedef enum {
+    DACH_OK = 0,
+    DACH_INVALID_ARGUMENT = 1,
+    DACH_AUTOMATON_SCALE = 2,
+    DACH_INVALID_CONVERSION = 3,
+    DACH_INVALID_AUTOMATON = 4,
+    DACH_MATCH_KIND_MISMATCH = 5,
+    DACH_OUTPUT_OVERFLOW = 6, /* out_cap too small; *needed holds the required capacity */
+    DACH_CUDA_ERROR = 7
+} dach_status;
+
+/* MatchKind, #[repr(u8)] (src/lib.rs:324-346) */
+typedef enum {
+    DACH_STANDARD = 0,
+    DACH_LEFTMOST_LONGEST = 1,
+    DACH_LEFTMOST_FIRST = 2
+} dach_match_kind;
+
+/* Which iterator of the crate a batch scan reproduces. */
+typedef enum {
+    DACH_FIND = 0,                       /* find_iter                        src/bytewise.rs:190, src/charwise.rs:184 */
+    DACH_FIND_OVERLAPPING = 1,           /* find_overlapping_iter            src/bytewise.rs:292, src/charwise.rs:290 */
+    DACH_FIND_OVERLAPPING_NO_SUFFIX = 2, /* find_overlapping_no_suffix_iter  src/bytewise.rs:410, src/charwise.rs:412 */
+    DACH_LEFTMOST_FIND = 3               /* leftmost_find_iter               src/bytewise.rs:547, src/charwise.rs:553 */
+} dach_scan_mode;
+
+/* One reported match: Match<u32>{length,end,value} seen through start()/end()/value()
+ * (src/lib.rs:287-320); start = end - length. */
+typedef struct {
+    uint32_t start;
+    uint32_t end;
+    uint32_t value;
+} dach_match;
+
+typedef struct dach_pma dach_pma; /* host-side automaton  (DoubleArrayAhoCorasick / Charwise...) */
+typedef struct dach_dev dach_dev; /* device-resident scan image of one automaton            */
+
+/* ---- construction (host) --------------------------------------------------------- */
+
+/* DoubleArrayAhoCorasickBuilder::new().match_kind(k).num_free_blocks(n).build_with_values()
+ * (src/bytewise/builder.rs:57,90,112,152,204); DoubleArrayAhoCorasick::new / with_values
+ * (src/bytewise.rs:103,145) are the match_kind = Standard, num_free_blocks = 16 case.
+ * Patterns: one byte blob + n+1 offsets.  values == NULL associates value i with pattern i.
+ * num_free_blocks == 0 -> DACH_INVALID_ARGUMENT (the crate panics, builder.rs:113). */
+int dach_bytewise_build(const uint8_t *pattern_bytes, const uint64_t *pattern_offs,
+                        const uint32_t *values, uint32_t n_patterns, uint8_t match_kind,
+                        uint32_t num_free_blocks, dach_pma **out);
+
+/* CharwiseDoubleArrayAhoCorasickBuilder (src/charwise/builder.rs:55,71,89,129,178);
+ * CharwiseDoubleArrayAhoCorasick::new / with_values (src/charwise.rs:100,139).
+ * Patterns must be valid UTF-8 (the crate takes &str); invalid UTF-8 ->
+ * DACH_INVALID_ARGUMENT. */
+int dach_charwise_build(const uint8_t *pattern_bytes, const uint64_t *pattern_offs,
+                        const uint32_t *values, uint32_t n_patterns, uint8_t match_kind,
+                        uint32_t num_free_blocks, dach_pma **out);
+
+/* deserialize (src/bytewise.rs:868-964, src/charwise.rs:896-952): parses the crate's own
+ * wire format, runs the same validation, rebuilds root_table.  *consumed receives the
+ * number of bytes read (the crate returns the remaining slice).  This is the hand-off a
+ * Rust caller uses: pma.serialize() -> dach_pma_deserialize -> dach_dev_upload.
+ * deserialize_unchecked (src/bytewise.rs:1009, src/charwise.rs:997) maps to this same
+ * checked entry point: device loads are unchecked too, so validation is mandatory. */
+int dach_pma_deserialize(const uint8_t *src, size_t len, int charwise, dach_pma **out,
+                         size_t *consumed);
+
+/* serialize (src/bytewise.rs:801-820, src/charwise.rs:831-848): byte-identical to the
+ * crate's output.  dach_pma_serialized_bytes gives the exact size. */
+size_t dach_pma_serialized_bytes(const dach_pma *pma);
+int dach_pma_serialize(const dach_pma *pma, uint8_t *dst, size_t cap, size_t *written);
+
+/* match_kind (src/bytewise.rs:747, src/charwise.rs:762), num_states (:785 / :779),
+ * heap_bytes (:764 / :813), num_elements (src/charwise.rs:796; double-array length for
+ * both variants). */
+uint8_t dach_pma_match_kind(const dach_pma *pma);
+uint32_t dach_pma_num_states(const dach_pma *pma);
+size_t dach_pma_heap_bytes(const dach_pma *pma);
+size_t dach_pma_num_elements(const dach_pma *pma);
+int dach_pma_is_charwise(const dach_pma *pma);
+uint32_t dach_pma_max_pattern_len(const dach_pma *pma); /* longest pattern in bytes */
+void dach_pma_free(dach_pma *pma);
+
+/* ---- device image ---------------------------------------------------------------- */
+
+/* Builds the scan image of `pma` (records repacked for the kernels, root table, mapper,
+ * outputs) and uploads it once to CUDA device `device`. */
+int dach_dev_upload(const dach_pma *pma, int device, dach_dev **out);
+void dach_dev_free(dach_dev *dev);
+size_t dach_dev_image_bytes(const dach_dev *dev); /* bytes resident in HBM for the automaton */
+
+/* ---- batch scan (the hot path) ---------------------------------------------------- */
+
+/* Scans n haystacks that are ALREADY RESIDENT on the device and writes, for haystack i,
+ * exactly the matches the crate's iterator `mode` yields on it, in the same order, to
+ * d_out[d_out_offs[i] .. d_out_offs[i+1]).
+ *
+ *   d_text      device pointer, the haystack bytes back to back
+ *   d_offs      device pointer, n+1 u64 byte offsets into d_text (ascending)
+ *   text_bytes  total byte length of d_text (== offs[n]); the kernel never reads past it
+ *   d_out       device pointer, capacity out_cap matches
+ *   d_out_offs  device pointer, n+1 u64
+ *   needed      host pointer; receives the total number of matches
+ *   stream      cudaStream_t (NULL = default stream); the call synchronises the stream
+ *               before returning
+ *
+ * Returns DACH_OUTPUT_OVERFLOW (and *needed) when out_cap is too small; nothing useful is
+ * in d_out then.  DACH_MATCH_KIND_MISMATCH mirrors the crate's panics.  Charwise haystacks
+ * must be valid UTF-8 (as &str guarantees in the crate). */
+int dach_dev_scan_batch(dach_dev *dev, int mode, const uint8_t *d_text, const uint64_t *d_offs,
+                        uint64_t n, uint64_t text_bytes, dach_match *d_out, uint64_t out_cap,
+                        uint64_t *d_out_offs, uint64_t *needed, void *stream);
+
+/* Same contract with HOST buffers (pageable or pinned): copies text/offsets to the
+ * device in slices overlapped with scanning, copies matches and offsets back.  This is
+ * the call the crate-facing wrappers use and the one bench.py times as `e2e`. */
+int dach_scan_batch_host(dach_dev *dev, int mode, const uint8_t *text, const uint64_t *offs,
+                         uint64_t n, dach_match *out, uint64_t out_cap, uint64_t *out_offs,
+                         uint64_t *needed);
+
+/* ---- introspection for the bench / tests ------------------------------------------ */
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+uint64_t dach_dev_kernel_launches(const dach_dev *dev);
+/* Device time (ms, CUDA events on the launch stream) of the scan kernel alone and of the
+ * whole device-side pipeline in the most recent dach_dev_scan_batch call. */
+double dach_dev_last_scan_kernel_ms(const dach_dev *dev);
+double dach_dev_last_total_ms(const dach_dev *dev);
+/* Bytes moved host<->device by the most recent dach_scan_batch_host call. */
+uint64_t dach_dev_last_h2d_bytes(const dach_dev *dev);
+uint64_t dach_dev_last_d2h_bytes(const dach_dev *dev);
+/* Tuning knobs (0 keeps the default): hot records staged in shared memory, CTAs per SM,
+ * threads per CTA, segment length for intra-haystack chunking of find_overlapping. */
+int dach_dev_set_option(dach_dev *dev, const char *name, int64_t value);
+
+/* Human-readable text of the last error on this thread ("" if none). */
+const char *dach_last_error(void);
+int dach_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAACHORSE_B200_H */

@@ -1441,6 +1441,27 @@ static void scan_leftmost(const orc_pma *p, const uint8_t *hay, size_t len, sink
         /* after the loop (iter.rs:320-339) */
         if (self_pos == len) init_output_pos = 0;
         if (last != 0) {
+            if (self_pos < len && last == init_output_pos) {
+                /* DOCUMENTED DIVERGENCE (DESIGN.md "Reference divergences"): the input ended inside
+                 * a partial match while only the empty pattern is pending.  The reference returns
+                 * this empty match WITHOUT advancing self.pos (iter.rs:320-335), so its iterator
+                 * never terminates on such input.  We treat end-of-input like the fall-back-to-ROOT
+                 * branch (iter.rs:283-293): consume one unit at self.pos, honour skip_empty. */
+                size_t end = self_pos;
+                if (!p->charwise) {
+                    self_pos += 1;
+                } else {
+                    size_t t = self_pos;
+                    (void)orc_utf8_next(hay, &t);
+                    self_pos = t;
+                }
+                if (skip_empty) {
+                    skip_empty = 0;
+                    continue;
+                }
+                emit(k, end, p->outputs[last - 1].length, p->outputs[last - 1].value);
+                continue;
+            }
             emit(k, self_pos, p->outputs[last - 1].length, p->outputs[last - 1].value);
             continue;
         }

@@ -1,0 +1,110 @@
+// CPU emulation harness for the per-lane scan logic (TEST INFRASTRUCTURE ONLY).
+//
+// Compiles daachorse_b200/csrc/scan_lane.cuh -- the exact code the CUDA kernels run -- with
+// g++ (-DDACH_EMU) and drives it the way dev_scan.cu does (items -> lanes, pooled 256-byte
+// blocks, exclusive scan of counts, gather), so that lane-logic bugs surface on the CPU box
+// before GPU minutes are spent.  It is never loaded by the product.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../daachorse_b200/csrc/dev_image.h"
+#include "../../daachorse_b200/csrc/host.h"
+#include "../../daachorse_b200/csrc/scan_lane.cuh"
+
+using namespace dach;
+
+template <bool CW, int MODE>
+static void run_items(const ScanParams& P, const RecView& V, const uint8_t* lo, const uint8_t* hi) {
+    for (uint64_t item = 0; item < P.n_items; ++item) {
+        TextWin T;
+        T.emu_lo = lo;
+        T.emu_hi = hi;
+        Emitter E;
+        const uint64_t o0 = P.offs[item], o1 = P.offs[item + 1];
+        T.open(P.text + o0);
+        E.begin((uint32_t)item);
+        if (MODE == M_LEFTMOST)
+            scan_leftmost<CW>(P, V, T, E, (uint32_t)(o1 - o0));
+        else
+            scan_standard<CW, MODE>(P, V, T, E, (uint32_t)(o1 - o0));
+        E.finish(P);
+    }
+}
+
+extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int charwise, int mode,
+                                   const uint8_t* text, const uint64_t* offs, uint64_t n, uint32_t hot_n,
+                                   uint32_t pool_blocks, dach_match* out, uint64_t out_cap, uint64_t* out_offs,
+                                   uint64_t* needed) {
+    dach_pma* pma = nullptr;
+    size_t used = 0;
+    int rc = wire_read(wire, wire_len, charwise != 0, &pma, &used);
+    if (rc) return rc;
+    HostImage img;
+    rc = build_image(pma, &img);
+    const bool lm = is_leftmost(pma->match_kind);
+    delete pma;
+    if (rc) return rc;
+    if ((mode == M_LEFTMOST) != lm) return DACH_MATCH_KIND_MISMATCH;
+
+    std::vector<uint32_t> counts(n ? n : 1, 0);
+    std::vector<uint32_t> pool((size_t)pool_blocks * BLK_WORDS, 0xdeadbeefu);
+    ScanCtrl ctrl;
+    memset(&ctrl, 0, sizeof(ctrl));
+    ScanParams P;
+    memset(&P, 0, sizeof(P));
+    P.rec = reinterpret_cast<const uint4*>(img.rec.data());
+    P.outputs = reinterpret_cast<const uint4*>(img.outputs.data());
+    P.root_table = img.root_table.data();
+    P.mapper = img.mapper.data();
+    P.mapper_len = (uint32_t)img.mapper.size();
+    P.n_slots = img.n_slots;
+    P.root_opos = img.root_opos;
+    if (hot_n > img.n_slots) hot_n = img.n_slots;
+    P.hot_n = hot_n;
+    P.text = text;
+    P.offs = offs;
+    P.n_items = n;
+    P.counts = counts.data();
+    P.pool = pool.data();
+    P.pool_blocks = pool_blocks;
+    P.ctrl = &ctrl;
+    // "shared memory" copy of the hot records
+    std::vector<uint32_t> hot(img.rec.begin(), img.rec.begin() + (size_t)hot_n * 4);
+    hot.resize(hot.size() + 4);
+    RecView V{P.rec, reinterpret_cast<const uint4*>(hot.data()), hot_n, img.root_table.data()};
+    const uint8_t* lo = text + (n ? offs[0] : 0);
+    const uint8_t* hi = text + (n ? offs[n] : 0);
+    switch ((charwise ? 4 : 0) + mode) {
+        case 0: run_items<false, M_FIND>(P, V, lo, hi); break;
+        case 1: run_items<false, M_OVERLAPPING>(P, V, lo, hi); break;
+        case 2: run_items<false, M_NO_SUFFIX>(P, V, lo, hi); break;
+        case 3: run_items<false, M_LEFTMOST>(P, V, lo, hi); break;
+        case 4: run_items<true, M_FIND>(P, V, lo, hi); break;
+        case 5: run_items<true, M_OVERLAPPING>(P, V, lo, hi); break;
+        case 6: run_items<true, M_NO_SUFFIX>(P, V, lo, hi); break;
+        case 7: run_items<true, M_LEFTMOST>(P, V, lo, hi); break;
+        default: return DACH_INVALID_ARGUMENT;
+    }
+    // offsets (k_offsets_*) and gather (k_gather)
+    uint64_t run = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        out_offs[i] = run;
+        run += counts[i];
+    }
+    out_offs[n] = run;
+    if (needed) *needed = run;
+    if (ctrl.overflow || run > out_cap) return DACH_OUTPUT_OVERFLOW;
+    const uint32_t used_blocks = ctrl.blk_cursor < pool_blocks ? ctrl.blk_cursor : pool_blocks;
+    uint32_t* out_words = reinterpret_cast<uint32_t*>(out);
+    for (uint32_t b = 0; b < used_blocks; ++b) {
+        const uint32_t* blk = pool.data() + (size_t)b * BLK_WORDS;
+        const uint32_t item = blk[0], seq = blk[1];
+        const uint32_t first = seq * BLK_MATCHES;
+        uint32_t nm = counts[item] - first;
+        if (nm > BLK_MATCHES) nm = BLK_MATCHES;
+        uint32_t* dst = out_words + (out_offs[item] + first) * 3ull;
+        for (uint32_t w = 0; w < nm * 3; ++w) dst[w] = blk[2 + w];
+    }
+    return DACH_OK;
+}

@@ -1,0 +1,47 @@
+"""ctypes binding of tests/emu/libdach_emu.so: the kernels' lane logic compiled for the CPU
+(test infrastructure only)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(_HERE, "emu")
+LIB = os.path.join(EMU_DIR, "libdach_emu.so")
+MATCH_DTYPE = np.dtype([("start", "<u4"), ("end", "<u4"), ("value", "<u4")])
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-C", EMU_DIR, "-s"])
+        _lib = C.CDLL(LIB)
+        _lib.emu_scan_batch_wire.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
+                                             C.c_void_p, C.POINTER(C.c_uint64)]
+        _lib.emu_scan_batch_wire.restype = C.c_int
+    return _lib
+
+
+def scan(wire, charwise, mode, text, offs, hot_n=0, pool_blocks=None, out_cap=None):
+    """Returns (rc, matches, out_offs, needed)."""
+    wire_a = np.frombuffer(wire, dtype=np.uint8)
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    n = len(offs) - 1
+    cap = int(out_cap) if out_cap is not None else 1 << 16
+    while True:
+        pb = int(pool_blocks) if pool_blocks is not None else cap // 20 + n + 16
+        out = np.zeros(max(cap, 1), dtype=MATCH_DTYPE)
+        oo = np.zeros(n + 1, dtype=np.uint64)
+        need = C.c_uint64()
+        pad = text if text.size else np.zeros(16, dtype=np.uint8)
+        rc = lib().emu_scan_batch_wire(wire_a.ctypes.data, wire_a.size, int(charwise), mode, pad.ctypes.data,
+                                       offs.ctypes.data, n, hot_n, pb, out.ctypes.data, cap, oo.ctypes.data,
+                                       C.byref(need))
+        if rc == 6 and out_cap is None and pool_blocks is None:
+            cap = max(cap * 2, int(need.value))
+            continue
+        return rc, out[: need.value] if rc == 0 else None, oo, need.value

@@ -1,0 +1,115 @@
+"""The kernels' per-lane logic (daachorse_b200/csrc/scan_lane.cuh), compiled for the CPU by
+tests/emu, against the oracle and the reference's golden vectors.  No GPU needed; the same
+checks run against the real kernels in test_gpu_parity.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import emu_api as E
+import oracle_api as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "search_tests.json"), encoding="utf-8"))
+MODE = {"find_iter": 0, "find_overlapping_iter": 1, "find_overlapping_no_suffix_iter": 2, "leftmost_find_iter": 3}
+ORC_MODE = {0: O.FIND, 1: O.FIND_OVERLAPPING, 2: O.FIND_OVERLAPPING_NO_SUFFIX, 3: O.LEFTMOST_FIND}
+
+
+def triples(m):
+    return [(int(a), int(b), int(c)) for a, b, c in zip(m["start"], m["end"], m["value"])]
+
+
+def _cases():
+    for variant, iterator, coll, kind in GOLD["configs"]:
+        if iterator not in MODE:
+            continue
+        for g in GOLD["collections"][coll]:
+            for t in GOLD["groups"][g]:
+                yield pytest.param(variant, iterator, kind, t, id="%s-%s-%s-%s" % (variant, iterator, kind, t["name"]))
+
+
+@pytest.mark.parametrize("variant,iterator,kind,t", list(_cases()))
+def test_golden_vectors(variant, iterator, kind, t):
+    cw = variant == "charwise"
+    wire = O.OraclePma.build(t["patterns"], charwise=cw, match_kind=O.KIND[kind]).serialize()
+    hay = t["haystack"].encode()
+    text = np.frombuffer(hay, dtype=np.uint8)
+    for hot in (0, 1 << 20):
+        rc, m, oo, need = E.scan(wire, cw, MODE[iterator], text, np.array([0, len(hay)], dtype=np.uint64), hot_n=hot)
+        assert rc == 0
+        assert triples(m) == [(s, e, v) for v, s, e in t["matches"]]
+
+
+def rand_patterns(rng, n, alpha, maxlen, allow_empty=False):
+    return [bytes(rng.integers(97, 97 + alpha, size=int(rng.integers(0 if allow_empty else 1, maxlen + 1))).tolist())
+            for _ in range(n)]
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("cw", [False, True])
+def test_random_batches(seed, kind, cw):
+    rng = np.random.default_rng(100 * seed + 10 * kind + cw)
+    alpha = int(rng.integers(2, 5))
+    pats = rand_patterns(rng, int(rng.integers(1, 60)), alpha, 7, allow_empty=(seed == 0))
+    if cw:  # mix in multi-byte symbols
+        table = ["a", "b", "é", "あ", "𝄞"]
+        pats = ["".join(table[b - 97] for b in p) for p in pats]
+        hay_syms = [table[i] for i in range(alpha)] + ["z"]
+    pma = O.OraclePma.build(pats, charwise=cw, match_kind=kind)
+    wire = pma.serialize()
+    n = 25
+    hays = []
+    for _ in range(n):
+        L = int(rng.integers(0, 120))
+        if cw:
+            hays.append("".join(hay_syms[int(i)] for i in rng.integers(0, len(hay_syms), size=L)).encode())
+        else:
+            hays.append(bytes(rng.integers(97, 97 + alpha + 1, size=L).tolist()))
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(h) for h in hays])
+    text = np.frombuffer(b"".join(hays), dtype=np.uint8)
+    modes = [3] if kind else [0, 1, 2]
+    for mode in modes:
+        ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
+        for hot in (0, 7, 1 << 20):
+            rc, m, oo, need = E.scan(wire, cw, mode, text, offs, hot_n=hot)
+            assert rc == 0
+            assert need == ref["total"]
+            assert np.array_equal(np.diff(oo.astype(np.int64)), ref["counts"].astype(np.int64))
+            assert m.tobytes() == ref["matches"].tobytes(), (pats, mode, hot)
+
+
+def test_unaligned_offsets_and_long_chains():
+    """Haystack starts at every alignment of the 16-byte text window; many outputs per position
+    so that matches span several 20-match blocks."""
+    pats = [b"a" * k for k in range(1, 30)] + [b"a"] * 5
+    pma = O.OraclePma.build(pats)
+    wire = pma.serialize()
+    for shift in range(0, 33):
+        text = np.frombuffer(b"x" * shift + b"a" * 70 + b"b" + b"a" * 40, dtype=np.uint8)
+        offs = np.array([shift, shift + 50, shift + 50, shift + 111], dtype=np.uint64)
+        ref = pma.scan_batch(O.FIND_OVERLAPPING, text, offs, want_matches=True)
+        rc, m, oo, need = E.scan(wire, False, 1, text, offs)
+        assert rc == 0 and m.tobytes() == ref["matches"].tobytes()
+        assert list(oo) == [0] + list(np.cumsum(ref["counts"]))
+
+
+def test_overflow_protocol():
+    pma = O.OraclePma.build([b"a", b"aa"])
+    wire = pma.serialize()
+    text = np.frombuffer(b"a" * 100, dtype=np.uint8)
+    offs = np.array([0, 100], dtype=np.uint64)
+    rc, m, oo, need = E.scan(wire, False, 1, text, offs, out_cap=10)
+    assert rc == 6 and need == 199
+    rc, m, oo, need = E.scan(wire, False, 1, text, offs, out_cap=199, pool_blocks=3)
+    assert rc == 6 and need == 199  # pool exhausted: counting continues
+    rc, m, oo, need = E.scan(wire, False, 1, text, offs, out_cap=199)
+    assert rc == 0 and len(m) == 199
+
+
+def test_mode_gating():
+    wire = O.OraclePma.build([b"a"], match_kind=1).serialize()
+    rc, *_ = E.scan(wire, False, 1, np.zeros(0, np.uint8), np.array([0, 0], dtype=np.uint64))
+    assert rc == 5
