@@ -1,0 +1,281 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle and the
+reference's golden vectors.  Bit-exact: identical (start, end, value) tuples in identical
+per-haystack order."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import daachorse_b200 as D
+import oracle_api as O
+from daachorse_b200 import synth as S
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "search_tests.json"), encoding="utf-8"))
+MODE = {"find_iter": D.FIND, "find_overlapping_iter": D.FIND_OVERLAPPING,
+        "find_overlapping_no_suffix_iter": D.FIND_OVERLAPPING_NO_SUFFIX, "leftmost_find_iter": D.LEFTMOST_FIND}
+ORC = {D.FIND: O.FIND, D.FIND_OVERLAPPING: O.FIND_OVERLAPPING,
+       D.FIND_OVERLAPPING_NO_SUFFIX: O.FIND_OVERLAPPING_NO_SUFFIX, D.LEFTMOST_FIND: O.LEFTMOST_FIND}
+KIND = {"Standard": 0, "LeftmostLongest": 1, "LeftmostFirst": 2}
+
+
+def builder(cw):
+    return D.CharwiseDoubleArrayAhoCorasickBuilder if cw else D.DoubleArrayAhoCorasickBuilder
+
+
+def check_batch(pma, opma, mode, text, offs, nthreads=8):
+    r = pma.scan_batch_host(mode, text, offs)
+    ref = opma.scan_batch(ORC[mode], text, offs, nthreads=nthreads, want_matches=True)
+    assert len(r.matches) == ref["total"]
+    assert np.array_equal(np.diff(r.offsets.astype(np.int64)), ref["counts"].astype(np.int64))
+    assert r.matches.tobytes() == ref["matches"].tobytes()
+    return r
+
+
+@pytest.mark.parametrize("variant,iterator,coll,kind", [tuple(c) for c in GOLD["configs"] if c[1] in MODE])
+def test_golden_vectors(variant, iterator, coll, kind):
+    """tests/aho_corasick_crate_test.rs:63-382 through the iterator surface of the package."""
+    cw = variant == "charwise"
+    for g in GOLD["collections"][coll]:
+        for t in GOLD["groups"][g]:
+            pma = builder(cw).new().match_kind(KIND[kind]).build(t["patterns"])
+            it = getattr(pma, iterator)(t["haystack"])
+            got = [(m.value(), m.start(), m.end()) for m in it]
+            assert got == [tuple(x) for x in t["matches"]], (t["name"], t["patterns"], t["haystack"])
+
+
+def test_config_c1():
+    """BASELINE.json configs[0]: ['bcd','ab','a'] over 'abcd' x 10k (README.md:57-71)."""
+    pma = D.DoubleArrayAhoCorasick.new(["bcd", "ab", "a"])
+    r = pma.find_overlapping_batch(["abcd"] * 10000)
+    assert len(r.matches) == 30000
+    m = r.matches.reshape(10000, 3)
+    assert (m["start"] == [0, 0, 1]).all() and (m["end"] == [1, 2, 4]).all() and (m["value"] == [2, 1, 0]).all()
+    assert np.array_equal(r.offsets, np.arange(10001, dtype=np.uint64) * 3)
+
+
+def test_charwise_zero_length_multibyte():
+    """src/charwise.rs:1373-1456."""
+    pats = ["a", "æ", "あ", ""]
+    hay = "いあabcÆæう"
+    pma = D.CharwiseDoubleArrayAhoCorasick.new(pats)
+    assert [(m.start(), m.end(), m.value()) for m in pma.find_overlapping_iter(hay)] == [
+        (0, 0, 3), (3, 3, 3), (3, 6, 2), (6, 6, 3), (6, 7, 0), (7, 7, 3), (8, 8, 3), (9, 9, 3),
+        (11, 11, 3), (11, 13, 1), (13, 13, 3), (16, 16, 3)]
+    assert [(m.start(), m.end(), m.value()) for m in pma.find_iter(hay)] == [
+        (0, 0, 3), (3, 3, 3), (6, 6, 3), (7, 7, 3), (8, 8, 3), (9, 9, 3), (11, 11, 3), (13, 13, 3), (16, 16, 3)]
+    pml = D.CharwiseDoubleArrayAhoCorasickBuilder.new().match_kind(D.MatchKind.LeftmostLongest).build(pats)
+    assert [(m.start(), m.end(), m.value()) for m in pml.leftmost_find_iter(hay)] == [
+        (0, 0, 3), (3, 6, 2), (6, 7, 0), (8, 8, 3), (9, 9, 3), (11, 13, 1), (16, 16, 3)]
+
+
+def test_no_suffix_iter():
+    """src/bytewise/iter.rs:484-509."""
+    for cls in (D.DoubleArrayAhoCorasick, D.CharwiseDoubleArrayAhoCorasick):
+        pma = cls.new(["a", "ab", ""])
+        assert [(m.end() - m.start(), m.end(), m.value()) for m in pma.find_overlapping_no_suffix_iter("ab")] == [
+            (0, 0, 2), (1, 1, 0), (2, 2, 1)]
+
+
+def test_empty_pattern_set_all_short_haystacks():
+    """test_empty_pattern_set, src/bytewise.rs:1418-1431."""
+    pma = D.DoubleArrayAhoCorasick.new([])
+    hays = [bytes([a]) for a in range(256)] + [bytes([a, b]) for a in range(256) for b in range(256)]
+    r = pma.find_overlapping_batch(hays)
+    assert len(r.matches) == 0 and int(r.offsets[-1]) == 0
+
+
+def test_empty_batch_and_empty_haystacks():
+    pma = D.DoubleArrayAhoCorasick.new(["a", ""])
+    r = pma.scan_batch_host(D.FIND_OVERLAPPING, np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert len(r.matches) == 0 and list(r.offsets) == [0]
+    r = pma.find_overlapping_batch(["", "", "a", ""])
+    assert [r.triples(i) for i in range(4)] == [[(0, 0, 1)], [(0, 0, 1)], [(0, 0, 1), (0, 1, 0), (1, 1, 1)], [(0, 0, 1)]]
+
+
+def _random_case(rng, cw, allow_empty):
+    alpha = int(rng.integers(2, 6))
+    pats = [bytes(rng.integers(97, 97 + alpha, size=int(rng.integers(0 if allow_empty else 1, 8))).tolist())
+            for _ in range(int(rng.integers(1, 300)))]
+    table = ["a", "b", "é", "あ", "𝄞", "c"]
+    if cw:
+        pats = ["".join(table[b - 97] for b in p) for p in pats]
+    n = int(rng.integers(1, 2000))
+    hays = []
+    for _ in range(n):
+        L = int(rng.integers(0, 200))
+        sym = rng.integers(0, alpha + 1, size=L)
+        hays.append("".join(table[int(i)] for i in sym).encode() if cw else bytes((97 + sym).astype(np.uint8).tolist()))
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(h) for h in hays])
+    return pats, np.frombuffer(b"".join(hays), dtype=np.uint8), offs
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("cw", [False, True])
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_random_batches(seed, cw, kind):
+    rng = np.random.default_rng(1000 + 100 * seed + 10 * kind + cw)
+    pats, text, offs = _random_case(rng, cw, allow_empty=(seed == 0))
+    pma = builder(cw).new().match_kind(kind).build(pats)
+    opma = O.OraclePma.build(pats, charwise=cw, match_kind=kind)
+    for mode in ([D.LEFTMOST_FIND] if kind else [D.FIND, D.FIND_OVERLAPPING, D.FIND_OVERLAPPING_NO_SUFFIX]):
+        check_batch(pma, opma, mode, text, offs)
+
+
+def test_kernel_options_do_not_change_results():
+    rng = np.random.default_rng(77)
+    pats, text, offs = _random_case(rng, False, False)
+    pma = D.DoubleArrayAhoCorasick.new(pats)
+    base = pma.scan_batch_host(D.FIND_OVERLAPPING, text, offs)
+    for opts in ({"hot_records": 0}, {"hot_records": 17}, {"threads": 128}, {"threads": 512, "ctas_per_sm": 2}):
+        for k, v in opts.items():
+            pma.set_option(k, v)
+        r = pma.scan_batch_host(D.FIND_OVERLAPPING, text, offs)
+        assert r.matches.tobytes() == base.matches.tobytes() and np.array_equal(r.offsets, base.offsets)
+        pma.set_option("hot_records", -1)
+        pma.set_option("threads", 1024)
+        pma.set_option("ctas_per_sm", 1)
+
+
+def test_overflow_protocol_through_the_c_abi():
+    import ctypes as C
+
+    from daachorse_b200 import _lib
+
+    pma = D.DoubleArrayAhoCorasick.new(["a", "aa"])
+    L = _lib.load()
+    d = pma.device_handle()
+    text = np.frombuffer(b"a" * 1000, dtype=np.uint8)
+    offs = np.array([0, 1000], dtype=np.uint64)
+    out = np.zeros(1999, dtype=D.MATCH_DTYPE)
+    oo = np.zeros(2, dtype=np.uint64)
+    need = C.c_uint64()
+    rc = L.dach_scan_batch_host(d, D.FIND_OVERLAPPING, text.ctypes.data, offs.ctypes.data, 1, out.ctypes.data, 10,
+                                oo.ctypes.data, C.byref(need))
+    assert rc == _lib.OUTPUT_OVERFLOW and need.value == 1999
+    rc = L.dach_scan_batch_host(d, D.FIND_OVERLAPPING, text.ctypes.data, offs.ctypes.data, 1, out.ctypes.data, 1999,
+                                oo.ctypes.data, C.byref(need))
+    assert rc == 0 and need.value == 1999 and list(oo) == [0, 1999]
+    rc = L.dach_scan_batch_host(d, D.LEFTMOST_FIND, text.ctypes.data, offs.ctypes.data, 1, out.ctypes.data, 1999,
+                                oo.ctypes.data, C.byref(need))
+    assert rc == _lib.MATCH_KIND_MISMATCH
+
+
+def test_device_resident_api_equals_host_api():
+    import torch
+
+    rng = np.random.default_rng(5)
+    pats, text, offs = _random_case(rng, False, False)
+    pma = D.DoubleArrayAhoCorasick.new(pats)
+    host = pma.scan_batch_host(D.FIND_OVERLAPPING, text, offs)
+    t = torch.from_numpy(text.copy()).cuda()
+    o = torch.from_numpy(offs.astype(np.int64)).cuda()
+    dev = pma.scan_batch_device(D.FIND_OVERLAPPING, t, o)
+    got = dev.matches.cpu().numpy().view(np.uint32).reshape(-1, 3)
+    want = np.stack([host.matches["start"], host.matches["end"], host.matches["value"]], axis=1)
+    assert np.array_equal(got, want)
+    assert np.array_equal(dev.offsets.cpu().numpy().astype(np.uint64), host.offsets)
+
+
+def _synth_case(name, n_patterns, n_hay, pool_bytes):
+    cfg = S.config(name)
+    ps = S.make_patterns(cfg, n_patterns)
+    pool, b = S.make_pool(cfg, ps, pool_bytes)
+    starts = S.window_starts(b, len(pool), n_hay, cfg["hay_len"])
+    text, offs = S.materialise_host(pool, starts, cfg["hay_len"])
+    return cfg, ps, text, offs
+
+
+def test_config_c2_full_compare():
+    """BASELINE.json configs[1]: 10k ASCII patterns, find_overlapping_iter, 256K x 256 B."""
+    cfg, ps, text, offs = _synth_case("C2", None, 262144, 32 << 20)
+    pats = ps.as_list()
+    pma = D.DoubleArrayAhoCorasick.new(pats)
+    opma = O.OraclePma.build_packed(ps.blob, ps.offs)
+    r = check_batch(pma, opma, D.FIND_OVERLAPPING, text, offs)
+    assert 0.01 < len(r.matches) / text.size < 0.5
+
+
+def test_config_c3_reduced_batch_all_standard_modes():
+    """BASELINE.json configs[2] automaton (675k patterns) on a 64 MiB slice of the batch, full
+    tuple compare in find_overlapping_iter and find_iter."""
+    cfg, ps, text, offs = _synth_case("C3", None, 16384, 32 << 20)
+    pma = D.DoubleArrayAhoCorasick.new(ps.as_list())
+    opma = O.OraclePma.build_packed(ps.blob, ps.offs)
+    assert pma.serialize() == opma.serialize()
+    check_batch(pma, opma, D.FIND_OVERLAPPING, text, offs)
+    check_batch(pma, opma, D.FIND, text, offs)
+    check_batch(pma, opma, D.FIND_OVERLAPPING_NO_SUFFIX, text[: 4096 * 2048], offs[:2049])
+
+
+def test_config_c4_reduced_charwise_leftmost_longest():
+    """BASELINE.json configs[3]: charwise 100k CJK patterns, leftmost_find_iter LeftmostLongest.
+    Haystacks are cut at char boundaries and padded with ASCII spaces."""
+    cfg = S.config("C4")
+    ps = S.make_patterns(cfg)
+    pool, b = S.make_pool(cfg, ps, 16 << 20)
+    hay_len, n = cfg["hay_len"], 16384
+    starts = S.window_starts(b, len(pool), n, hay_len)
+    text, offs = S.materialise_host(pool, starts, hay_len)
+    text = S.pad_to_char_boundary(text.reshape(n, hay_len)).reshape(-1)
+    text.tobytes().decode("utf-8")  # must be valid UTF-8 now
+    pma = D.CharwiseDoubleArrayAhoCorasickBuilder.new().match_kind(D.MatchKind.LeftmostLongest).build(
+        [p.decode() for p in ps.as_list()])
+    opma = O.OraclePma.build_packed(ps.blob, ps.offs, charwise=True, match_kind=1)
+    assert pma.serialize() == opma.serialize()
+    check_batch(pma, opma, D.LEFTMOST_FIND, text, offs)
+    # bytewise leftmost on the same data
+    pmb = D.DoubleArrayAhoCorasickBuilder.new().match_kind(D.MatchKind.LeftmostLongest).build(ps.as_list())
+    opmb = O.OraclePma.build_packed(ps.blob, ps.offs, match_kind=1)
+    check_batch(pmb, opmb, D.LEFTMOST_FIND, text, offs)
+
+
+def test_full_size_properties_c3():
+    """Size-independent properties at a larger batch (1 GiB of the C3 workload, device resident):
+    (1) find_iter output == greedy filter of the find_overlapping_iter output;
+    (2) per-haystack order-sensitive hashes of a 1 % sample == oracle;
+    (3) total == sum of the per-haystack ranges, offsets ascending."""
+    import torch
+
+    cfg = S.config("C3")
+    ps = S.make_patterns(cfg)
+    pool, b = S.make_pool(cfg, ps, 64 << 20)
+    n, hay_len = 262144, cfg["hay_len"]
+    starts = S.window_starts(b, len(pool), n, hay_len)
+    pool_t = torch.from_numpy(pool).cuda()
+    text_t, offs_t = S.materialise_on_device(pool_t, torch.from_numpy(starts).cuda(), hay_len)
+    pma = D.DoubleArrayAhoCorasick.new(ps.as_list())
+    ov = pma.scan_batch_device(D.FIND_OVERLAPPING, text_t, offs_t)
+    fi = pma.scan_batch_device(D.FIND, text_t, offs_t)
+    oo = ov.offsets.cpu().numpy()
+    assert oo[0] == 0 and (np.diff(oo) >= 0).all() and oo[-1] == ov.matches.shape[0]
+    # (2) oracle on a 1 % sample
+    opma = O.OraclePma.build_packed(ps.blob, ps.offs)
+    rng = np.random.default_rng(9)
+    sample = np.sort(rng.choice(n, size=n // 100, replace=False))
+    stext, soffs = S.materialise_host(pool, starts[sample], hay_len)
+    ref = opma.scan_batch(O.FIND_OVERLAPPING, stext, soffs, nthreads=8, want_matches=True)
+    om = ov.matches.cpu().numpy().view(np.uint32)
+    pos = 0
+    for k, h in enumerate(sample):
+        got = om[oo[h]:oo[h + 1]]
+        cnt = int(ref["counts"][k])
+        want = ref["matches"][pos:pos + cnt]
+        pos += cnt
+        assert got.shape[0] == cnt
+        assert np.array_equal(got, np.stack([want["start"], want["end"], want["value"]], axis=1))
+    # (1) greedy filter identity on the first 4096 haystacks
+    fo = fi.offsets.cpu().numpy()
+    fm = fi.matches.cpu().numpy().view(np.uint32)
+    for h in range(4096):
+        r = 0
+        exp = []
+        for s, e, v in om[oo[h]:oo[h + 1]]:
+            if s >= r:
+                exp.append((s, e, v))
+                r = e
+        assert [tuple(x) for x in fm[fo[h]:fo[h + 1]]] == exp
