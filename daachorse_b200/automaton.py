@@ -263,7 +263,9 @@ class _Automaton:
                                         C.c_void_p(out.ctypes.data), cap, C.c_void_p(out_offs.ctypes.data),
                                         C.byref(need))
             if rc == _lib.OUTPUT_OVERFLOW:
-                cap = max(int(need.value), cap * 2)
+                if int(need.value) <= cap:
+                    raise DaachorseError(rc, "overflow reported although capacity %d >= needed %d" % (cap, need.value))
+                cap = int(need.value)
                 continue
             _check(rc)
             return BatchResult(out[: need.value], out_offs)
@@ -291,7 +293,9 @@ class _Automaton:
                                        text.numel(), C.c_void_p(out.data_ptr()), out.shape[0],
                                        C.c_void_p(out_offs.data_ptr()), C.byref(need), st)
             if rc == _lib.OUTPUT_OVERFLOW:
-                cap = max(int(need.value), cap * 2)
+                if int(need.value) <= cap:
+                    raise DaachorseError(rc, "overflow reported although capacity %d >= needed %d" % (cap, need.value))
+                cap = int(need.value)
                 out = None
                 continue
             _check(rc)

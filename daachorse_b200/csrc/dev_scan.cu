@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_scan(ScanParams P) {
     TextWin T;
     Emitter E;
     for (;;) {
-        const unsigned long long item = atomicAdd(&P.ctrl->next_item, 1ull);
+        const unsigned long long item = bump_u64(&P.ctrl->next_item);
         if (item >= P.n_items) break;
         const uint64_t o0 = P.offs[item], o1 = P.offs[item + 1];
         const uint32_t len = (uint32_t)(o1 - o0);
@@ -365,7 +365,11 @@ int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, const uint64_t* d_
     const uint64_t total = d->pinned->total;
     if (needed) *needed = total;
     if (d->pinned->ctrl.overflow || total > out_cap) {
-        set_error("output capacity too small");
+        char buf[256];
+        snprintf(buf, sizeof(buf), "output capacity too small (needed %llu, out_cap %llu, pool blocks used %u of %u, overflow flag %u)",
+                 (unsigned long long)total, (unsigned long long)out_cap, d->pinned->ctrl.blk_cursor, pool_blocks,
+                 d->pinned->ctrl.overflow);
+        set_error(buf);
         return DACH_OUTPUT_OVERFLOW;
     }
     return DACH_OK;

@@ -33,6 +33,19 @@ struct uint4 {
 #endif
 #endif
 
+#if defined(DACH_WATCHDOG) && defined(__CUDA_ARCH__)
+#include <cstdio>
+#define DACH_WD_DECL(name) unsigned long long name = 0
+#define DACH_WD_TICK(name, limit, ...)                 \
+    if (++name > (limit)) {                            \
+        printf(__VA_ARGS__);                           \
+        return;                                        \
+    }
+#else
+#define DACH_WD_DECL(name)
+#define DACH_WD_TICK(name, limit, ...)
+#endif
+
 namespace dach {
 
 constexpr uint32_t D_ROOT = 0;
@@ -87,6 +100,29 @@ DACH_HD uint32_t ld_u32(const uint32_t* p) {
     return __ldg(p);
 #else
     return *p;
+#endif
+}
+
+// Per-lane atomic increments, written as inline PTX on the device: lanes of one warp reach
+// these at unrelated times (each lane walks its own haystack), and the explicit instruction keeps
+// the compiler from fusing them into a vote + leader-atomic + shuffle sequence that needs the
+// warp to be converged at that point.
+DACH_HD uint32_t bump_u32(unsigned int* p) {
+#if defined(__CUDA_ARCH__)
+    unsigned int old;
+    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p) : "memory");
+    return old;
+#else
+    return (*p)++;
+#endif
+}
+DACH_HD unsigned long long bump_u64(unsigned long long* p) {
+#if defined(__CUDA_ARCH__)
+    unsigned long long old;
+    asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(old) : "l"(p) : "memory");
+    return old;
+#else
+    return (*p)++;
 #endif
 }
 
@@ -153,11 +189,7 @@ struct Emitter {
     }
     DACH_HD void emit(const ScanParams& P, uint32_t start, uint32_t end, uint32_t value) {
         if (fill == 0) {
-#if defined(__CUDA_ARCH__)
-            const uint32_t b = atomicAdd(&P.ctrl->blk_cursor, 1u);
-#else
-            const uint32_t b = P.ctrl->blk_cursor++;
-#endif
+            const uint32_t b = bump_u32(&P.ctrl->blk_cursor);
             if (b < P.pool_blocks) {
                 blk = P.pool + (size_t)b * BLK_WORDS;
                 blk[0] = item;
@@ -375,13 +407,19 @@ DACH_HD void scan_leftmost(const ScanParams& P, const RecView& V, TextWin& T, Em
     bool skip_empty = false;
     uint4 root_rec = {0, 0, 0, 0};
     if (CHARWISE) root_rec = V.get(D_ROOT);
+    DACH_WD_DECL(wd_outer);
+    DACH_WD_DECL(wd_inner);
     for (;;) {
         uint32_t s = D_ROOT;
         uint4 r = root_rec;
         uint32_t last = init_opos;
         bool yielded = false;
         uint32_t i = self_pos;
+        DACH_WD_TICK(wd_outer, 1000000ull, "WD outer item=%u len=%u self_pos=%u init=%u skip=%d count=%u\n", E.item, len,
+                     self_pos, init_opos, (int)skip_empty, E.count)
         while (i < len) {
+            DACH_WD_TICK(wd_inner, 100000000ull, "WD inner item=%u len=%u i=%u self_pos=%u s=%u last=%u init=%u\n", E.item,
+                         len, i, self_pos, s, last, init_opos)
             const uint32_t unit_start = i;
             if (CHARWISE) {
                 const uint32_t cp = utf8_at(T, i);
