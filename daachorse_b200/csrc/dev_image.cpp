@@ -43,6 +43,10 @@ int build_image(const dach_pma* p, HostImage* img) {
     for (const OutputRec& o : p->outputs)
         if (o.length > img->max_pattern_len) img->max_pattern_len = o.length;
 
+    if (n >= 0x80000000ull) {
+        set_error("automaton too large for the device image (2^31 slots)");
+        return DACH_AUTOMATON_SCALE;
+    }
     if (!fail_chains_terminate(p, p->charwise || lm)) {
         set_error("invalid automaton: a failure chain never reaches the root");
         return DACH_INVALID_AUTOMATON;
@@ -50,14 +54,19 @@ int build_image(const dach_pma* p, HostImage* img) {
 
     img->rec.resize(n * 4);
     if (!p->charwise) {
-        for (size_t s = 0; s < n; ++s) {
-            // failure target with child-less states skipped
-            uint32_t f = p->fail[s];
+        auto skip_leaves = [&](uint32_t f) {  // failure target with child-less states skipped
             while (f != kRoot && !(lm && f == kDead) && p->base[f] == 0) f = p->fail[f];
+            return f;
+        };
+        for (size_t s = 0; s < n; ++s) {
+            const uint32_t f = skip_leaves(p->fail[s]);
+            const bool terminal = f == kRoot || (lm && f == kDead);
             uint32_t* r = &img->rec[s * 4];
             r[0] = p->base[s];
             r[1] = f;
-            r[2] = (f == kRoot || (lm && f == kDead)) ? 0 : p->base[f];
+            r[2] = terminal ? 0 : p->base[f];
+            // bit 31: the failure state's own (leaf-skipped) failure target is ROOT
+            if (!terminal && !lm && skip_leaves(p->fail[f]) == kRoot) r[2] |= 0x80000000u;
             r[3] = p->opos_ch[s];
         }
         // dense ROOT row; also valid for the leftmost automaton, whose ROOT transition is
@@ -70,6 +79,17 @@ int build_image(const dach_pma* p, HostImage* img) {
                 if (ci < n && (p->opos_ch[ci] & 0xff) == c) img->root_table[c] = ci;
             }
         }
+        // dense root row with the child's whole record inlined; "no child" is an entry whose CHECK
+        // byte differs from the label
+        img->root4.assign(1024, 0);
+        for (uint32_t c = 0; c < 256; ++c) {
+            const uint32_t ci = img->root_table[c];
+            if (ci == kRoot) {
+                img->root4[c * 4 + 3] = (c ^ 1u) & 0xffu;
+                continue;
+            }
+            for (int k = 0; k < 4; ++k) img->root4[c * 4 + k] = img->rec[size_t(ci) * 4 + k];
+        }
     } else {
         for (size_t s = 0; s < n; ++s) {
             uint32_t* r = &img->rec[s * 4];
@@ -79,6 +99,7 @@ int build_image(const dach_pma* p, HostImage* img) {
             r[3] = p->output_pos[s];
         }
         img->root_table.assign(256, kRoot);  // unused by the charwise kernels
+        img->root4.assign(1024, 0);
         img->mapper = p->mapper_table;
     }
     img->outputs.resize(p->outputs.size() * 4);

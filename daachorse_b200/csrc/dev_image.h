@@ -17,6 +17,7 @@ struct HostImage {
     std::vector<uint32_t> rec;         // 4 words per slot
     std::vector<uint32_t> outputs;     // 4 words per output
     std::vector<uint32_t> root_table;  // 256 words (bytewise)
+    std::vector<uint32_t> root4;       // 256 x record of ROOT's child for that byte (bytewise)
     std::vector<uint32_t> mapper;      // charwise code table
 };
 

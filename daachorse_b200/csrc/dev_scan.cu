@@ -58,6 +58,66 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_scan(ScanParams P) {
     }
 }
 
+// ---- v1: warp-synchronous lane machine for the bytewise Standard modes ---------------------------
+// One warp = 32 independent haystack walkers kept in lock step: every iteration each lane does at
+// most one record fetch (shared memory for the hot prefix, L1/L2 otherwise).  When any lane's
+// event queue is full or its haystack is finished, the whole warp runs the service phase: drain
+// all queues (output-list walks, match stores), close finished items, pull new items with one
+// warp-aggregated atomic.
+constexpr uint32_t kRoot4Bytes = 4096;  // 256 x uint4 at the front of dynamic shared memory
+
+template <int MODE>
+__global__ void __launch_bounds__(kMaxThreads, 1) k_scan_std(ScanParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* s_root4 = reinterpret_cast<uint4*>(smem_raw);
+    uint4* s_hot = reinterpret_cast<uint4*>(smem_raw + kRoot4Bytes);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_root4[i] = P.root4[i];
+    for (uint32_t i = threadIdx.x; i < P.hot_n; i += blockDim.x) s_hot[i] = P.rec[i];
+    __syncthreads();
+
+    using M = StdMachine<MODE>;
+    const StdEnv Ev{P.rec, s_hot, P.hot_n, s_root4, P.text_end, P.root_opos};
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    LaneStd L;
+    L.active = false;
+    L.done = false;
+    L.qn = 0;
+    L.kind = K_NONE;
+    Emitter E;
+    E.begin(0);
+    bool exhausted = false;
+    for (;;) {
+        // ---- service phase (the warp is converged here) ----
+        if (L.active) M::drain(L, P, E);
+        if (L.active && L.done) {
+            E.finish(P);
+            L.active = false;
+        }
+        const bool need = !L.active && !exhausted;
+        const unsigned m = __ballot_sync(FULL, need);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(&P.ctrl->next_item, (unsigned long long)__popc(m));
+            base = __shfl_sync(FULL, base, leader);
+            if (need) {
+                const unsigned long long item = base + __popc(m & ((1u << lane) - 1u));
+                if (item < P.n_items)
+                    M::begin_item(L, P, Ev, E, item, nullptr);
+                else
+                    exhausted = true;
+            }
+        }
+        if (!__any_sync(FULL, L.active)) break;
+        // ---- lock-step iterations until some lane needs service ----
+        for (;;) {
+            const bool ok = M::step(L, Ev, nullptr);
+            if (__any_sync(FULL, !ok && L.active)) break;
+        }
+    }
+}
+
 // ---- exclusive scan of counts (u32) into offsets (u64) -----------------------------------
 constexpr int kScanThreads = 256;
 constexpr int kScanPerThread = 8;
@@ -221,6 +281,7 @@ struct dach_dev {
     uint4* d_rec = nullptr;
     uint4* d_outputs = nullptr;
     uint32_t* d_root = nullptr;
+    uint4* d_root4 = nullptr;
     uint32_t* d_mapper = nullptr;
     // workspace (guarded by mu)
     std::mutex mu;
@@ -232,6 +293,7 @@ struct dach_dev {
     int64_t opt_hot_records = -1;  // -1: as many as fit
     int64_t opt_threads = 1024;
     int64_t opt_ctas_per_sm = 1;
+    int64_t opt_kernel = 1;  // 1: warp-synchronous lane machine where it applies; 0: always the v0 kernels
     // stats
     uint64_t launches = 0;
     double last_scan_ms = 0, last_total_ms = 0;
@@ -264,6 +326,27 @@ cudaError_t launch_scan_t(const ScanParams& P, int grid, int threads, size_t sme
     return cudaGetLastError();
 }
 
+template <int MODE>
+cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_scan_std<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    k_scan_std<MODE><<<grid, threads, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_std(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
+    switch (mode) {
+        case M_FIND: return launch_std_t<M_FIND>(P, grid, threads, smem, st);
+        case M_OVERLAPPING: return launch_std_t<M_OVERLAPPING>(P, grid, threads, smem, st);
+        case M_NO_SUFFIX: return launch_std_t<M_NO_SUFFIX>(P, grid, threads, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_scan(bool cw, int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
     switch ((cw ? 4 : 0) + mode) {
         case 0: return launch_scan_t<false, M_FIND>(P, grid, threads, smem, st);
@@ -292,7 +375,7 @@ int check_mode(const dach_dev* d, int mode) {
 }
 
 // the device-side pipeline; caller holds d->mu and has set the device
-int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, const uint64_t* d_offs, uint64_t n,
+int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, uint64_t text_bytes, const uint64_t* d_offs, uint64_t n,
                 dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs, uint64_t* needed, cudaStream_t st) {
     if (n > 0xfffffff0ull) {
         set_error("too many haystacks in one batch (max 2^32-16)");
@@ -318,11 +401,13 @@ int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, const uint64_t* d_
     P.rec = d->d_rec;
     P.outputs = d->d_outputs;
     P.root_table = d->d_root;
+    P.root4 = d->d_root4;
     P.mapper = d->d_mapper;
     P.mapper_len = d->mapper_len;
     P.n_slots = d->n_slots;
     P.root_opos = d->root_opos;
     P.text = d_text;
+    P.text_end = d_text + text_bytes;
     P.offs = d_offs;
     P.n_items = n;
     P.counts = static_cast<uint32_t*>(d->counts.p);
@@ -334,16 +419,22 @@ int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, const uint64_t* d_
     threads = (threads / 32) * 32;
     int ctas_per_sm = (int)std::min<int64_t>(std::max<int64_t>(d->opt_ctas_per_sm, 1), 2048 / threads);
     const size_t smem_budget = std::min<size_t>(d->smem_optin, 227 * 1024) / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
-    uint64_t hot = smem_budget > kRootBytes ? (smem_budget - kRootBytes) / 16 : 0;
+    // the lane machine serves the bytewise Standard iterators; find_iter with an empty pattern
+    // (it only reports zero-length matches, src/bytewise/iter.rs:60-85) keeps the simple kernel
+    const bool v1 = d->opt_kernel >= 1 && !d->charwise && mode != M_LEFTMOST && !(mode == M_FIND && d->root_opos != 0);
+    const size_t front = v1 ? kRoot4Bytes : kRootBytes;
+    uint64_t hot = smem_budget > front ? (smem_budget - front) / 16 : 0;
     if (d->opt_hot_records >= 0) hot = std::min<uint64_t>(hot, (uint64_t)d->opt_hot_records);
     hot = std::min<uint64_t>(hot, d->n_slots);
     P.hot_n = (uint32_t)hot;
-    const size_t smem = kRootBytes + (size_t)hot * 16;
+    const size_t smem = front + (size_t)hot * 16;
     const int grid = d->sm_count * ctas_per_sm;
 
     if (!cuda_ok(cudaMemsetAsync(d->ctrl.p, 0, sizeof(ScanCtrl), st), "memset ctrl")) return DACH_CUDA_ERROR;
     cudaEventRecord(d->ev[0], st);
-    if (!cuda_ok(launch_scan(d->charwise, mode, P, grid, threads, smem, st), "k_scan launch")) return DACH_CUDA_ERROR;
+    if (!cuda_ok(v1 ? launch_std(mode, P, grid, threads, smem, st) : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
+                 "k_scan launch"))
+        return DACH_CUDA_ERROR;
     cudaEventRecord(d->ev[1], st);
     unsigned long long* offs64 = reinterpret_cast<unsigned long long*>(d_out_offs);
     unsigned long long* tiles = static_cast<unsigned long long*>(d->tiles.p);
@@ -418,7 +509,8 @@ int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
         return true;
     };
     bool ok = up(img.rec, reinterpret_cast<void**>(&d->d_rec)) && up(img.outputs, reinterpret_cast<void**>(&d->d_outputs)) &&
-              up(img.root_table, reinterpret_cast<void**>(&d->d_root)) && up(img.mapper, reinterpret_cast<void**>(&d->d_mapper));
+              up(img.root_table, reinterpret_cast<void**>(&d->d_root)) && up(img.root4, reinterpret_cast<void**>(&d->d_root4)) &&
+              up(img.mapper, reinterpret_cast<void**>(&d->d_mapper));
     ok = ok && cuda_ok(cudaMallocHost(reinterpret_cast<void**>(&d->pinned), sizeof(HostPinned)), "cudaMallocHost");
     for (int i = 0; ok && i < 4; ++i) ok = cuda_ok(cudaEventCreate(&d->ev[i]), "cudaEventCreate");
     if (!ok) {
@@ -435,6 +527,7 @@ void dach_dev_free(dach_dev* d) {
     cudaFree(d->d_rec);
     cudaFree(d->d_outputs);
     cudaFree(d->d_root);
+    cudaFree(d->d_root4);
     cudaFree(d->d_mapper);
     for (DevBuf* b : {&d->counts, &d->tiles, &d->ctrl, &d->pool, &d->h_text, &d->h_offs, &d->h_out, &d->h_out_offs})
         if (b->p) cudaFree(b->p);
@@ -449,7 +542,6 @@ size_t dach_dev_image_bytes(const dach_dev* d) { return d ? d->image_bytes : 0; 
 int dach_dev_scan_batch(dach_dev* d, int mode, const uint8_t* d_text, const uint64_t* d_offs, uint64_t n,
                         uint64_t text_bytes, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs,
                         uint64_t* needed, void* stream) {
-    (void)text_bytes;
     if (!d || !d_offs || !d_out_offs || (out_cap && !d_out)) {
         set_error("null argument");
         return DACH_INVALID_ARGUMENT;
@@ -459,7 +551,7 @@ int dach_dev_scan_batch(dach_dev* d, int mode, const uint8_t* d_text, const uint
     std::lock_guard<std::mutex> lk(d->mu);
     DeviceGuard g(d->device);
     if (!g.ok) return DACH_CUDA_ERROR;
-    return scan_locked(d, mode, d_text, d_offs, n, d_out, out_cap, d_out_offs, needed, static_cast<cudaStream_t>(stream));
+    return scan_locked(d, mode, d_text, text_bytes, d_offs, n, d_out, out_cap, d_out_offs, needed, static_cast<cudaStream_t>(stream));
 }
 
 int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint64_t* offs, uint64_t n,
@@ -487,7 +579,7 @@ int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint6
         return DACH_CUDA_ERROR;
     const uint8_t* d_text = static_cast<const uint8_t*>(d->h_text.p) - offs[0];
     uint64_t total = 0;
-    rc = scan_locked(d, mode, d_text, static_cast<const uint64_t*>(d->h_offs.p), n,
+    rc = scan_locked(d, mode, d_text, offs[0] + text_bytes, static_cast<const uint64_t*>(d->h_offs.p), n,
                      static_cast<dach_match*>(d->h_out.p), out_cap, static_cast<uint64_t*>(d->h_out_offs.p), &total, st);
     if (needed) *needed = total;
     d->last_h2d = text_bytes + (n + 1) * 8;
@@ -518,6 +610,8 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
         d->opt_threads = value;
     else if (k == "ctas_per_sm")
         d->opt_ctas_per_sm = value;
+    else if (k == "kernel")
+        d->opt_kernel = value;
     else {
         set_error("unknown option " + k);
         return DACH_INVALID_ARGUMENT;

@@ -13,7 +13,8 @@
 //               dense root table, kDead (leftmost only) ends it at ROOT without a probe
 //               (src/bytewise.rs:1120-1123)
 //       fbase   BASE of efail, so a missed probe is followed by the next probe without first
-//               loading the failure state's record
+//               loading the failure state's record; bit 31 (F2ROOT_BIT) says efail(efail) == ROOT,
+//               so a second miss goes straight to the dense root row (slots are < 2^31)
 //   charwise record  uint4 {base, check(parent), fail, output_pos}         src/charwise.rs:1096-1101
 //   output           uint4 {value, length, parent, 0}                      src/lib.rs:213-218
 //   root table       256 x u32                                             src/bytewise.rs:1040-1056
@@ -72,6 +73,7 @@ struct ScanParams {
     const uint4* rec;
     const uint4* outputs;
     const uint32_t* root_table;  // global copy (kernels stage it in shared memory)
+    const uint4* root4;          // dense root row with the child records inlined (v1 kernels)
     const uint32_t* mapper;
     uint32_t mapper_len;
     uint32_t n_slots;
@@ -79,6 +81,7 @@ struct ScanParams {
     uint32_t hot_n;      // leading records staged in shared memory
     // batch
     const uint8_t* text;
+    const uint8_t* text_end;  // text + total bytes: no 16-byte block starting at or past it is read
     const uint64_t* offs;
     uint64_t n_items;
     // results
@@ -248,7 +251,7 @@ DACH_HD uint32_t bw_step(const RecView& V, uint32_t s, uint4& r, uint32_t c) {
                 return ci;
             }
         }
-        uint32_t f = r.y, fb = r.z;
+        uint32_t f = r.y, fb = r.z & 0x7fffffffu;  // bit 31 of word z is a flag (F2ROOT_BIT)
         while (f != D_ROOT) {  // failure chase; every visited state has children
             const uint32_t ci = fb ^ c;
             const uint4 x = V.get(ci);
@@ -258,7 +261,7 @@ DACH_HD uint32_t bw_step(const RecView& V, uint32_t s, uint4& r, uint32_t c) {
             }
             const uint4 fr = V.get(f);
             f = fr.y;
-            fb = fr.z;
+            fb = fr.z & 0x7fffffffu;
         }
     }
     const uint32_t n = V.root[c];
@@ -278,7 +281,7 @@ DACH_HD uint32_t bw_step_leftmost(const RecView& V, uint32_t s, uint4& r, uint32
                 return ci;
             }
         }
-        uint32_t f = r.y, fb = r.z;
+        uint32_t f = r.y, fb = r.z & 0x7fffffffu;
         while (f != D_ROOT) {
             if (f == D_DEAD) return D_ROOT;
             const uint32_t ci = fb ^ c;
@@ -289,7 +292,7 @@ DACH_HD uint32_t bw_step_leftmost(const RecView& V, uint32_t s, uint4& r, uint32
             }
             const uint4 fr = V.get(f);
             f = fr.y;
-            fb = fr.z;
+            fb = fr.z & 0x7fffffffu;
         }
     }
     const uint32_t n = V.root[c];
@@ -484,5 +487,241 @@ DACH_HD void scan_leftmost(const ScanParams& P, const RecView& V, TextWin& T, Em
         return;
     }
 }
+
+
+// =============================================================================================
+// v1 lane machine for the bytewise Standard modes (find_overlapping / no_suffix / find without an
+// empty pattern).
+//
+// The per-byte loop of src/bytewise.rs:1063-1088 is re-cut so that every lane of a warp does the
+// same thing in every iteration: at most ONE 16-byte record fetch, then a short decision.  Lanes
+// walk unrelated haystacks, so a loop shaped like the reference's ("for each byte: while miss:
+// follow fail") leaves ~4 of 32 lanes active per issued instruction (profiles/r1_v0_summary.md);
+// here a lane that misses simply spends its next iteration on the next probe of the same byte.
+//
+//   kind = K_NONE        the lane sits in a state and needs the next byte
+//          K_PROBE       fetch rec[addr], addr = base ^ c; CHECK decides hit / miss
+//          K_LEARN       fetch rec[pend] to learn (efail, fbase) of a failure state whose probe missed
+//
+// Matches are not expanded in the loop: a lane that lands on a state with an output list only
+// queues (end, output_pos).  The warp drains all queues together (service phase), so the output
+// walk -- a divergent pointer chase -- runs with many lanes at once instead of one.
+// =============================================================================================
+
+constexpr uint32_t K_NONE = 0, K_PROBE = 1, K_LEARN = 3;
+constexpr int LANE_Q = 4;                    // queued output events per lane
+constexpr uint32_t F2ROOT_BIT = 0x80000000u;  // in record word 2: efail(efail(s)) == ROOT
+
+// Dense root row (shared memory): entry c is the whole record of ROOT's child for byte c, so
+// landing on it needs no fetch; an entry whose CHECK byte differs from c means "stay in ROOT".
+struct LaneStd {
+    // item
+    const uint8_t* hay;
+    uint32_t len, pos, item;
+    bool active, done;
+    // text: current and prefetched 16-byte windows
+    uint64_t blk;  // (address >> 4) of `cw`
+    uint4 cw, nw;
+    // automaton
+    uint32_t c;              // byte being matched
+    uint32_t cb;             // BASE to probe with (0: the state has no children)
+    uint32_t nf, nfb;        // where to fall on a miss, and its BASE | F2ROOT_BIT (valid if know)
+    uint32_t pend;           // failure state whose BASE is being probed (know == false)
+    bool know, pend_f2root;
+    uint32_t kind, addr;
+    // queued outputs
+    uint32_t qn;
+    uint32_t qe[LANE_Q], qo[LANE_Q];
+};
+
+struct StdEnv {
+    const uint4* glob;   // records in global memory
+    const uint4* hot;    // leading records in shared memory
+    uint32_t hot_n;
+    const uint4* root4;  // dense root row (shared memory)
+    const uint8_t* text_end;
+    uint32_t root_opos;
+};
+
+DACH_HD uint4 ld_text16(const uint8_t* q, const uint8_t* text_end, const uint8_t* emu_lo) {
+    uint4 w;
+    w.x = w.y = w.z = w.w = 0;
+    (void)emu_lo;
+    if (q >= text_end) return w;  // never touch a block that starts past the text
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                 : "l"(q));
+#elif defined(DACH_EMU)
+    uint32_t v[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 16; ++i) {
+        const uint8_t* qi = q + i;
+        uint32_t b = (qi >= emu_lo && qi < text_end) ? *qi : 0;
+        v[i >> 2] |= b << ((i & 3) * 8);
+    }
+    w.x = v[0], w.y = v[1], w.z = v[2], w.w = v[3];
+#endif
+    return w;
+}
+
+template <int MODE>
+struct StdMachine {
+    // ---- text ---------------------------------------------------------------------------------
+    static DACH_HD void text_open(LaneStd& L, const StdEnv& Ev, const uint8_t* emu_lo) {
+        const uint64_t a = (uint64_t)(uintptr_t)L.hay;
+        L.blk = a >> 4;
+        const uint8_t* q = reinterpret_cast<const uint8_t*>((uintptr_t)(L.blk << 4));
+        L.cw = ld_text16(q, Ev.text_end, emu_lo);
+        L.nw = ld_text16(q + 16, Ev.text_end, emu_lo);
+    }
+    static DACH_HD uint32_t text_byte(LaneStd& L, const StdEnv& Ev, const uint8_t* emu_lo) {
+        const uint64_t a = (uint64_t)(uintptr_t)L.hay + L.pos;
+        if ((a >> 4) != L.blk) {  // sequential reader: this is always the next block
+            L.blk = a >> 4;
+            L.cw = L.nw;
+            const uint8_t* q = reinterpret_cast<const uint8_t*>((uintptr_t)((L.blk + 1) << 4));
+            L.nw = ld_text16(q, Ev.text_end, emu_lo);
+        }
+        const uint32_t o = (uint32_t)a & 15u;
+        const uint32_t lo = (o & 8u) ? L.cw.z : L.cw.x;
+        const uint32_t hi = (o & 8u) ? L.cw.w : L.cw.y;
+        const uint32_t word = (o & 4u) ? hi : lo;
+        return (word >> ((o & 3u) * 8u)) & 0xffu;
+    }
+
+    // ---- queue ----------------------------------------------------------------------------------
+    static DACH_HD void push(LaneStd& L, uint32_t end, uint32_t opos) {
+        // LANE_Q == 4, unrolled so that the queue stays in registers
+        if (L.qn == 0) { L.qe[0] = end; L.qo[0] = opos; }
+        else if (L.qn == 1) { L.qe[1] = end; L.qo[1] = opos; }
+        else if (L.qn == 2) { L.qe[2] = end; L.qo[2] = opos; }
+        else { L.qe[3] = end; L.qo[3] = opos; }
+        ++L.qn;
+    }
+
+    // ---- landing ----------------------------------------------------------------------------------
+    // The lane has arrived in a non-root state whose record fields are given; the byte was consumed.
+    static DACH_HD void land(LaneStd& L, uint32_t base, uint32_t efail, uint32_t fbase, uint32_t opos) {
+        L.cb = base;
+        L.nf = efail;
+        L.nfb = fbase;
+        L.know = true;
+        L.kind = K_NONE;
+        if (opos != 0) {
+            push(L, L.pos, opos);
+            if (MODE == M_FIND) {  // every next() restarts at ROOT (src/bytewise/iter.rs:87)
+                L.cb = 0;
+                L.nf = D_ROOT;
+            }
+        }
+    }
+    static DACH_HD void land_root(LaneStd& L, const StdEnv& Ev) {
+        L.cb = 0;
+        L.nf = D_ROOT;
+        L.nfb = 0;
+        L.know = true;
+        L.kind = K_NONE;
+        if (MODE != M_FIND && Ev.root_opos != 0) push(L, L.pos, Ev.root_opos);
+    }
+
+    // A probe missed (or the state has no children) and (nf, nfb) are known: take the failure link.
+    static DACH_HD void fall(LaneStd& L, const StdEnv& Ev) {
+        if (L.nf == D_ROOT) {
+            const uint4 t = Ev.root4[L.c];  // dense ROOT row (src/bytewise.rs:1067-1069)
+            ++L.pos;                        // the byte is consumed
+            if ((t.w & 0xffu) != L.c)
+                land_root(L, Ev);
+            else
+                land(L, t.x, t.y, t.z, t.w >> 8);
+        } else {
+            L.cb = L.nfb & ~F2ROOT_BIT;
+            L.pend = L.nf;
+            L.pend_f2root = (L.nfb & F2ROOT_BIT) != 0;
+            L.know = false;
+            L.kind = K_PROBE;
+            L.addr = L.cb ^ L.c;
+        }
+    }
+
+    // ---- one iteration ----------------------------------------------------------------------------
+    // Returns true if the lane can keep stepping, false if it needs the service phase
+    // (queue full or item finished).
+    static DACH_HD bool step(LaneStd& L, const StdEnv& Ev, const uint8_t* emu_lo) {
+        if (!L.active || L.done) return false;
+        if (L.qn == LANE_Q) return false;  // a landing pushes at most one event; it happens only in K_NONE
+        if (L.kind == K_NONE) {
+            if (L.pos >= L.len) {
+                L.done = true;
+                return false;
+            }
+            L.c = text_byte(L, Ev, emu_lo);
+            if (L.cb != 0) {
+                L.kind = K_PROBE;
+                L.addr = L.cb ^ L.c;
+            } else {
+                fall(L, Ev);
+            }
+        }
+        if (L.kind != K_NONE) {
+            const uint32_t a = L.addr;
+            const uint4 x = a < Ev.hot_n ? Ev.hot[a] : ld_u4(Ev.glob + a);
+            if (L.kind == K_PROBE) {
+                if ((x.w & 0xffu) == L.c) {
+                    ++L.pos;
+                    land(L, x.x, x.y, x.z, x.w >> 8);
+                } else if (L.know) {
+                    fall(L, Ev);
+                } else if (L.pend_f2root) {
+                    L.nf = D_ROOT;
+                    L.know = true;
+                    fall(L, Ev);
+                } else {
+                    L.kind = K_LEARN;
+                    L.addr = L.pend;
+                }
+            } else {  // K_LEARN
+                L.nf = x.y;
+                L.nfb = x.z;
+                L.know = true;
+                fall(L, Ev);
+            }
+        }
+        return true;
+    }
+
+    // ---- service pieces ---------------------------------------------------------------------------
+    static DACH_HD void drain(LaneStd& L, const ScanParams& P, Emitter& E) {
+#define DACH_DRAIN_ONE(J)                                     \
+    if (L.qn > (J)) {                                         \
+        if (MODE == M_OVERLAPPING)                            \
+            emit_chain(P, E, L.qo[J], L.qe[J]);               \
+        else                                                  \
+            emit_head(P, E, L.qo[J], L.qe[J]);                \
+    }
+        DACH_DRAIN_ONE(0)
+        DACH_DRAIN_ONE(1)
+        DACH_DRAIN_ONE(2)
+        DACH_DRAIN_ONE(3)
+#undef DACH_DRAIN_ONE
+        L.qn = 0;
+    }
+
+    static DACH_HD void begin_item(LaneStd& L, const ScanParams& P, const StdEnv& Ev, Emitter& E, uint64_t item,
+                                   const uint8_t* emu_lo) {
+        const uint64_t o0 = P.offs[item], o1 = P.offs[item + 1];
+        L.hay = P.text + o0;
+        L.len = (uint32_t)(o1 - o0);
+        L.pos = 0;
+        L.item = (uint32_t)item;
+        L.active = true;
+        L.done = false;
+        L.qn = 0;
+        E.begin((uint32_t)item);
+        text_open(L, Ev, emu_lo);
+        // the iterator starts in ROOT with ROOT's output list pending at position 0
+        // (src/bytewise.rs:303-313; no-suffix variant: src/bytewise/iter.rs:196-216)
+        land_root(L, Ev);
+    }
+};
 
 }  // namespace dach

@@ -32,9 +32,79 @@ static void run_items(const ScanParams& P, const RecView& V, const uint8_t* lo, 
     }
 }
 
+// Warp-level driver of the v1 lane machine, mirroring k_scan_std in dev_scan.cu with the warp
+// collectives (ballot / any / shuffle) written out as loops over 32 lane states.
+template <int MODE>
+static void run_items_v1(const ScanParams& P, const StdEnv& Ev, const uint8_t* lo, int n_warps) {
+    using M = StdMachine<MODE>;
+    struct Warp {
+        LaneStd L[32];
+        Emitter E[32];
+        bool exhausted[32];
+        bool finished;
+    };
+    std::vector<Warp> warps(n_warps);
+    for (auto& w : warps) {
+        for (int l = 0; l < 32; ++l) {
+            w.L[l].active = false;
+            w.L[l].done = false;
+            w.L[l].qn = 0;
+            w.L[l].kind = K_NONE;
+            w.E[l].begin(0);
+            w.exhausted[l] = false;
+        }
+        w.finished = false;
+    }
+    // round-robin over warps, one "service + run" turn each, to interleave allocation order
+    bool any_left = true;
+    while (any_left) {
+        any_left = false;
+        for (auto& w : warps) {
+            if (w.finished) continue;
+            for (int l = 0; l < 32; ++l)
+                if (w.L[l].active) M::drain(w.L[l], P, w.E[l]);
+            for (int l = 0; l < 32; ++l)
+                if (w.L[l].active && w.L[l].done) {
+                    w.E[l].finish(P);
+                    w.L[l].active = false;
+                }
+            unsigned m = 0;
+            for (int l = 0; l < 32; ++l)
+                if (!w.L[l].active && !w.exhausted[l]) m |= 1u << l;
+            if (m) {
+                unsigned long long base = P.ctrl->next_item;
+                P.ctrl->next_item += __builtin_popcount(m);
+                for (int l = 0; l < 32; ++l)
+                    if (m & (1u << l)) {
+                        const unsigned long long item = base + __builtin_popcount(m & ((1u << l) - 1u));
+                        if (item < P.n_items)
+                            M::begin_item(w.L[l], P, Ev, w.E[l], item, lo);
+                        else
+                            w.exhausted[l] = true;
+                    }
+            }
+            bool any_active = false;
+            for (int l = 0; l < 32; ++l) any_active |= w.L[l].active;
+            if (!any_active) {
+                w.finished = true;
+                continue;
+            }
+            any_left = true;
+            for (;;) {
+                bool need_service = false;
+                for (int l = 0; l < 32; ++l) {
+                    const bool ok = M::step(w.L[l], Ev, lo);
+                    if (!ok && w.L[l].active) need_service = true;
+                }
+                if (need_service) break;
+            }
+        }
+    }
+}
+
 extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int charwise, int mode,
                                    const uint8_t* text, const uint64_t* offs, uint64_t n, uint32_t hot_n,
-                                   uint32_t pool_blocks, dach_match* out, uint64_t out_cap, uint64_t* out_offs,
+                                   int kernel_version, uint32_t pool_blocks, dach_match* out, uint64_t out_cap, uint64_t* out_offs,
                                    uint64_t* needed) {
     dach_pma* pma = nullptr;
     size_t used = 0;
@@ -63,7 +133,9 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     if (hot_n > img.n_slots) hot_n = img.n_slots;
     P.hot_n = hot_n;
     P.text = text;
+    P.text_end = text + (n ? offs[n] : 0);
     P.offs = offs;
+    P.root4 = reinterpret_cast<const uint4*>(img.root4.data());
     P.n_items = n;
     P.counts = counts.data();
     P.pool = pool.data();
@@ -75,6 +147,14 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     RecView V{P.rec, reinterpret_cast<const uint4*>(hot.data()), hot_n, img.root_table.data()};
     const uint8_t* lo = text + (n ? offs[0] : 0);
     const uint8_t* hi = text + (n ? offs[n] : 0);
+    const bool v1 = kernel_version >= 1 && !charwise && mode != M_LEFTMOST && !(mode == M_FIND && img.root_opos != 0);
+    if (v1) {
+        const StdEnv Ev{P.rec, reinterpret_cast<const uint4*>(hot.data()), hot_n, P.root4, P.text_end, P.root_opos};
+        const int n_warps = 3;
+        if (mode == M_FIND) run_items_v1<M_FIND>(P, Ev, lo, n_warps);
+        if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING>(P, Ev, lo, n_warps);
+        if (mode == M_NO_SUFFIX) run_items_v1<M_NO_SUFFIX>(P, Ev, lo, n_warps);
+    } else
     switch ((charwise ? 4 : 0) + mode) {
         case 0: run_items<false, M_FIND>(P, V, lo, hi); break;
         case 1: run_items<false, M_OVERLAPPING>(P, V, lo, hi); break;

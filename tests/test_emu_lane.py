@@ -35,8 +35,9 @@ def test_golden_vectors(variant, iterator, kind, t):
     wire = O.OraclePma.build(t["patterns"], charwise=cw, match_kind=O.KIND[kind]).serialize()
     hay = t["haystack"].encode()
     text = np.frombuffer(hay, dtype=np.uint8)
-    for hot in (0, 1 << 20):
-        rc, m, oo, need = E.scan(wire, cw, MODE[iterator], text, np.array([0, len(hay)], dtype=np.uint64), hot_n=hot)
+    for hot, kernel in ((0, 1), (1 << 20, 1), (3, 0)):
+        rc, m, oo, need = E.scan(wire, cw, MODE[iterator], text, np.array([0, len(hay)], dtype=np.uint64), hot_n=hot,
+                                 kernel=kernel)
         assert rc == 0
         assert triples(m) == [(s, e, v) for v, s, e in t["matches"]]
 
@@ -73,8 +74,8 @@ def test_random_batches(seed, kind, cw):
     modes = [3] if kind else [0, 1, 2]
     for mode in modes:
         ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
-        for hot in (0, 7, 1 << 20):
-            rc, m, oo, need = E.scan(wire, cw, mode, text, offs, hot_n=hot)
+        for hot, kernel in ((0, 1), (7, 1), (1 << 20, 1), (5, 0)):
+            rc, m, oo, need = E.scan(wire, cw, mode, text, offs, hot_n=hot, kernel=kernel)
             assert rc == 0
             assert need == ref["total"]
             assert np.array_equal(np.diff(oo.astype(np.int64)), ref["counts"].astype(np.int64))
@@ -91,9 +92,10 @@ def test_unaligned_offsets_and_long_chains():
         text = np.frombuffer(b"x" * shift + b"a" * 70 + b"b" + b"a" * 40, dtype=np.uint8)
         offs = np.array([shift, shift + 50, shift + 50, shift + 111], dtype=np.uint64)
         ref = pma.scan_batch(O.FIND_OVERLAPPING, text, offs, want_matches=True)
-        rc, m, oo, need = E.scan(wire, False, 1, text, offs)
-        assert rc == 0 and m.tobytes() == ref["matches"].tobytes()
-        assert list(oo) == [0] + list(np.cumsum(ref["counts"]))
+        for kernel in (0, 1):
+            rc, m, oo, need = E.scan(wire, False, 1, text, offs, kernel=kernel)
+            assert rc == 0 and m.tobytes() == ref["matches"].tobytes()
+            assert list(oo) == [0] + list(np.cumsum(ref["counts"]))
 
 
 def test_overflow_protocol():
