@@ -70,18 +70,20 @@ template <int MODE>
 __global__ void __launch_bounds__(kMaxThreads, 1) k_scan_std(ScanParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* s_root4 = reinterpret_cast<uint4*>(smem_raw);
-    uint4* s_hot = reinterpret_cast<uint4*>(smem_raw + kRoot4Bytes);
+    QEntry* s_queue = reinterpret_cast<QEntry*>(smem_raw + kRoot4Bytes);  // [LANE_Q][blockDim.x]
+    uint4* s_hot = reinterpret_cast<uint4*>(smem_raw + kRoot4Bytes + (size_t)LANE_Q * blockDim.x * sizeof(QEntry));
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_root4[i] = P.root4[i];
     for (uint32_t i = threadIdx.x; i < P.hot_n; i += blockDim.x) s_hot[i] = P.rec[i];
     __syncthreads();
 
     using M = StdMachine<MODE>;
-    const StdEnv Ev{P.rec, s_hot, P.hot_n, s_root4, P.text_end, P.root_opos};
+    const StdEnv Ev{P.rec, s_hot, P.hot_n, s_root4, P.text_end, P.root_opos, s_queue + threadIdx.x, blockDim.x};
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     LaneStd L;
     L.active = false;
     L.done = false;
+    L.need_nw = false;
     L.qn = 0;
     L.kind = K_NONE;
     Emitter E;
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_scan_std(ScanParams P) {
     bool exhausted = false;
     for (;;) {
         // ---- service phase (the warp is converged here) ----
-        if (L.active) M::drain(L, P, E);
+        if (L.active) M::drain(L, Ev, P, E);
         if (L.active && L.done) {
             E.finish(P);
             L.active = false;
@@ -111,9 +113,17 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_scan_std(ScanParams P) {
         }
         if (!__any_sync(FULL, L.active)) break;
         // ---- lock-step iterations until some lane needs service ----
-        for (;;) {
-            const bool ok = M::step(L, Ev, nullptr);
-            if (__any_sync(FULL, !ok && L.active)) break;
+        bool stop = false;
+        while (!stop) {
+            M::text_topup(L, Ev, nullptr);
+#pragma unroll 1
+            for (int k = 0; k < TEXT_TOPUP; ++k) {
+                const bool ok = M::step(L, Ev);
+                if (__any_sync(FULL, !ok && L.active)) {
+                    stop = true;
+                    break;
+                }
+            }
         }
     }
 }
@@ -422,7 +432,7 @@ int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, uint64_t text_byte
     // the lane machine serves the bytewise Standard iterators; find_iter with an empty pattern
     // (it only reports zero-length matches, src/bytewise/iter.rs:60-85) keeps the simple kernel
     const bool v1 = d->opt_kernel >= 1 && !d->charwise && mode != M_LEFTMOST && !(mode == M_FIND && d->root_opos != 0);
-    const size_t front = v1 ? kRoot4Bytes : kRootBytes;
+    const size_t front = v1 ? kRoot4Bytes + (size_t)LANE_Q * threads * sizeof(QEntry) : kRootBytes;
     uint64_t hot = smem_budget > front ? (smem_budget - front) / 16 : 0;
     if (d->opt_hot_records >= 0) hot = std::min<uint64_t>(hot, (uint64_t)d->opt_hot_records);
     hot = std::min<uint64_t>(hot, d->n_slots);

@@ -490,7 +490,7 @@ DACH_HD void scan_leftmost(const ScanParams& P, const RecView& V, TextWin& T, Em
 
 
 // =============================================================================================
-// v1 lane machine for the bytewise Standard modes (find_overlapping / no_suffix / find without an
+// Lane machine for the bytewise Standard modes (find_overlapping / no_suffix / find without an
 // empty pattern).
 //
 // The per-byte loop of src/bytewise.rs:1063-1088 is re-cut so that every lane of a warp does the
@@ -499,48 +499,62 @@ DACH_HD void scan_leftmost(const ScanParams& P, const RecView& V, TextWin& T, Em
 // follow fail") leaves ~4 of 32 lanes active per issued instruction (profiles/r1_v0_summary.md);
 // here a lane that misses simply spends its next iteration on the next probe of the same byte.
 //
-//   kind = K_NONE        the lane sits in a state and needs the next byte
-//          K_PROBE       fetch rec[addr], addr = base ^ c; CHECK decides hit / miss
-//          K_LEARN       fetch rec[pend] to learn (efail, fbase) of a failure state whose probe missed
+//   kind = K_NONE    the lane sits in a state and needs the next byte
+//          K_PROBE   fetch rec[addr], addr = BASE ^ c; CHECK decides hit / miss
+//          K_LEARN   fetch rec[pend] to learn (efail, fbase) of a failure state whose probe missed
 //
-// Matches are not expanded in the loop: a lane that lands on a state with an output list only
-// queues (end, output_pos).  The warp drains all queues together (service phase), so the output
-// walk -- a divergent pointer chase -- runs with many lanes at once instead of one.
+// One iteration = [next byte] -> [one fetch] -> [fall: failure link / dense root row] -> [land].
+// There is exactly one "fall" site and one "land" site, so the divergent part of an iteration is
+// a handful of predicated instructions.  ROOT is represented as the record {0, ROOT, 0, opos<<8}:
+// "no children, fail to ROOT", which sends every byte through the dense root row.
+//
+// Matches are not expanded in the loop: a lane that lands on a state with an output list stores
+// (end, output_pos) in its shared-memory queue.  The warp drains all queues together (service
+// phase), so the output walk -- a divergent pointer chase -- runs with many lanes at once.
+//
+// Text: two 16-byte register windows per lane (current, next).  Crossing into the next window is
+// four predicated moves; the load that re-arms `next` is issued on a warp-uniform schedule (every
+// TEXT_TOPUP iterations), which is early enough because a lane consumes at most one byte per
+// iteration.
 // =============================================================================================
 
-constexpr uint32_t K_NONE = 0, K_PROBE = 1, K_LEARN = 3;
-constexpr int LANE_Q = 4;                    // queued output events per lane
+constexpr uint32_t K_NONE = 0, K_PROBE = 1, K_LEARN = 2;
+constexpr int LANE_Q = 6;                     // queued output events per lane (shared memory)
+constexpr int TEXT_TOPUP = 8;                 // iterations between window top-ups (must be < 16)
 constexpr uint32_t F2ROOT_BIT = 0x80000000u;  // in record word 2: efail(efail(s)) == ROOT
 
-// Dense root row (shared memory): entry c is the whole record of ROOT's child for byte c, so
-// landing on it needs no fetch; an entry whose CHECK byte differs from c means "stay in ROOT".
+struct QEntry {
+    uint32_t end, opos;
+};
+
 struct LaneStd {
     // item
     const uint8_t* hay;
     uint32_t len, pos, item;
     bool active, done;
-    // text: current and prefetched 16-byte windows
-    uint64_t blk;  // (address >> 4) of `cw`
+    // text windows
     uint4 cw, nw;
+    bool need_nw;
     // automaton
-    uint32_t c;              // byte being matched
-    uint32_t cb;             // BASE to probe with (0: the state has no children)
-    uint32_t nf, nfb;        // where to fall on a miss, and its BASE | F2ROOT_BIT (valid if know)
-    uint32_t pend;           // failure state whose BASE is being probed (know == false)
+    uint32_t c;        // byte being matched
+    uint32_t cb;       // BASE to probe with (0: the state has no children)
+    uint32_t nf, nfb;  // where to fall on a miss, and its BASE | F2ROOT_BIT (valid if know)
+    uint32_t pend;     // failure state whose BASE is being probed (know == false)
     bool know, pend_f2root;
     uint32_t kind, addr;
-    // queued outputs
+    // queue fill
     uint32_t qn;
-    uint32_t qe[LANE_Q], qo[LANE_Q];
 };
 
 struct StdEnv {
     const uint4* glob;   // records in global memory
     const uint4* hot;    // leading records in shared memory
     uint32_t hot_n;
-    const uint4* root4;  // dense root row (shared memory)
+    const uint4* root4;  // dense root row (shared memory): the record of ROOT's child per byte
     const uint8_t* text_end;
     uint32_t root_opos;
+    QEntry* q;           // this lane's queue: entry j at q[j * q_stride]
+    uint32_t q_stride;
 };
 
 DACH_HD uint4 ld_text16(const uint8_t* q, const uint8_t* text_end, const uint8_t* emu_lo) {
@@ -566,100 +580,39 @@ DACH_HD uint4 ld_text16(const uint8_t* q, const uint8_t* text_end, const uint8_t
 
 template <int MODE>
 struct StdMachine {
-    // ---- text ---------------------------------------------------------------------------------
-    static DACH_HD void text_open(LaneStd& L, const StdEnv& Ev, const uint8_t* emu_lo) {
-        const uint64_t a = (uint64_t)(uintptr_t)L.hay;
-        L.blk = a >> 4;
-        const uint8_t* q = reinterpret_cast<const uint8_t*>((uintptr_t)(L.blk << 4));
-        L.cw = ld_text16(q, Ev.text_end, emu_lo);
-        L.nw = ld_text16(q + 16, Ev.text_end, emu_lo);
-    }
-    static DACH_HD uint32_t text_byte(LaneStd& L, const StdEnv& Ev, const uint8_t* emu_lo) {
-        const uint64_t a = (uint64_t)(uintptr_t)L.hay + L.pos;
-        if ((a >> 4) != L.blk) {  // sequential reader: this is always the next block
-            L.blk = a >> 4;
-            L.cw = L.nw;
-            const uint8_t* q = reinterpret_cast<const uint8_t*>((uintptr_t)((L.blk + 1) << 4));
-            L.nw = ld_text16(q, Ev.text_end, emu_lo);
-        }
-        const uint32_t o = (uint32_t)a & 15u;
-        const uint32_t lo = (o & 8u) ? L.cw.z : L.cw.x;
-        const uint32_t hi = (o & 8u) ? L.cw.w : L.cw.y;
-        const uint32_t word = (o & 4u) ? hi : lo;
-        return (word >> ((o & 3u) * 8u)) & 0xffu;
+    static DACH_HD const uint8_t* block_of(const LaneStd& L) {
+        return reinterpret_cast<const uint8_t*>(((uintptr_t)L.hay + L.pos) & ~(uintptr_t)15);
     }
 
-    // ---- queue ----------------------------------------------------------------------------------
-    static DACH_HD void push(LaneStd& L, uint32_t end, uint32_t opos) {
-        // LANE_Q == 4, unrolled so that the queue stays in registers
-        if (L.qn == 0) { L.qe[0] = end; L.qo[0] = opos; }
-        else if (L.qn == 1) { L.qe[1] = end; L.qo[1] = opos; }
-        else if (L.qn == 2) { L.qe[2] = end; L.qo[2] = opos; }
-        else { L.qe[3] = end; L.qo[3] = opos; }
-        ++L.qn;
-    }
-
-    // ---- landing ----------------------------------------------------------------------------------
-    // The lane has arrived in a non-root state whose record fields are given; the byte was consumed.
-    static DACH_HD void land(LaneStd& L, uint32_t base, uint32_t efail, uint32_t fbase, uint32_t opos) {
-        L.cb = base;
-        L.nf = efail;
-        L.nfb = fbase;
-        L.know = true;
-        L.kind = K_NONE;
-        if (opos != 0) {
-            push(L, L.pos, opos);
-            if (MODE == M_FIND) {  // every next() restarts at ROOT (src/bytewise/iter.rs:87)
-                L.cb = 0;
-                L.nf = D_ROOT;
-            }
-        }
-    }
-    static DACH_HD void land_root(LaneStd& L, const StdEnv& Ev) {
-        L.cb = 0;
-        L.nf = D_ROOT;
-        L.nfb = 0;
-        L.know = true;
-        L.kind = K_NONE;
-        if (MODE != M_FIND && Ev.root_opos != 0) push(L, L.pos, Ev.root_opos);
-    }
-
-    // A probe missed (or the state has no children) and (nf, nfb) are known: take the failure link.
-    static DACH_HD void fall(LaneStd& L, const StdEnv& Ev) {
-        if (L.nf == D_ROOT) {
-            const uint4 t = Ev.root4[L.c];  // dense ROOT row (src/bytewise.rs:1067-1069)
-            ++L.pos;                        // the byte is consumed
-            if ((t.w & 0xffu) != L.c)
-                land_root(L, Ev);
-            else
-                land(L, t.x, t.y, t.z, t.w >> 8);
-        } else {
-            L.cb = L.nfb & ~F2ROOT_BIT;
-            L.pend = L.nf;
-            L.pend_f2root = (L.nfb & F2ROOT_BIT) != 0;
-            L.know = false;
-            L.kind = K_PROBE;
-            L.addr = L.cb ^ L.c;
+    // warp-uniform schedule: re-arm the prefetched window of the lanes that crossed since last time
+    static DACH_HD void text_topup(LaneStd& L, const StdEnv& Ev, const uint8_t* emu_lo) {
+        if (L.active && L.need_nw) {
+            L.nw = ld_text16(block_of(L) + 16, Ev.text_end, emu_lo);
+            L.need_nw = false;
         }
     }
 
-    // ---- one iteration ----------------------------------------------------------------------------
-    // Returns true if the lane can keep stepping, false if it needs the service phase
-    // (queue full or item finished).
-    static DACH_HD bool step(LaneStd& L, const StdEnv& Ev, const uint8_t* emu_lo) {
-        if (!L.active || L.done) return false;
-        if (L.qn == LANE_Q) return false;  // a landing pushes at most one event; it happens only in K_NONE
+    // One iteration.  Returns false if the lane cannot step (inactive, finished, or queue full).
+    static DACH_HD bool step(LaneStd& L, const StdEnv& Ev) {
+        if (!L.active || L.done || L.qn == LANE_Q) return false;
+        bool do_fall = false, landed = false;
+        uint4 r;  // record the lane lands on
+        r.x = r.y = r.z = r.w = 0;
         if (L.kind == K_NONE) {
             if (L.pos >= L.len) {
                 L.done = true;
                 return false;
             }
-            L.c = text_byte(L, Ev, emu_lo);
+            const uint32_t o = ((uint32_t)(uintptr_t)L.hay + L.pos) & 15u;
+            const uint32_t lo = (o & 8u) ? L.cw.z : L.cw.x;
+            const uint32_t hi = (o & 8u) ? L.cw.w : L.cw.y;
+            const uint32_t word = (o & 4u) ? hi : lo;
+            L.c = (word >> ((o & 3u) * 8u)) & 0xffu;
             if (L.cb != 0) {
                 L.kind = K_PROBE;
                 L.addr = L.cb ^ L.c;
             } else {
-                fall(L, Ev);
+                do_fall = true;
             }
         }
         if (L.kind != K_NONE) {
@@ -667,14 +620,14 @@ struct StdMachine {
             const uint4 x = a < Ev.hot_n ? Ev.hot[a] : ld_u4(Ev.glob + a);
             if (L.kind == K_PROBE) {
                 if ((x.w & 0xffu) == L.c) {
-                    ++L.pos;
-                    land(L, x.x, x.y, x.z, x.w >> 8);
+                    landed = true;
+                    r = x;
                 } else if (L.know) {
-                    fall(L, Ev);
+                    do_fall = true;
                 } else if (L.pend_f2root) {
                     L.nf = D_ROOT;
                     L.know = true;
-                    fall(L, Ev);
+                    do_fall = true;
                 } else {
                     L.kind = K_LEARN;
                     L.addr = L.pend;
@@ -683,26 +636,67 @@ struct StdMachine {
                 L.nf = x.y;
                 L.nfb = x.z;
                 L.know = true;
-                fall(L, Ev);
+                do_fall = true;
+            }
+        }
+        if (do_fall) {  // take the failure link (nf, nfb are known)
+            if (L.nf == D_ROOT) {
+                r = Ev.root4[L.c];  // dense ROOT row (src/bytewise.rs:1067-1069)
+                landed = true;
+                if ((r.w & 0xffu) != L.c) {  // no child: stay in ROOT
+                    r.x = 0;
+                    r.y = D_ROOT;
+                    r.z = 0;
+                    r.w = Ev.root_opos << 8;
+                }
+            } else {
+                L.cb = L.nfb & ~F2ROOT_BIT;
+                L.pend = L.nf;
+                L.pend_f2root = (L.nfb & F2ROOT_BIT) != 0;
+                L.know = false;
+                L.kind = K_PROBE;
+                L.addr = L.cb ^ L.c;
+            }
+        }
+        if (landed) {  // the byte is consumed; the lane now sits in the state described by r
+            ++L.pos;
+            if ((((uint32_t)(uintptr_t)L.hay + L.pos) & 15u) == 0) {  // crossed into the next window
+                L.cw = L.nw;
+                L.need_nw = true;
+            }
+            L.cb = r.x;
+            L.nf = r.y;
+            L.nfb = r.z;
+            L.know = true;
+            L.kind = K_NONE;
+            const uint32_t opos = r.w >> 8;
+            if (opos != 0) {
+                QEntry e;
+                e.end = L.pos;
+                e.opos = opos;
+                Ev.q[L.qn * Ev.q_stride] = e;
+                ++L.qn;
+                if (MODE == M_FIND) {  // every next() restarts at ROOT (src/bytewise/iter.rs:87)
+                    L.cb = 0;
+                    L.nf = D_ROOT;
+                    L.nfb = 0;
+                }
             }
         }
         return true;
     }
 
     // ---- service pieces ---------------------------------------------------------------------------
-    static DACH_HD void drain(LaneStd& L, const ScanParams& P, Emitter& E) {
-#define DACH_DRAIN_ONE(J)                                     \
-    if (L.qn > (J)) {                                         \
-        if (MODE == M_OVERLAPPING)                            \
-            emit_chain(P, E, L.qo[J], L.qe[J]);               \
-        else                                                  \
-            emit_head(P, E, L.qo[J], L.qe[J]);                \
-    }
-        DACH_DRAIN_ONE(0)
-        DACH_DRAIN_ONE(1)
-        DACH_DRAIN_ONE(2)
-        DACH_DRAIN_ONE(3)
-#undef DACH_DRAIN_ONE
+    static DACH_HD void drain(LaneStd& L, const StdEnv& Ev, const ScanParams& P, Emitter& E) {
+        for (uint32_t j = 0; j < (uint32_t)LANE_Q; ++j) {
+            if (j < L.qn) {
+                const QEntry e = Ev.q[j * Ev.q_stride];
+                if (MODE == M_OVERLAPPING)
+                    emit_chain(P, E, e.opos, e.end);
+                else
+                    emit_head(P, E, e.opos, e.end);
+            }
+        }
         L.qn = 0;
     }
 
@@ -717,10 +711,24 @@ struct StdMachine {
         L.done = false;
         L.qn = 0;
         E.begin((uint32_t)item);
-        text_open(L, Ev, emu_lo);
+        const uint8_t* b0 = block_of(L);
+        L.cw = ld_text16(b0, Ev.text_end, emu_lo);
+        L.nw = ld_text16(b0 + 16, Ev.text_end, emu_lo);
+        L.need_nw = false;
         // the iterator starts in ROOT with ROOT's output list pending at position 0
         // (src/bytewise.rs:303-313; no-suffix variant: src/bytewise/iter.rs:196-216)
-        land_root(L, Ev);
+        L.cb = 0;
+        L.nf = D_ROOT;
+        L.nfb = 0;
+        L.know = true;
+        L.kind = K_NONE;
+        if (MODE != M_FIND && Ev.root_opos != 0) {
+            QEntry e;
+            e.end = 0;
+            e.opos = Ev.root_opos;
+            Ev.q[0] = e;
+            L.qn = 1;
+        }
     }
 };
 

@@ -35,23 +35,30 @@ static void run_items(const ScanParams& P, const RecView& V, const uint8_t* lo, 
 // Warp-level driver of the v1 lane machine, mirroring k_scan_std in dev_scan.cu with the warp
 // collectives (ballot / any / shuffle) written out as loops over 32 lane states.
 template <int MODE>
-static void run_items_v1(const ScanParams& P, const StdEnv& Ev, const uint8_t* lo, int n_warps) {
+static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* lo, int n_warps) {
     using M = StdMachine<MODE>;
     struct Warp {
         LaneStd L[32];
         Emitter E[32];
+        StdEnv Ev[32];
+        std::vector<QEntry> queue;
         bool exhausted[32];
         bool finished;
     };
     std::vector<Warp> warps(n_warps);
     for (auto& w : warps) {
+        w.queue.assign((size_t)LANE_Q * 32, QEntry{0, 0});
         for (int l = 0; l < 32; ++l) {
             w.L[l].active = false;
             w.L[l].done = false;
+            w.L[l].need_nw = false;
             w.L[l].qn = 0;
             w.L[l].kind = K_NONE;
             w.E[l].begin(0);
             w.exhausted[l] = false;
+            w.Ev[l] = Ev0;
+            w.Ev[l].q = w.queue.data() + l;
+            w.Ev[l].q_stride = 32;
         }
         w.finished = false;
     }
@@ -62,7 +69,7 @@ static void run_items_v1(const ScanParams& P, const StdEnv& Ev, const uint8_t* l
         for (auto& w : warps) {
             if (w.finished) continue;
             for (int l = 0; l < 32; ++l)
-                if (w.L[l].active) M::drain(w.L[l], P, w.E[l]);
+                if (w.L[l].active) M::drain(w.L[l], w.Ev[l], P, w.E[l]);
             for (int l = 0; l < 32; ++l)
                 if (w.L[l].active && w.L[l].done) {
                     w.E[l].finish(P);
@@ -78,7 +85,7 @@ static void run_items_v1(const ScanParams& P, const StdEnv& Ev, const uint8_t* l
                     if (m & (1u << l)) {
                         const unsigned long long item = base + __builtin_popcount(m & ((1u << l) - 1u));
                         if (item < P.n_items)
-                            M::begin_item(w.L[l], P, Ev, w.E[l], item, lo);
+                            M::begin_item(w.L[l], P, w.Ev[l], w.E[l], item, lo);
                         else
                             w.exhausted[l] = true;
                     }
@@ -90,13 +97,17 @@ static void run_items_v1(const ScanParams& P, const StdEnv& Ev, const uint8_t* l
                 continue;
             }
             any_left = true;
-            for (;;) {
-                bool need_service = false;
-                for (int l = 0; l < 32; ++l) {
-                    const bool ok = M::step(w.L[l], Ev, lo);
-                    if (!ok && w.L[l].active) need_service = true;
+            bool stop = false;
+            while (!stop) {
+                for (int l = 0; l < 32; ++l) M::text_topup(w.L[l], w.Ev[l], lo);
+                for (int k = 0; k < TEXT_TOPUP && !stop; ++k) {
+                    bool need_service = false;
+                    for (int l = 0; l < 32; ++l) {
+                        const bool ok = M::step(w.L[l], w.Ev[l]);
+                        if (!ok && w.L[l].active) need_service = true;
+                    }
+                    if (need_service) stop = true;
                 }
-                if (need_service) break;
             }
         }
     }
@@ -149,7 +160,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     const uint8_t* hi = text + (n ? offs[n] : 0);
     const bool v1 = kernel_version >= 1 && !charwise && mode != M_LEFTMOST && !(mode == M_FIND && img.root_opos != 0);
     if (v1) {
-        const StdEnv Ev{P.rec, reinterpret_cast<const uint4*>(hot.data()), hot_n, P.root4, P.text_end, P.root_opos};
+        const StdEnv Ev{P.rec, reinterpret_cast<const uint4*>(hot.data()), hot_n, P.root4, P.text_end, P.root_opos, nullptr, 0};
         const int n_warps = 3;
         if (mode == M_FIND) run_items_v1<M_FIND>(P, Ev, lo, n_warps);
         if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING>(P, Ev, lo, n_warps);
