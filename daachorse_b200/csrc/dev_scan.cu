@@ -293,6 +293,8 @@ struct dach_dev {
     uint32_t* d_root = nullptr;
     uint4* d_root4 = nullptr;
     uint32_t* d_mapper = nullptr;
+    void* image_base = nullptr;
+    size_t image_alloc = 0, l2_window = 0, l2_persist = 0;
     // workspace (guarded by mu)
     std::mutex mu;
     DevBuf counts, tiles, ctrl, pool;
@@ -303,6 +305,7 @@ struct dach_dev {
     int64_t opt_hot_records = -1;  // -1: as many as fit
     int64_t opt_threads = 1024;
     int64_t opt_ctas_per_sm = 1;
+    int64_t opt_l2_persist = 1;  // 1: access-policy window over the image during the scan kernel
     int64_t opt_kernel = 1;  // 1: warp-synchronous lane machine where it applies; 0: always the v0 kernels
     // stats
     uint64_t launches = 0;
@@ -441,11 +444,28 @@ int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, uint64_t text_byte
     const int grid = d->sm_count * ctas_per_sm;
 
     if (!cuda_ok(cudaMemsetAsync(d->ctrl.p, 0, sizeof(ScanCtrl), st), "memset ctrl")) return DACH_CUDA_ERROR;
+    const bool window = d->opt_l2_persist && d->l2_persist > 0;
+    if (window) {
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        av.accessPolicyWindow.base_ptr = d->image_base;
+        av.accessPolicyWindow.num_bytes = d->l2_window;
+        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)d->l2_persist / (double)d->l2_window);
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+    }
     cudaEventRecord(d->ev[0], st);
     if (!cuda_ok(v1 ? launch_std(mode, P, grid, threads, smem, st) : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
                  "k_scan launch"))
         return DACH_CUDA_ERROR;
     cudaEventRecord(d->ev[1], st);
+    if (window) {
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        av.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+    }
     unsigned long long* offs64 = reinterpret_cast<unsigned long long*>(d_out_offs);
     unsigned long long* tiles = static_cast<unsigned long long*>(d->tiles.p);
     k_offsets_tile_sums<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n, tiles);
@@ -510,17 +530,35 @@ int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
     if (!cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return DACH_CUDA_ERROR;
     d->sm_count = prop.multiProcessorCount;
     d->smem_optin = prop.sharedMemPerBlockOptin;
-    auto up = [&](const std::vector<uint32_t>& v, void** dst) -> bool {
-        const size_t bytes = std::max<size_t>(v.size() * 4, 16);
-        if (!cuda_ok(cudaMalloc(dst, bytes), "cudaMalloc image")) return false;
-        if (!v.empty() && !cuda_ok(cudaMemcpy(*dst, v.data(), v.size() * 4, cudaMemcpyHostToDevice), "upload image"))
-            return false;
-        d->image_bytes += v.size() * 4;
-        return true;
-    };
-    bool ok = up(img.rec, reinterpret_cast<void**>(&d->d_rec)) && up(img.outputs, reinterpret_cast<void**>(&d->d_outputs)) &&
-              up(img.root_table, reinterpret_cast<void**>(&d->d_root)) && up(img.root4, reinterpret_cast<void**>(&d->d_root4)) &&
-              up(img.mapper, reinterpret_cast<void**>(&d->d_mapper));
+    // one allocation for the whole image (records | outputs | root rows | mapper), 256-byte aligned
+    // parts, so that a single L2 access-policy window can cover it
+    const std::vector<uint32_t>* parts[5] = {&img.rec, &img.outputs, &img.root_table, &img.root4, &img.mapper};
+    size_t part_off[5], total = 0;
+    for (int i = 0; i < 5; ++i) {
+        part_off[i] = total;
+        total += (std::max<size_t>(parts[i]->size() * 4, 16) + 255) & ~size_t(255);
+        d->image_bytes += parts[i]->size() * 4;
+    }
+    bool ok = cuda_ok(cudaMalloc(&d->image_base, total), "cudaMalloc image");
+    d->image_alloc = total;
+    for (int i = 0; ok && i < 5; ++i)
+        if (!parts[i]->empty())
+            ok = cuda_ok(cudaMemcpy(static_cast<char*>(d->image_base) + part_off[i], parts[i]->data(), parts[i]->size() * 4,
+                                    cudaMemcpyHostToDevice),
+                         "upload image");
+    if (ok) {
+        char* b = static_cast<char*>(d->image_base);
+        d->d_rec = reinterpret_cast<uint4*>(b + part_off[0]);
+        d->d_outputs = reinterpret_cast<uint4*>(b + part_off[1]);
+        d->d_root = reinterpret_cast<uint32_t*>(b + part_off[2]);
+        d->d_root4 = reinterpret_cast<uint4*>(b + part_off[3]);
+        d->d_mapper = reinterpret_cast<uint32_t*>(b + part_off[4]);
+        // let the automaton persist in L2 while text and match streams pass through it
+        d->l2_window = std::min<size_t>(total, (size_t)prop.accessPolicyMaxWindowSize);
+        d->l2_persist = std::min<size_t>(d->l2_window, (size_t)prop.persistingL2CacheMaxSize);
+        if (d->l2_persist) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, d->l2_persist);
+        cudaGetLastError();
+    }
     ok = ok && cuda_ok(cudaMallocHost(reinterpret_cast<void**>(&d->pinned), sizeof(HostPinned)), "cudaMallocHost");
     for (int i = 0; ok && i < 4; ++i) ok = cuda_ok(cudaEventCreate(&d->ev[i]), "cudaEventCreate");
     if (!ok) {
@@ -534,11 +572,7 @@ int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
 void dach_dev_free(dach_dev* d) {
     if (!d) return;
     DeviceGuard g(d->device);
-    cudaFree(d->d_rec);
-    cudaFree(d->d_outputs);
-    cudaFree(d->d_root);
-    cudaFree(d->d_root4);
-    cudaFree(d->d_mapper);
+    cudaFree(d->image_base);
     for (DevBuf* b : {&d->counts, &d->tiles, &d->ctrl, &d->pool, &d->h_text, &d->h_offs, &d->h_out, &d->h_out_offs})
         if (b->p) cudaFree(b->p);
     if (d->pinned) cudaFreeHost(d->pinned);
@@ -622,6 +656,8 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
         d->opt_ctas_per_sm = value;
     else if (k == "kernel")
         d->opt_kernel = value;
+    else if (k == "l2_persist")
+        d->opt_l2_persist = value;
     else {
         set_error("unknown option " + k);
         return DACH_INVALID_ARGUMENT;

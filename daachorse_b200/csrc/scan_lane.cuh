@@ -34,6 +34,12 @@ struct uint4 {
 #endif
 #endif
 
+#if defined(__CUDA_ARCH__)
+#define DACH_SYNCWARP() __syncwarp()
+#else
+#define DACH_SYNCWARP()
+#endif
+
 #if defined(DACH_WATCHDOG) && defined(__CUDA_ARCH__)
 #include <cstdio>
 #define DACH_WD_DECL(name) unsigned long long name = 0
@@ -592,30 +598,36 @@ struct StdMachine {
         }
     }
 
-    // One iteration.  Returns false if the lane cannot step (inactive, finished, or queue full).
+    // One iteration, called by all 32 lanes of the warp together.  Returns false if the lane did
+    // not step (inactive, finished, or queue full).  The four phases are separated by warp
+    // barriers so that every phase is executed once per iteration by all the lanes that need it
+    // (without them the compiler threads the lanes through the phases in separate passes).
     static DACH_HD bool step(LaneStd& L, const StdEnv& Ev) {
-        if (!L.active || L.done || L.qn == LANE_Q) return false;
+        bool run = L.active && !L.done && L.qn != LANE_Q;
         bool do_fall = false, landed = false;
         uint4 r;  // record the lane lands on
         r.x = r.y = r.z = r.w = 0;
-        if (L.kind == K_NONE) {
+        // ---- phase 1: next byte ------------------------------------------------------------------
+        if (run && L.kind == K_NONE) {
             if (L.pos >= L.len) {
                 L.done = true;
-                return false;
-            }
-            const uint32_t o = ((uint32_t)(uintptr_t)L.hay + L.pos) & 15u;
-            const uint32_t lo = (o & 8u) ? L.cw.z : L.cw.x;
-            const uint32_t hi = (o & 8u) ? L.cw.w : L.cw.y;
-            const uint32_t word = (o & 4u) ? hi : lo;
-            L.c = (word >> ((o & 3u) * 8u)) & 0xffu;
-            if (L.cb != 0) {
-                L.kind = K_PROBE;
-                L.addr = L.cb ^ L.c;
+                run = false;
             } else {
-                do_fall = true;
+                const uint32_t o = ((uint32_t)(uintptr_t)L.hay + L.pos) & 15u;
+                const uint32_t lo = (o & 8u) ? L.cw.z : L.cw.x;
+                const uint32_t hi = (o & 8u) ? L.cw.w : L.cw.y;
+                const uint32_t word = (o & 4u) ? hi : lo;
+                L.c = (word >> ((o & 3u) * 8u)) & 0xffu;
+                L.addr = L.cb ^ L.c;
+                if (L.cb != 0)
+                    L.kind = K_PROBE;
+                else
+                    do_fall = true;
             }
         }
-        if (L.kind != K_NONE) {
+        DACH_SYNCWARP();
+        // ---- phase 2: the one record fetch ---------------------------------------------------------
+        if (run && L.kind != K_NONE) {
             const uint32_t a = L.addr;
             const uint4 x = a < Ev.hot_n ? Ev.hot[a] : ld_u4(Ev.glob + a);
             if (L.kind == K_PROBE) {
@@ -639,7 +651,9 @@ struct StdMachine {
                 do_fall = true;
             }
         }
-        if (do_fall) {  // take the failure link (nf, nfb are known)
+        DACH_SYNCWARP();
+        // ---- phase 3: take the failure link (nf, nfb are known) -------------------------------------
+        if (do_fall) {
             if (L.nf == D_ROOT) {
                 r = Ev.root4[L.c];  // dense ROOT row (src/bytewise.rs:1067-1069)
                 landed = true;
@@ -658,7 +672,9 @@ struct StdMachine {
                 L.addr = L.cb ^ L.c;
             }
         }
-        if (landed) {  // the byte is consumed; the lane now sits in the state described by r
+        DACH_SYNCWARP();
+        // ---- phase 4: land (the byte is consumed; the lane sits in the state described by r) ---------
+        if (landed) {
             ++L.pos;
             if ((((uint32_t)(uintptr_t)L.hay + L.pos) & 15u) == 0) {  // crossed into the next window
                 L.cw = L.nw;
@@ -683,7 +699,7 @@ struct StdMachine {
                 }
             }
         }
-        return true;
+        return run;
     }
 
     // ---- service pieces ---------------------------------------------------------------------------
