@@ -79,16 +79,38 @@ int build_image(const dach_pma* p, HostImage* img) {
                 if (ci < n && (p->opos_ch[ci] & 0xff) == c) img->root_table[c] = ci;
             }
         }
-        // dense root row with the child's whole record inlined; "no child" is an entry whose CHECK
-        // byte differs from the label
+        // compact image for the lane-machine kernels (Standard automata of at most 2^24 slots)
         img->root4.assign(1024, 0);
-        for (uint32_t c = 0; c < 256; ++c) {
-            const uint32_t ci = img->root_table[c];
-            if (ci == kRoot) {
-                img->root4[c * 4 + 3] = (c ^ 1u) & 0xffu;
-                continue;
+        img->root_base = n ? p->base[kRoot] : 0;
+        if (!lm && n <= (size_t(1) << 24) && p->outputs.size() < (size_t(1) << 24)) {
+            img->crec.resize(n * 4);
+            img->opos_tab.resize(n);
+            for (size_t s = 0; s < n; ++s) {
+                const uint32_t* w = &img->rec[s * 4];
+                uint32_t sig = 0;
+                if (w[0] != 0)
+                    for (uint32_t c = 0; c < 256; ++c) {
+                        const uint32_t ci = w[0] ^ c;
+                        if (ci < n && (p->opos_ch[ci] & 0xff) == c) sig |= 1u << (c & 31);
+                    }
+                uint32_t* r = &img->crec[s * 4];
+                const uint32_t opos = p->opos_ch[s] >> 8;
+                r[0] = (w[0] << 8) | (p->opos_ch[s] & 0xff);
+                r[1] = (w[1] << 8) | (opos ? 1u : 0u) | ((w[2] & 0x80000000u) ? 2u : 0u);
+                r[2] = (w[2] & 0x7fffffffu) << 8;
+                r[3] = sig;
+                img->opos_tab[s] = opos;
             }
-            for (int k = 0; k < 4; ++k) img->root4[c * 4 + k] = img->rec[size_t(ci) * 4 + k];
+            // dense root row: entry c = compact record of ROOT's child for byte c; "no child" is an
+            // entry whose CHECK byte differs from the label
+            for (uint32_t c = 0; c < 256; ++c) {
+                const uint32_t ci = img->root_table[c];
+                if (ci == kRoot) {
+                    img->root4[c * 4 + 0] = (c ^ 1u) & 0xffu;
+                    continue;
+                }
+                for (int k = 0; k < 4; ++k) img->root4[c * 4 + k] = img->crec[size_t(ci) * 4 + k];
+            }
         }
     } else {
         for (size_t s = 0; s < n; ++s) {

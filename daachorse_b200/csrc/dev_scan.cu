@@ -73,30 +73,28 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_scan_std(ScanParams P) {
     QEntry* s_queue = reinterpret_cast<QEntry*>(smem_raw + kRoot4Bytes);  // [LANE_Q][blockDim.x]
     uint4* s_hot = reinterpret_cast<uint4*>(smem_raw + kRoot4Bytes + (size_t)LANE_Q * blockDim.x * sizeof(QEntry));
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_root4[i] = P.root4[i];
-    for (uint32_t i = threadIdx.x; i < P.hot_n; i += blockDim.x) s_hot[i] = P.rec[i];
+    for (uint32_t i = threadIdx.x; i < P.hot_n; i += blockDim.x) s_hot[i] = P.crec[i];
     __syncthreads();
 
     using M = StdMachine<MODE>;
-    const StdEnv Ev{P.rec, s_hot, P.hot_n, s_root4, P.text_end, P.root_opos, s_queue + threadIdx.x, blockDim.x};
+    const StdEnv Ev{P.crec,      s_hot,        P.hot_n,          s_root4, P.opos_tab, P.text_end, P.root_base, P.root_opos ? CF_OUT : 0u,
+                    s_queue + threadIdx.x, blockDim.x};
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     LaneStd L;
-    L.active = false;
-    L.done = false;
-    L.need_nw = false;
+    L.fl = 0;
     L.qn = 0;
-    L.kind = K_NONE;
     Emitter E;
     E.begin(0);
     bool exhausted = false;
     for (;;) {
         // ---- service phase (the warp is converged here) ----
-        if (L.active) M::drain(L, Ev, P, E);
-        if (L.active && L.done) {
+        if (L.fl & F_ACTIVE) M::drain(L, Ev, P, E);
+        if ((L.fl & (F_ACTIVE | F_DONE)) == (F_ACTIVE | F_DONE)) {
             E.finish(P);
-            L.active = false;
+            L.fl = 0;
         }
-        const bool need = !L.active && !exhausted;
+        const bool need = !(L.fl & F_ACTIVE) && !exhausted;
         const unsigned m = __ballot_sync(FULL, need);
         if (m) {
             const int leader = __ffs(m) - 1;
@@ -111,7 +109,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_scan_std(ScanParams P) {
                     exhausted = true;
             }
         }
-        if (!__any_sync(FULL, L.active)) break;
+        if (!__any_sync(FULL, (L.fl & F_ACTIVE) != 0)) break;
         // ---- lock-step iterations until some lane needs service ----
         bool stop = false;
         while (!stop) {
@@ -119,7 +117,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_scan_std(ScanParams P) {
 #pragma unroll 1
             for (int k = 0; k < TEXT_TOPUP; ++k) {
                 const bool ok = M::step(L, Ev);
-                if (__any_sync(FULL, !ok && L.active)) {
+                if (__any_sync(FULL, !ok && (L.fl & F_ACTIVE))) {
                     stop = true;
                     break;
                 }
@@ -292,6 +290,9 @@ struct dach_dev {
     uint4* d_outputs = nullptr;
     uint32_t* d_root = nullptr;
     uint4* d_root4 = nullptr;
+    uint4* d_crec = nullptr;
+    uint32_t* d_opos = nullptr;
+    uint32_t root_base = 0;
     uint32_t* d_mapper = nullptr;
     void* image_base = nullptr;
     size_t image_alloc = 0, l2_window = 0, l2_persist = 0;
@@ -415,6 +416,9 @@ int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, uint64_t text_byte
     P.outputs = d->d_outputs;
     P.root_table = d->d_root;
     P.root4 = d->d_root4;
+    P.crec = d->d_crec;
+    P.opos_tab = d->d_opos;
+    P.root_base = d->root_base;
     P.mapper = d->d_mapper;
     P.mapper_len = d->mapper_len;
     P.n_slots = d->n_slots;
@@ -434,7 +438,7 @@ int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, uint64_t text_byte
     const size_t smem_budget = std::min<size_t>(d->smem_optin, 227 * 1024) / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
     // the lane machine serves the bytewise Standard iterators; find_iter with an empty pattern
     // (it only reports zero-length matches, src/bytewise/iter.rs:60-85) keeps the simple kernel
-    const bool v1 = d->opt_kernel >= 1 && !d->charwise && mode != M_LEFTMOST && !(mode == M_FIND && d->root_opos != 0);
+    const bool v1 = d->opt_kernel >= 1 && d->d_crec && !d->charwise && mode != M_LEFTMOST && !(mode == M_FIND && d->root_opos != 0);
     const size_t front = v1 ? kRoot4Bytes + (size_t)LANE_Q * threads * sizeof(QEntry) : kRootBytes;
     uint64_t hot = smem_budget > front ? (smem_budget - front) / 16 : 0;
     if (d->opt_hot_records >= 0) hot = std::min<uint64_t>(hot, (uint64_t)d->opt_hot_records);
@@ -532,16 +536,16 @@ int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
     d->smem_optin = prop.sharedMemPerBlockOptin;
     // one allocation for the whole image (records | outputs | root rows | mapper), 256-byte aligned
     // parts, so that a single L2 access-policy window can cover it
-    const std::vector<uint32_t>* parts[5] = {&img.rec, &img.outputs, &img.root_table, &img.root4, &img.mapper};
-    size_t part_off[5], total = 0;
-    for (int i = 0; i < 5; ++i) {
+    const std::vector<uint32_t>* parts[7] = {&img.rec, &img.outputs, &img.root_table, &img.root4, &img.mapper, &img.crec, &img.opos_tab};
+    size_t part_off[7], total = 0;
+    for (int i = 0; i < 7; ++i) {
         part_off[i] = total;
         total += (std::max<size_t>(parts[i]->size() * 4, 16) + 255) & ~size_t(255);
         d->image_bytes += parts[i]->size() * 4;
     }
     bool ok = cuda_ok(cudaMalloc(&d->image_base, total), "cudaMalloc image");
     d->image_alloc = total;
-    for (int i = 0; ok && i < 5; ++i)
+    for (int i = 0; ok && i < 7; ++i)
         if (!parts[i]->empty())
             ok = cuda_ok(cudaMemcpy(static_cast<char*>(d->image_base) + part_off[i], parts[i]->data(), parts[i]->size() * 4,
                                     cudaMemcpyHostToDevice),
@@ -553,6 +557,11 @@ int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
         d->d_root = reinterpret_cast<uint32_t*>(b + part_off[2]);
         d->d_root4 = reinterpret_cast<uint4*>(b + part_off[3]);
         d->d_mapper = reinterpret_cast<uint32_t*>(b + part_off[4]);
+        if (!img.crec.empty()) {
+            d->d_crec = reinterpret_cast<uint4*>(b + part_off[5]);
+            d->d_opos = reinterpret_cast<uint32_t*>(b + part_off[6]);
+        }
+        d->root_base = img.root_base;
         // let the automaton persist in L2 while text and match streams pass through it
         d->l2_window = std::min<size_t>(total, (size_t)prop.accessPolicyMaxWindowSize);
         d->l2_persist = std::min<size_t>(d->l2_window, (size_t)prop.persistingL2CacheMaxSize);

@@ -79,7 +79,10 @@ struct ScanParams {
     const uint4* rec;
     const uint4* outputs;
     const uint32_t* root_table;  // global copy (kernels stage it in shared memory)
-    const uint4* root4;          // dense root row with the child records inlined (v1 kernels)
+    const uint4* root4;          // dense root row, compact records (lane-machine kernels)
+    const uint4* crec;           // compact records (lane-machine kernels), nullptr if > 2^24 slots
+    const uint32_t* opos_tab;    // output_pos per slot (lane-machine kernels)
+    uint32_t root_base;          // BASE of ROOT
     const uint32_t* mapper;
     uint32_t mapper_len;
     uint32_t n_slots;
@@ -505,61 +508,72 @@ DACH_HD void scan_leftmost(const ScanParams& P, const RecView& V, TextWin& T, Em
 // follow fail") leaves ~4 of 32 lanes active per issued instruction (profiles/r1_v0_summary.md);
 // here a lane that misses simply spends its next iteration on the next probe of the same byte.
 //
-//   kind = K_NONE    the lane sits in a state and needs the next byte
-//          K_PROBE   fetch rec[addr], addr = BASE ^ c; CHECK decides hit / miss
-//          K_LEARN   fetch rec[pend] to learn (efail, fbase) of a failure state whose probe missed
+// Compact record (automata with at most 2^24 slots), 16 bytes:
+//     w0 = BASE << 8 | CHECK                      src/bytewise.rs:1131-1137
+//     w1 = efail << 8 | flags                     flags: CF_OUT (state has an output list),
+//                                                        CF_F2ROOT (efail(efail) == ROOT)
+//     w2 = fbase << 8                             BASE of efail
+//     w3 = child signature: bit (c & 31) is set iff the state has a child labelled c
+// The signature answers "no child for this byte" without touching the child slot: on the C3
+// workload 0.31 of the 1.28 probes per byte were misses of the state's own children
+// ("Iteration statistics"); with it almost every fetch is a successful probe.
+// output_pos lives in a side table (opos[slot]) that only the drain phase reads.
 //
-// One iteration = [next byte] -> [one fetch] -> [fall: failure link / dense root row] -> [land].
-// There is exactly one "fall" site and one "land" site, so the divergent part of an iteration is
-// a handful of predicated instructions.  ROOT is represented as the record {0, ROOT, 0, opos<<8}:
-// "no children, fail to ROOT", which sends every byte through the dense root row.
+//   F_PROBE   fetch rec[addr], addr = BASE ^ c; CHECK decides hit / miss
+//   F_LEARN   fetch rec[pend] to learn (efail, fbase) of a failure state whose probe missed
+//   neither   the lane sits in a state and needs the next byte
+//
+// One iteration = [next byte] | [one fetch] | [fall: failure link / dense root row] | [land],
+// the four phases separated by warp barriers so that each runs once per iteration for all lanes
+// that need it.  ROOT is the record "no children, fail to ROOT", which sends every byte through
+// the dense root row (shared memory; entry c = record of ROOT's child for byte c).
 //
 // Matches are not expanded in the loop: a lane that lands on a state with an output list stores
-// (end, output_pos) in its shared-memory queue.  The warp drains all queues together (service
-// phase), so the output walk -- a divergent pointer chase -- runs with many lanes at once.
+// (end, slot) in its shared-memory queue.  The warp drains all queues together (service phase),
+// so the output walk -- a divergent pointer chase -- runs with many lanes at once.
 //
 // Text: two 16-byte register windows per lane (current, next).  Crossing into the next window is
 // four predicated moves; the load that re-arms `next` is issued on a warp-uniform schedule (every
-// TEXT_TOPUP iterations), which is early enough because a lane consumes at most one byte per
-// iteration.
+// TEXT_TOPUP iterations), early enough because a lane consumes at most one byte per iteration.
 // =============================================================================================
 
-constexpr uint32_t K_NONE = 0, K_PROBE = 1, K_LEARN = 2;
-constexpr int LANE_Q = 6;                     // queued output events per lane (shared memory)
-constexpr int TEXT_TOPUP = 8;                 // iterations between window top-ups (must be < 16)
-constexpr uint32_t F2ROOT_BIT = 0x80000000u;  // in record word 2: efail(efail(s)) == ROOT
+constexpr int LANE_Q = 6;      // queued output events per lane (shared memory)
+constexpr int TEXT_TOPUP = 8;  // iterations between window top-ups (must be < 16)
+constexpr uint32_t CF_OUT = 1u, CF_F2ROOT = 2u;  // flags in record word 1
+constexpr uint32_t COMPACT_MAX_SLOTS = 1u << 24;
+
+// lane flags
+constexpr uint32_t F_ACTIVE = 1u, F_DONE = 2u, F_NEED_NW = 4u, F_KNOW = 8u, F_PF2R = 16u, F_PROBE = 32u, F_LEARN = 64u,
+                   F_FALL = 128u;
 
 struct QEntry {
-    uint32_t end, opos;
+    uint32_t end, slot;
 };
 
 struct LaneStd {
-    // item
     const uint8_t* hay;
     uint32_t len, pos, item;
-    bool active, done;
-    // text windows
-    uint4 cw, nw;
-    bool need_nw;
-    // automaton
+    uint4 cw, nw;      // text windows
     uint32_t c;        // byte being matched
-    uint32_t cb;       // BASE to probe with (0: the state has no children)
-    uint32_t nf, nfb;  // where to fall on a miss, and its BASE | F2ROOT_BIT (valid if know)
-    uint32_t pend;     // failure state whose BASE is being probed (know == false)
-    bool know, pend_f2root;
-    uint32_t kind, addr;
-    // queue fill
-    uint32_t qn;
+    uint32_t cb;       // BASE of the current candidate state
+    uint32_t sig;      // its child signature
+    uint32_t nf, nfb;  // where to fall on a miss, and its BASE (valid if F_KNOW)
+    uint32_t pend;     // failure state whose BASE is being probed (!F_KNOW)
+    uint32_t addr;     // slot to fetch
+    uint32_t qn;       // queued events
+    uint32_t fl;       // F_* flags
 };
 
 struct StdEnv {
-    const uint4* glob;   // records in global memory
-    const uint4* hot;    // leading records in shared memory
+    const uint4* glob;     // compact records in global memory
+    const uint4* hot;      // leading records in shared memory
     uint32_t hot_n;
-    const uint4* root4;  // dense root row (shared memory): the record of ROOT's child per byte
+    const uint4* root4;    // dense root row (shared memory)
+    const uint32_t* opos;  // output_pos per slot (global)
     const uint8_t* text_end;
-    uint32_t root_opos;
-    QEntry* q;           // this lane's queue: entry j at q[j * q_stride]
+    uint32_t root_base;    // BASE of ROOT: the child for byte c sits in slot root_base ^ c
+    uint32_t root_flags;   // CF_OUT if ROOT has an output list (an empty pattern)
+    QEntry* q;             // this lane's queue: entry j at q[j * q_stride]
     uint32_t q_stride;
 };
 
@@ -584,6 +598,16 @@ DACH_HD uint4 ld_text16(const uint8_t* q, const uint8_t* text_end, const uint8_t
     return w;
 }
 
+#if defined(DACH_EMU)
+struct EmuStats {
+    unsigned long long steps, probes, hits, miss_known, miss_f2root, learns, root_falls, root_stay, sig_skips, pushes;
+};
+extern EmuStats g_emu_stats;
+#define DACH_STAT(f) (++g_emu_stats.f)
+#else
+#define DACH_STAT(f)
+#endif
+
 template <int MODE>
 struct StdMachine {
     static DACH_HD const uint8_t* block_of(const LaneStd& L) {
@@ -592,25 +616,27 @@ struct StdMachine {
 
     // warp-uniform schedule: re-arm the prefetched window of the lanes that crossed since last time
     static DACH_HD void text_topup(LaneStd& L, const StdEnv& Ev, const uint8_t* emu_lo) {
-        if (L.active && L.need_nw) {
+        if ((L.fl & (F_ACTIVE | F_NEED_NW)) == (F_ACTIVE | F_NEED_NW)) {
             L.nw = ld_text16(block_of(L) + 16, Ev.text_end, emu_lo);
-            L.need_nw = false;
+            L.fl &= ~F_NEED_NW;
         }
     }
 
     // One iteration, called by all 32 lanes of the warp together.  Returns false if the lane did
-    // not step (inactive, finished, or queue full).  The four phases are separated by warp
-    // barriers so that every phase is executed once per iteration by all the lanes that need it
-    // (without them the compiler threads the lanes through the phases in separate passes).
+    // not step (inactive, finished, or queue full).  Phase order: next byte -> failure link ->
+    // fetch -> land.  A fetch that misses (rare once the signature filters the probes) leaves
+    // F_FALL set and takes its failure link at the start of the next iteration.
     static DACH_HD bool step(LaneStd& L, const StdEnv& Ev) {
-        bool run = L.active && !L.done && L.qn != LANE_Q;
-        bool do_fall = false, landed = false;
-        uint4 r;  // record the lane lands on
+        bool run = (L.fl & (F_ACTIVE | F_DONE)) == F_ACTIVE && L.qn != (uint32_t)LANE_Q;
+        if (run) DACH_STAT(steps);
+        bool landed = false;
+        uint4 r;            // record the lane lands on
+        uint32_t slot = 0;  // and its slot
         r.x = r.y = r.z = r.w = 0;
         // ---- phase 1: next byte ------------------------------------------------------------------
-        if (run && L.kind == K_NONE) {
+        if (run && (L.fl & (F_PROBE | F_LEARN | F_FALL)) == 0) {
             if (L.pos >= L.len) {
-                L.done = true;
+                L.fl |= F_DONE;
                 run = false;
             } else {
                 const uint32_t o = ((uint32_t)(uintptr_t)L.hay + L.pos) & 15u;
@@ -619,85 +645,97 @@ struct StdMachine {
                 const uint32_t word = (o & 4u) ? hi : lo;
                 L.c = (word >> ((o & 3u) * 8u)) & 0xffu;
                 L.addr = L.cb ^ L.c;
-                if (L.cb != 0)
-                    L.kind = K_PROBE;
-                else
-                    do_fall = true;
-            }
-        }
-        DACH_SYNCWARP();
-        // ---- phase 2: the one record fetch ---------------------------------------------------------
-        if (run && L.kind != K_NONE) {
-            const uint32_t a = L.addr;
-            const uint4 x = a < Ev.hot_n ? Ev.hot[a] : ld_u4(Ev.glob + a);
-            if (L.kind == K_PROBE) {
-                if ((x.w & 0xffu) == L.c) {
-                    landed = true;
-                    r = x;
-                } else if (L.know) {
-                    do_fall = true;
-                } else if (L.pend_f2root) {
-                    L.nf = D_ROOT;
-                    L.know = true;
-                    do_fall = true;
+                if ((L.sig >> (L.c & 31u)) & 1u) {
+                    L.fl |= F_PROBE;
                 } else {
-                    L.kind = K_LEARN;
-                    L.addr = L.pend;
+                    DACH_STAT(sig_skips);
+                    L.fl |= F_FALL;  // certainly no child for this byte
                 }
-            } else {  // K_LEARN
-                L.nf = x.y;
-                L.nfb = x.z;
-                L.know = true;
-                do_fall = true;
             }
         }
         DACH_SYNCWARP();
-        // ---- phase 3: take the failure link (nf, nfb are known) -------------------------------------
-        if (do_fall) {
+        // ---- phase 2: take the failure link (nf, nfb are known) -------------------------------------
+        if (run && (L.fl & F_FALL)) {
+            L.fl &= ~F_FALL;
             if (L.nf == D_ROOT) {
+                DACH_STAT(root_falls);
                 r = Ev.root4[L.c];  // dense ROOT row (src/bytewise.rs:1067-1069)
+                slot = Ev.root_base ^ L.c;
                 landed = true;
-                if ((r.w & 0xffu) != L.c) {  // no child: stay in ROOT
+                if ((r.x & 0xffu) != L.c) {  // no child: stay in ROOT
+                    DACH_STAT(root_stay);
                     r.x = 0;
-                    r.y = D_ROOT;
+                    r.y = Ev.root_flags;  // efail = ROOT
                     r.z = 0;
-                    r.w = Ev.root_opos << 8;
+                    r.w = 0;
+                    slot = D_ROOT;
                 }
             } else {
-                L.cb = L.nfb & ~F2ROOT_BIT;
+                L.cb = L.nfb;
                 L.pend = L.nf;
-                L.pend_f2root = (L.nfb & F2ROOT_BIT) != 0;
-                L.know = false;
-                L.kind = K_PROBE;
-                L.addr = L.cb ^ L.c;
+                L.fl = (L.fl & ~F_KNOW) | F_PROBE;  // F_PF2R already describes `pend`
+                L.addr = L.nfb ^ L.c;
+            }
+        }
+        DACH_SYNCWARP();
+        // ---- phase 3: the one record fetch ---------------------------------------------------------
+        if (run && !landed && (L.fl & (F_PROBE | F_LEARN)) != 0) {
+            const uint32_t a = L.addr;
+            const uint4 x = a < Ev.hot_n ? Ev.hot[a] : ld_u4(Ev.glob + a);
+            if (L.fl & F_PROBE) {
+                DACH_STAT(probes);
+                if ((x.x & 0xffu) == L.c) {
+                    DACH_STAT(hits);
+                    landed = true;
+                    r = x;
+                    slot = a;
+                } else if (L.fl & F_KNOW) {
+                    DACH_STAT(miss_known);
+                    L.fl = (L.fl & ~F_PROBE) | F_FALL;
+                } else if (L.fl & F_PF2R) {
+                    DACH_STAT(miss_f2root);
+                    L.nf = D_ROOT;
+                    L.fl = (L.fl & ~F_PROBE) | F_KNOW | F_FALL;
+                } else {
+                    L.fl = (L.fl & ~F_PROBE) | F_LEARN;
+                    L.addr = L.pend;
+                }
+            } else {  // F_LEARN: x is the record of `pend`
+                DACH_STAT(learns);
+                L.nf = x.y >> 8;
+                L.nfb = x.z >> 8;
+                L.fl = (L.fl & ~(F_LEARN | F_PF2R)) | F_KNOW | F_FALL | ((x.y & CF_F2ROOT) ? F_PF2R : 0u);
             }
         }
         DACH_SYNCWARP();
         // ---- phase 4: land (the byte is consumed; the lane sits in the state described by r) ---------
         if (landed) {
             ++L.pos;
+            uint32_t fl = (L.fl & ~(F_PROBE | F_LEARN | F_FALL | F_PF2R)) | F_KNOW | ((r.y & CF_F2ROOT) ? F_PF2R : 0u);
             if ((((uint32_t)(uintptr_t)L.hay + L.pos) & 15u) == 0) {  // crossed into the next window
                 L.cw = L.nw;
-                L.need_nw = true;
+                fl |= F_NEED_NW;
             }
-            L.cb = r.x;
-            L.nf = r.y;
-            L.nfb = r.z;
-            L.know = true;
-            L.kind = K_NONE;
-            const uint32_t opos = r.w >> 8;
-            if (opos != 0) {
+            L.cb = r.x >> 8;
+            L.nf = r.y >> 8;
+            L.nfb = r.z >> 8;
+            L.sig = r.w;
+            if (r.y & CF_OUT) {
+                DACH_STAT(pushes);
                 QEntry e;
                 e.end = L.pos;
-                e.opos = opos;
+                e.slot = slot;
                 Ev.q[L.qn * Ev.q_stride] = e;
                 ++L.qn;
                 if (MODE == M_FIND) {  // every next() restarts at ROOT (src/bytewise/iter.rs:87)
                     L.cb = 0;
+                    L.sig = 0;
                     L.nf = D_ROOT;
                     L.nfb = 0;
+                    fl &= ~F_PF2R;
                 }
             }
+            L.fl = fl;
         }
         return run;
     }
@@ -707,10 +745,11 @@ struct StdMachine {
         for (uint32_t j = 0; j < (uint32_t)LANE_Q; ++j) {
             if (j < L.qn) {
                 const QEntry e = Ev.q[j * Ev.q_stride];
+                const uint32_t op = ld_u32(Ev.opos + e.slot);
                 if (MODE == M_OVERLAPPING)
-                    emit_chain(P, E, e.opos, e.end);
+                    emit_chain(P, E, op, e.end);
                 else
-                    emit_head(P, E, e.opos, e.end);
+                    emit_head(P, E, op, e.end);
             }
         }
         L.qn = 0;
@@ -723,25 +762,22 @@ struct StdMachine {
         L.len = (uint32_t)(o1 - o0);
         L.pos = 0;
         L.item = (uint32_t)item;
-        L.active = true;
-        L.done = false;
         L.qn = 0;
         E.begin((uint32_t)item);
         const uint8_t* b0 = block_of(L);
         L.cw = ld_text16(b0, Ev.text_end, emu_lo);
         L.nw = ld_text16(b0 + 16, Ev.text_end, emu_lo);
-        L.need_nw = false;
         // the iterator starts in ROOT with ROOT's output list pending at position 0
         // (src/bytewise.rs:303-313; no-suffix variant: src/bytewise/iter.rs:196-216)
         L.cb = 0;
+        L.sig = 0;
         L.nf = D_ROOT;
         L.nfb = 0;
-        L.know = true;
-        L.kind = K_NONE;
-        if (MODE != M_FIND && Ev.root_opos != 0) {
+        L.fl = F_ACTIVE | F_KNOW;
+        if (MODE != M_FIND && (Ev.root_flags & CF_OUT)) {
             QEntry e;
             e.end = 0;
-            e.opos = Ev.root_opos;
+            e.slot = D_ROOT;
             Ev.q[0] = e;
             L.qn = 1;
         }

@@ -14,6 +14,14 @@
 
 using namespace dach;
 
+namespace dach {
+EmuStats g_emu_stats;
+}
+extern "C" void emu_stats(unsigned long long* out, int reset) {
+    memcpy(out, &g_emu_stats, sizeof(g_emu_stats));
+    if (reset) memset(&g_emu_stats, 0, sizeof(g_emu_stats));
+}
+
 template <bool CW, int MODE>
 static void run_items(const ScanParams& P, const RecView& V, const uint8_t* lo, const uint8_t* hi) {
     for (uint64_t item = 0; item < P.n_items; ++item) {
@@ -49,11 +57,8 @@ static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* 
     for (auto& w : warps) {
         w.queue.assign((size_t)LANE_Q * 32, QEntry{0, 0});
         for (int l = 0; l < 32; ++l) {
-            w.L[l].active = false;
-            w.L[l].done = false;
-            w.L[l].need_nw = false;
+            w.L[l].fl = 0;
             w.L[l].qn = 0;
-            w.L[l].kind = K_NONE;
             w.E[l].begin(0);
             w.exhausted[l] = false;
             w.Ev[l] = Ev0;
@@ -69,15 +74,15 @@ static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* 
         for (auto& w : warps) {
             if (w.finished) continue;
             for (int l = 0; l < 32; ++l)
-                if (w.L[l].active) M::drain(w.L[l], w.Ev[l], P, w.E[l]);
+                if (w.L[l].fl & F_ACTIVE) M::drain(w.L[l], w.Ev[l], P, w.E[l]);
             for (int l = 0; l < 32; ++l)
-                if (w.L[l].active && w.L[l].done) {
+                if ((w.L[l].fl & (F_ACTIVE | F_DONE)) == (F_ACTIVE | F_DONE)) {
                     w.E[l].finish(P);
-                    w.L[l].active = false;
+                    w.L[l].fl = 0;
                 }
             unsigned m = 0;
             for (int l = 0; l < 32; ++l)
-                if (!w.L[l].active && !w.exhausted[l]) m |= 1u << l;
+                if (!(w.L[l].fl & F_ACTIVE) && !w.exhausted[l]) m |= 1u << l;
             if (m) {
                 unsigned long long base = P.ctrl->next_item;
                 P.ctrl->next_item += __builtin_popcount(m);
@@ -91,7 +96,7 @@ static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* 
                     }
             }
             bool any_active = false;
-            for (int l = 0; l < 32; ++l) any_active |= w.L[l].active;
+            for (int l = 0; l < 32; ++l) any_active |= (w.L[l].fl & F_ACTIVE) != 0;
             if (!any_active) {
                 w.finished = true;
                 continue;
@@ -104,7 +109,7 @@ static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* 
                     bool need_service = false;
                     for (int l = 0; l < 32; ++l) {
                         const bool ok = M::step(w.L[l], w.Ev[l]);
-                        if (!ok && w.L[l].active) need_service = true;
+                        if (!ok && (w.L[l].fl & F_ACTIVE)) need_service = true;
                     }
                     if (need_service) stop = true;
                 }
@@ -158,9 +163,12 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     RecView V{P.rec, reinterpret_cast<const uint4*>(hot.data()), hot_n, img.root_table.data()};
     const uint8_t* lo = text + (n ? offs[0] : 0);
     const uint8_t* hi = text + (n ? offs[n] : 0);
-    const bool v1 = kernel_version >= 1 && !charwise && mode != M_LEFTMOST && !(mode == M_FIND && img.root_opos != 0);
+    const bool v1 = kernel_version >= 1 && !img.crec.empty() && !charwise && mode != M_LEFTMOST && !(mode == M_FIND && img.root_opos != 0);
     if (v1) {
-        const StdEnv Ev{P.rec, reinterpret_cast<const uint4*>(hot.data()), hot_n, P.root4, P.text_end, P.root_opos, nullptr, 0};
+        std::vector<uint32_t> chot(img.crec.begin(), img.crec.begin() + (size_t)hot_n * 4);
+        chot.resize(chot.size() + 4);
+        const StdEnv Ev{reinterpret_cast<const uint4*>(img.crec.data()), reinterpret_cast<const uint4*>(chot.data()), hot_n, P.root4,
+                        img.opos_tab.data(), P.text_end, img.root_base, P.root_opos ? CF_OUT : 0u, nullptr, 0};
         const int n_warps = 3;
         if (mode == M_FIND) run_items_v1<M_FIND>(P, Ev, lo, n_warps);
         if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING>(P, Ev, lo, n_warps);
