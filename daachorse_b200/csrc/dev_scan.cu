@@ -303,7 +303,10 @@ struct dach_dev {
     HostPinned* pinned = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // options
-    int64_t opt_hot_records = -1;  // -1: as many as fit
+    // Leading records staged in shared memory: -1 = as many as fit, 0 = none.  Default 0: in the
+    // reference's slot order the first slots are not the hot ones and L1 caches the hot states
+    // better on its own (profiles/r1_v1_summary.md: 116 vs 76 GB/s).
+    int64_t opt_hot_records = 0;
     int64_t opt_threads = 1024;
     int64_t opt_ctas_per_sm = 1;
     int64_t opt_l2_persist = 1;  // 1: access-policy window over the image during the scan kernel
@@ -340,23 +343,46 @@ cudaError_t launch_scan_t(const ScanParams& P, int grid, int threads, size_t sme
     return cudaGetLastError();
 }
 
+struct L2Window {
+    void* base = nullptr;
+    size_t bytes = 0;
+    float hit_ratio = 1.0f;
+};
+
 template <int MODE>
-cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
+cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k_scan_std<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    k_scan_std<MODE><<<grid, threads, smem, st>>>(P);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    if (w.bytes) {
+        // keep the automaton image resident in L2 while text and match blocks stream through it
+        at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        at[0].val.accessPolicyWindow.base_ptr = w.base;
+        at[0].val.accessPolicyWindow.num_bytes = w.bytes;
+        at[0].val.accessPolicyWindow.hitRatio = w.hit_ratio;
+        at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, k_scan_std<MODE>, P);
 }
 
-cudaError_t launch_std(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
+cudaError_t launch_std(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
     switch (mode) {
-        case M_FIND: return launch_std_t<M_FIND>(P, grid, threads, smem, st);
-        case M_OVERLAPPING: return launch_std_t<M_OVERLAPPING>(P, grid, threads, smem, st);
-        case M_NO_SUFFIX: return launch_std_t<M_NO_SUFFIX>(P, grid, threads, smem, st);
+        case M_FIND: return launch_std_t<M_FIND>(P, grid, threads, smem, st, w);
+        case M_OVERLAPPING: return launch_std_t<M_OVERLAPPING>(P, grid, threads, smem, st, w);
+        case M_NO_SUFFIX: return launch_std_t<M_NO_SUFFIX>(P, grid, threads, smem, st, w);
     }
     return cudaErrorInvalidValue;
 }
@@ -448,28 +474,18 @@ int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, uint64_t text_byte
     const int grid = d->sm_count * ctas_per_sm;
 
     if (!cuda_ok(cudaMemsetAsync(d->ctrl.p, 0, sizeof(ScanCtrl), st), "memset ctrl")) return DACH_CUDA_ERROR;
-    const bool window = d->opt_l2_persist && d->l2_persist > 0;
-    if (window) {
-        cudaStreamAttrValue av;
-        memset(&av, 0, sizeof(av));
-        av.accessPolicyWindow.base_ptr = d->image_base;
-        av.accessPolicyWindow.num_bytes = d->l2_window;
-        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)d->l2_persist / (double)d->l2_window);
-        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+    L2Window win;
+    if (d->opt_l2_persist && d->l2_persist > 0 && v1) {
+        // the lane-machine kernels touch the compact records, the opos table and the outputs
+        win.base = d->d_outputs;
+        win.bytes = std::min<size_t>(d->l2_window, (size_t)((char*)d->image_base + d->image_alloc - (char*)d->d_outputs));
+        win.hit_ratio = (float)std::min(1.0, (double)d->l2_persist / (double)win.bytes);
     }
     cudaEventRecord(d->ev[0], st);
-    if (!cuda_ok(v1 ? launch_std(mode, P, grid, threads, smem, st) : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
+    if (!cuda_ok(v1 ? launch_std(mode, P, grid, threads, smem, st, win) : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
                  "k_scan launch"))
         return DACH_CUDA_ERROR;
     cudaEventRecord(d->ev[1], st);
-    if (window) {
-        cudaStreamAttrValue av;
-        memset(&av, 0, sizeof(av));
-        av.accessPolicyWindow.num_bytes = 0;
-        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
-    }
     unsigned long long* offs64 = reinterpret_cast<unsigned long long*>(d_out_offs);
     unsigned long long* tiles = static_cast<unsigned long long*>(d->tiles.p);
     k_offsets_tile_sums<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n, tiles);

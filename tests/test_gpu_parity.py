@@ -131,14 +131,17 @@ def test_kernel_options_do_not_change_results():
     pats, text, offs = _random_case(rng, False, False)
     pma = D.DoubleArrayAhoCorasick.new(pats)
     base = pma.scan_batch_host(D.FIND_OVERLAPPING, text, offs)
-    for opts in ({"hot_records": 0}, {"hot_records": 17}, {"threads": 128}, {"threads": 512, "ctas_per_sm": 2}):
+    for opts in ({"hot_records": -1}, {"hot_records": 17}, {"threads": 128}, {"threads": 512, "ctas_per_sm": 2},
+                 {"kernel": 0}, {"kernel": 0, "hot_records": 100}, {"l2_persist": 0}):
         for k, v in opts.items():
             pma.set_option(k, v)
         r = pma.scan_batch_host(D.FIND_OVERLAPPING, text, offs)
         assert r.matches.tobytes() == base.matches.tobytes() and np.array_equal(r.offsets, base.offsets)
-        pma.set_option("hot_records", -1)
+        pma.set_option("hot_records", 0)
         pma.set_option("threads", 1024)
         pma.set_option("ctas_per_sm", 1)
+        pma.set_option("kernel", 1)
+        pma.set_option("l2_persist", 1)
 
 
 def test_overflow_protocol_through_the_c_abi():
