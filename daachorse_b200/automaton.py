@@ -246,29 +246,37 @@ class _Automaton:
             raise AssertionError("Error: match_kind must be %s." % ("standard" if lm else "leftmost"))
 
     # -- batch scans ----------------------------------------------------------------------------
-    def scan_batch_host(self, mode, text, offs, out_cap=None, device=None):
-        """Host buffers in, host buffers out (numpy).  ``text`` uint8, ``offs`` uint64 (n+1)."""
+    def scan_batch_host(self, mode, text, offs, out_cap=None, device=None, out=None, out_offs=None):
+        """Host buffers in, host buffers out (numpy).  ``text`` uint8, ``offs`` uint64 (n+1).
+        ``out`` (MATCH_DTYPE) / ``out_offs`` (uint64, n+1) may be preallocated -- e.g. views of pinned
+        memory -- to keep allocation and page faults out of the call."""
         self._assert_mode(mode)
         L = _lib.load()
         d = self.device_handle(device)
         text = np.ascontiguousarray(text, dtype=np.uint8)
         offs = np.ascontiguousarray(offs, dtype=np.uint64)
         n = len(offs) - 1
-        cap = int(out_cap) if out_cap else max(1024, int(text.size // 8))
-        while True:
-            out = np.empty(cap, dtype=MATCH_DTYPE)
+        if out is not None:
+            cap = len(out)
+        else:
+            cap = int(out_cap) if out_cap else max(1024, int(text.size // 8))
+        if out_offs is None:
             out_offs = np.empty(n + 1, dtype=np.uint64)
+        while True:
+            if out is None or len(out) < cap:
+                out = np.empty(cap, dtype=MATCH_DTYPE)
             need = C.c_uint64()
             rc = L.dach_scan_batch_host(d, mode, _ptr(text), C.c_void_p(offs.ctypes.data), n,
-                                        C.c_void_p(out.ctypes.data), cap, C.c_void_p(out_offs.ctypes.data),
+                                        C.c_void_p(out.ctypes.data), len(out), C.c_void_p(out_offs.ctypes.data),
                                         C.byref(need))
             if rc == _lib.OUTPUT_OVERFLOW:
-                if int(need.value) <= cap:
-                    raise DaachorseError(rc, "overflow reported although capacity %d >= needed %d" % (cap, need.value))
+                if int(need.value) <= len(out):
+                    raise DaachorseError(rc, "overflow reported although capacity %d >= needed %d" % (len(out), need.value))
                 cap = int(need.value)
+                out = None
                 continue
             _check(rc)
-            return BatchResult(out[: need.value], out_offs)
+            return BatchResult(out[: need.value], out_offs[: n + 1])
 
     def scan_batch_device(self, mode, text, offs, out=None, out_offs=None, stream=None):
         """Device-resident scan.  ``text`` (uint8) and ``offs`` (int64/uint64, n+1) are CUDA torch

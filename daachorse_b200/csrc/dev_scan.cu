@@ -17,6 +17,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "dev_image.h"
 #include "host.h"
@@ -275,6 +276,42 @@ struct HostPinned {
     ScanCtrl ctrl;
 };
 
+// Everything one in-flight scan needs besides the automaton image.
+struct Workspace {
+    DevBuf counts, tiles, ctrl, pool;
+    HostPinned* pinned = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // host-batch slices only: device staging and the slice's stream
+    DevBuf text, offs, out, out_offs;
+    cudaStream_t stream = nullptr;
+    bool init(bool with_stream) {
+        if (!pinned && !cuda_ok(cudaMallocHost(reinterpret_cast<void**>(&pinned), sizeof(HostPinned)), "cudaMallocHost"))
+            return false;
+        for (int i = 0; i < 3; ++i)
+            if (!ev[i] && !cuda_ok(cudaEventCreate(&ev[i]), "cudaEventCreate")) return false;
+        if (with_stream && !stream && !cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate"))
+            return false;
+        return true;
+    }
+    void release() {
+        for (DevBuf* b : {&counts, &tiles, &ctrl, &pool, &text, &offs, &out, &out_offs})
+            if (b->p) {
+                cudaFree(b->p);
+                b->p = nullptr;
+                b->bytes = 0;
+            }
+        if (pinned) cudaFreeHost(pinned);
+        pinned = nullptr;
+        for (int i = 0; i < 3; ++i)
+            if (ev[i]) {
+                cudaEventDestroy(ev[i]);
+                ev[i] = nullptr;
+            }
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+};
+
 }  // namespace
 
 struct dach_dev {
@@ -298,10 +335,9 @@ struct dach_dev {
     size_t image_alloc = 0, l2_window = 0, l2_persist = 0;
     // workspace (guarded by mu)
     std::mutex mu;
-    DevBuf counts, tiles, ctrl, pool;
-    DevBuf h_text, h_offs, h_out, h_out_offs;  // device staging for dach_scan_batch_host
-    HostPinned* pinned = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    Workspace ws;        // dach_dev_scan_batch
+    Workspace slot[3];   // dach_scan_batch_host: slices in flight (H2D | scan | D2H)
+    int64_t opt_slice_mib = 64;
     // options
     // Leading records staged in shared memory: -1 = as many as fit, 0 = none.  Default 0: in the
     // reference's slot order the first slots are not the hot ones and L1 caches the hot states
@@ -415,8 +451,8 @@ int check_mode(const dach_dev* d, int mode) {
 }
 
 // the device-side pipeline; caller holds d->mu and has set the device
-int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, uint64_t text_bytes, const uint64_t* d_offs, uint64_t n,
-                dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs, uint64_t* needed, cudaStream_t st) {
+int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, uint64_t text_bytes, const uint64_t* d_offs,
+                uint64_t n, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs, uint64_t* needed, cudaStream_t st) {
     if (n > 0xfffffff0ull) {
         set_error("too many haystacks in one batch (max 2^32-16)");
         return DACH_INVALID_ARGUMENT;
@@ -432,8 +468,8 @@ int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, uint64_t text_byte
     uint64_t pool_blocks64 = out_cap / BLK_MATCHES + n + 1024;
     if (pool_blocks64 > 0xffffff00ull) pool_blocks64 = 0xffffff00ull;
     const uint32_t pool_blocks = (uint32_t)pool_blocks64;
-    if (!ensure(d->counts, n * 4) || !ensure(d->tiles, n_tiles * 8) || !ensure(d->ctrl, sizeof(ScanCtrl)) ||
-        !ensure(d->pool, (size_t)pool_blocks * BLK_WORDS * 4))
+    if (!ensure(W.counts, n * 4) || !ensure(W.tiles, n_tiles * 8) || !ensure(W.ctrl, sizeof(ScanCtrl)) ||
+        !ensure(W.pool, (size_t)pool_blocks * BLK_WORDS * 4))
         return DACH_CUDA_ERROR;
 
     ScanParams P;
@@ -453,10 +489,10 @@ int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, uint64_t text_byte
     P.text_end = d_text + text_bytes;
     P.offs = d_offs;
     P.n_items = n;
-    P.counts = static_cast<uint32_t*>(d->counts.p);
-    P.pool = static_cast<uint32_t*>(d->pool.p);
+    P.counts = static_cast<uint32_t*>(W.counts.p);
+    P.pool = static_cast<uint32_t*>(W.pool.p);
     P.pool_blocks = pool_blocks;
-    P.ctrl = static_cast<ScanCtrl*>(d->ctrl.p);
+    P.ctrl = static_cast<ScanCtrl*>(W.ctrl.p);
 
     int threads = (int)std::min<int64_t>(std::max<int64_t>(d->opt_threads, 32), kMaxThreads);
     threads = (threads / 32) * 32;
@@ -473,7 +509,7 @@ int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, uint64_t text_byte
     const size_t smem = front + (size_t)hot * 16;
     const int grid = d->sm_count * ctas_per_sm;
 
-    if (!cuda_ok(cudaMemsetAsync(d->ctrl.p, 0, sizeof(ScanCtrl), st), "memset ctrl")) return DACH_CUDA_ERROR;
+    if (!cuda_ok(cudaMemsetAsync(W.ctrl.p, 0, sizeof(ScanCtrl), st), "memset ctrl")) return DACH_CUDA_ERROR;
     L2Window win;
     if (d->opt_l2_persist && d->l2_persist > 0 && v1) {
         // the lane-machine kernels touch the compact records, the opos table and the outputs
@@ -481,13 +517,13 @@ int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, uint64_t text_byte
         win.bytes = std::min<size_t>(d->l2_window, (size_t)((char*)d->image_base + d->image_alloc - (char*)d->d_outputs));
         win.hit_ratio = (float)std::min(1.0, (double)d->l2_persist / (double)win.bytes);
     }
-    cudaEventRecord(d->ev[0], st);
+    cudaEventRecord(W.ev[0], st);
     if (!cuda_ok(v1 ? launch_std(mode, P, grid, threads, smem, st, win) : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
                  "k_scan launch"))
         return DACH_CUDA_ERROR;
-    cudaEventRecord(d->ev[1], st);
+    cudaEventRecord(W.ev[1], st);
     unsigned long long* offs64 = reinterpret_cast<unsigned long long*>(d_out_offs);
-    unsigned long long* tiles = static_cast<unsigned long long*>(d->tiles.p);
+    unsigned long long* tiles = static_cast<unsigned long long*>(W.tiles.p);
     k_offsets_tile_sums<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n, tiles);
     k_offsets_scan_tiles<<<1, kScanThreads, 0, st>>>(tiles, n_tiles);
     k_offsets_apply<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n, tiles, offs64);
@@ -496,20 +532,20 @@ int scan_locked(dach_dev* d, int mode, const uint8_t* d_text, uint64_t text_byte
                                          reinterpret_cast<uint32_t*>(d_out));
     d->launches += 5;
     if (!cuda_ok(cudaGetLastError(), "kernel launch")) return DACH_CUDA_ERROR;
-    cudaEventRecord(d->ev[2], st);
-    cudaMemcpyAsync(&d->pinned->total, offs64 + n, 8, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(&d->pinned->ctrl, d->ctrl.p, sizeof(ScanCtrl), cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(W.ev[2], st);
+    cudaMemcpyAsync(&W.pinned->total, offs64 + n, 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&W.pinned->ctrl, W.ctrl.p, sizeof(ScanCtrl), cudaMemcpyDeviceToHost, st);
     if (!cuda_ok(cudaStreamSynchronize(st), "scan pipeline")) return DACH_CUDA_ERROR;
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]) == cudaSuccess) d->last_scan_ms = ms;
-    if (cudaEventElapsedTime(&ms, d->ev[0], d->ev[2]) == cudaSuccess) d->last_total_ms = ms;
-    const uint64_t total = d->pinned->total;
+    if (cudaEventElapsedTime(&ms, W.ev[0], W.ev[1]) == cudaSuccess) d->last_scan_ms = ms;
+    if (cudaEventElapsedTime(&ms, W.ev[0], W.ev[2]) == cudaSuccess) d->last_total_ms = ms;
+    const uint64_t total = W.pinned->total;
     if (needed) *needed = total;
-    if (d->pinned->ctrl.overflow || total > out_cap) {
+    if (W.pinned->ctrl.overflow || total > out_cap) {
         char buf[256];
         snprintf(buf, sizeof(buf), "output capacity too small (needed %llu, out_cap %llu, pool blocks used %u of %u, overflow flag %u)",
-                 (unsigned long long)total, (unsigned long long)out_cap, d->pinned->ctrl.blk_cursor, pool_blocks,
-                 d->pinned->ctrl.overflow);
+                 (unsigned long long)total, (unsigned long long)out_cap, W.pinned->ctrl.blk_cursor, pool_blocks,
+                 W.pinned->ctrl.overflow);
         set_error(buf);
         return DACH_OUTPUT_OVERFLOW;
     }
@@ -584,8 +620,7 @@ int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
         if (d->l2_persist) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, d->l2_persist);
         cudaGetLastError();
     }
-    ok = ok && cuda_ok(cudaMallocHost(reinterpret_cast<void**>(&d->pinned), sizeof(HostPinned)), "cudaMallocHost");
-    for (int i = 0; ok && i < 4; ++i) ok = cuda_ok(cudaEventCreate(&d->ev[i]), "cudaEventCreate");
+    ok = ok && d->ws.init(false);
     if (!ok) {
         dach_dev_free(d.release());
         return DACH_CUDA_ERROR;
@@ -598,11 +633,8 @@ void dach_dev_free(dach_dev* d) {
     if (!d) return;
     DeviceGuard g(d->device);
     cudaFree(d->image_base);
-    for (DevBuf* b : {&d->counts, &d->tiles, &d->ctrl, &d->pool, &d->h_text, &d->h_offs, &d->h_out, &d->h_out_offs})
-        if (b->p) cudaFree(b->p);
-    if (d->pinned) cudaFreeHost(d->pinned);
-    for (int i = 0; i < 4; ++i)
-        if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+    d->ws.release();
+    for (Workspace& w : d->slot) w.release();
     delete d;
 }
 
@@ -620,7 +652,7 @@ int dach_dev_scan_batch(dach_dev* d, int mode, const uint8_t* d_text, const uint
     std::lock_guard<std::mutex> lk(d->mu);
     DeviceGuard g(d->device);
     if (!g.ok) return DACH_CUDA_ERROR;
-    return scan_locked(d, mode, d_text, text_bytes, d_offs, n, d_out, out_cap, d_out_offs, needed, static_cast<cudaStream_t>(stream));
+    return scan_locked(d, d->ws, mode, d_text, text_bytes, d_offs, n, d_out, out_cap, d_out_offs, needed, static_cast<cudaStream_t>(stream));
 }
 
 int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint64_t* offs, uint64_t n,
@@ -634,32 +666,110 @@ int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint6
     std::lock_guard<std::mutex> lk(d->mu);
     DeviceGuard g(d->device);
     if (!g.ok) return DACH_CUDA_ERROR;
-    const uint64_t text_bytes = offs[n] - offs[0];
-    if (!ensure(d->h_text, text_bytes + 16) || !ensure(d->h_offs, (n + 1) * 8) || !ensure(d->h_out, out_cap * 12 + 16) ||
-        !ensure(d->h_out_offs, (n + 1) * 8))
-        return DACH_CUDA_ERROR;
-    cudaStream_t st = nullptr;
-    // offsets are passed through unchanged: the text is copied from its first used byte so
-    // that offs[0] may be non-zero
-    const uint8_t* src = text ? text + offs[0] : nullptr;
-    if (text_bytes && !cuda_ok(cudaMemcpyAsync(d->h_text.p, src, text_bytes, cudaMemcpyHostToDevice, st), "H2D text"))
-        return DACH_CUDA_ERROR;
-    if (!cuda_ok(cudaMemcpyAsync(d->h_offs.p, offs, (n + 1) * 8, cudaMemcpyHostToDevice, st), "H2D offsets"))
-        return DACH_CUDA_ERROR;
-    const uint8_t* d_text = static_cast<const uint8_t*>(d->h_text.p) - offs[0];
-    uint64_t total = 0;
-    rc = scan_locked(d, mode, d_text, offs[0] + text_bytes, static_cast<const uint64_t*>(d->h_offs.p), n,
-                     static_cast<dach_match*>(d->h_out.p), out_cap, static_cast<uint64_t*>(d->h_out_offs.p), &total, st);
-    if (needed) *needed = total;
-    d->last_h2d = text_bytes + (n + 1) * 8;
-    d->last_d2h = 0;
-    if (rc) return rc;
-    if (!cuda_ok(cudaMemcpyAsync(out_offs, d->h_out_offs.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H offsets"))
-        return DACH_CUDA_ERROR;
-    if (total && !cuda_ok(cudaMemcpyAsync(out, d->h_out.p, total * 12, cudaMemcpyDeviceToHost, st), "D2H matches"))
-        return DACH_CUDA_ERROR;
-    if (!cuda_ok(cudaStreamSynchronize(st), "D2H")) return DACH_CUDA_ERROR;
-    d->last_d2h = (n + 1) * 8 + total * 12;
+    d->last_h2d = d->last_d2h = 0;
+    if (n == 0) {
+        out_offs[0] = 0;
+        if (needed) *needed = 0;
+        return DACH_OK;
+    }
+    for (uint64_t i = 0; i < n; ++i)
+        if (offs[i + 1] < offs[i]) {
+            set_error("haystack offsets must be ascending");
+            return DACH_INVALID_ARGUMENT;
+        }
+    // Slices of ~slice_mib MiB of text, three in flight: while slice k is scanned, slice k+1 is
+    // on its way to the device and the matches of slice k-1 are on their way back.
+    const uint64_t slice_bytes = (uint64_t)std::max<int64_t>(d->opt_slice_mib, 1) << 20;
+    struct Slice {
+        uint64_t first, last;  // haystacks [first, last)
+        uint64_t base;         // matches before this slice
+        uint64_t total;
+    };
+    std::vector<Slice> slices;
+    for (uint64_t i = 0; i < n;) {
+        uint64_t j = i + 1;
+        const uint64_t lim = offs[i] + slice_bytes;
+        if (j < n && offs[j + 1] <= lim) {  // largest j with offs[j] <= lim
+            uint64_t lo = j, hi = n;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi + 1) / 2;
+                if (offs[mid] <= lim)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            j = lo;
+        }
+        slices.push_back({i, j, 0, 0});
+        i = j;
+    }
+    for (Workspace& w : d->slot)
+        if (!w.init(true)) return DACH_CUDA_ERROR;
+    // every slot's previous work must be finished before its buffers are reused
+    bool overflow = false;
+    uint64_t base = 0;
+    auto issue_h2d = [&](size_t k) -> bool {
+        Workspace& W = d->slot[k % 3];
+        const Slice& s = slices[k];
+        const uint64_t tb = offs[s.last] - offs[s.first], ns = s.last - s.first;
+        if (!cuda_ok(cudaStreamSynchronize(W.stream), "slot reuse")) return false;
+        if (!ensure(W.text, tb + 32) || !ensure(W.offs, (ns + 1) * 8) || !ensure(W.out_offs, (ns + 1) * 8)) return false;
+        if (tb && !cuda_ok(cudaMemcpyAsync(W.text.p, text + offs[s.first], tb, cudaMemcpyHostToDevice, W.stream), "H2D text"))
+            return false;
+        if (!cuda_ok(cudaMemcpyAsync(W.offs.p, offs + s.first, (ns + 1) * 8, cudaMemcpyHostToDevice, W.stream), "H2D offsets"))
+            return false;
+        d->last_h2d += tb + (ns + 1) * 8;
+        return true;
+    };
+    if (!issue_h2d(0)) return DACH_CUDA_ERROR;
+    for (size_t k = 0; k < slices.size(); ++k) {
+        if (k + 1 < slices.size() && !issue_h2d(k + 1)) return DACH_CUDA_ERROR;
+        Workspace& W = d->slot[k % 3];
+        Slice& s = slices[k];
+        const uint64_t tb = offs[s.last] - offs[s.first], ns = s.last - s.first;
+        s.base = base;
+        // device-side capacity of this slice: what is left of the caller's buffer, bounded by a
+        // generous per-slice estimate that grows if a slice overflows it
+        uint64_t cap = std::max<uint64_t>(std::max<uint64_t>(tb / 4, 4096), W.out.bytes / 12);
+        for (;;) {
+            if (!ensure(W.out, cap * 12 + 16)) return DACH_CUDA_ERROR;
+            uint64_t total = 0;
+            const uint8_t* d_text = static_cast<const uint8_t*>(W.text.p) - offs[s.first];
+            rc = scan_locked(d, W, mode, d_text, offs[s.first] + tb, static_cast<const uint64_t*>(W.offs.p), ns,
+                             static_cast<dach_match*>(W.out.p), cap, static_cast<uint64_t*>(W.out_offs.p), &total, W.stream);
+            s.total = total;
+            if (rc == DACH_OUTPUT_OVERFLOW && total > cap) {
+                cap = total;
+                continue;
+            }
+            break;
+        }
+        if (rc != DACH_OK && rc != DACH_OUTPUT_OVERFLOW) return rc;
+        if (base + s.total > out_cap) overflow = true;
+        if (!overflow) {
+            // the slice's final offset is the next slice's first one: only the last slice copies it
+            const uint64_t no = (k + 1 == slices.size()) ? ns + 1 : ns;
+            if (!cuda_ok(cudaMemcpyAsync(out_offs + s.first, W.out_offs.p, no * 8, cudaMemcpyDeviceToHost, W.stream), "D2H offsets"))
+                return DACH_CUDA_ERROR;
+            if (s.total && !cuda_ok(cudaMemcpyAsync(out + base, W.out.p, s.total * 12, cudaMemcpyDeviceToHost, W.stream), "D2H matches"))
+                return DACH_CUDA_ERROR;
+            d->last_d2h += (ns + 1) * 8 + s.total * 12;
+        }
+        base += s.total;
+    }
+    for (Workspace& w : d->slot)
+        if (!cuda_ok(cudaStreamSynchronize(w.stream), "D2H")) return DACH_CUDA_ERROR;
+    if (needed) *needed = base;
+    if (overflow) {
+        set_error("output capacity too small");
+        return DACH_OUTPUT_OVERFLOW;
+    }
+    // slice-relative offsets -> batch offsets (slice k's last entry is slice k+1's first)
+    for (size_t k = slices.size(); k-- > 0;) {
+        const Slice& s = slices[k];
+        const uint64_t hi = (k + 1 == slices.size()) ? s.last + 1 : s.last;
+        for (uint64_t i = s.first; i < hi; ++i) out_offs[i] += s.base;
+    }
     return DACH_OK;
 }
 
@@ -683,6 +793,8 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
         d->opt_kernel = value;
     else if (k == "l2_persist")
         d->opt_l2_persist = value;
+    else if (k == "slice_mib")
+        d->opt_slice_mib = value;
     else {
         set_error("unknown option " + k);
         return DACH_INVALID_ARGUMENT;

@@ -282,3 +282,31 @@ def test_full_size_properties_c3():
                 exp.append((s, e, v))
                 r = e
         assert [tuple(x) for x in fm[fo[h]:fo[h + 1]]] == exp
+
+
+def test_host_batch_slicing_matches_single_slice():
+    """dach_scan_batch_host pipelines the batch in slices; results must not depend on the slicing
+    (slice boundaries at every haystack count, empty haystacks at the boundaries, non-zero offs[0])."""
+    rng = np.random.default_rng(21)
+    pats, text, offs = _random_case(rng, False, False)
+    n = len(offs) - 1
+    # make haystacks bigger so that 1 MiB slices cut the batch many times
+    reps = 40
+    big = np.tile(text, reps)
+    boffs = np.concatenate([offs[:-1] + np.uint64(k * int(offs[-1])) for k in range(reps)] + [np.array([reps * int(offs[-1])], dtype=np.uint64)])
+    pma = D.DoubleArrayAhoCorasick.new(pats)
+    opma = O.OraclePma.build(pats)
+    pma.set_option("slice_mib", 1 << 20)
+    one = pma.scan_batch_host(D.FIND_OVERLAPPING, big, boffs)
+    pma.set_option("slice_mib", 1)
+    many = pma.scan_batch_host(D.FIND_OVERLAPPING, big, boffs)
+    assert one.matches.tobytes() == many.matches.tobytes() and np.array_equal(one.offsets, many.offsets)
+    ref = opma.scan_batch(O.FIND_OVERLAPPING, big, boffs, nthreads=8, want_matches=True)
+    assert many.matches.tobytes() == ref["matches"].tobytes()
+    # a view that does not start at offset 0, with preallocated outputs and an exact capacity
+    sub = boffs[5:300]
+    out = np.empty(int(ref["counts"][5:299].sum()), dtype=D.MATCH_DTYPE)
+    r = pma.scan_batch_host(D.FIND_OVERLAPPING, big, sub, out=out)
+    lo = int(ref["counts"][:5].sum())
+    assert r.matches.tobytes() == ref["matches"][lo:lo + len(out)].tobytes()
+    pma.set_option("slice_mib", 64)
