@@ -191,22 +191,13 @@ def main():
     out_offs = torch.empty(n + 1, dtype=torch.int64, device=dev)
     del first
 
-    gather_bufs = None
-    if world > 1:
-        cnt = torch.tensor([total_matches], dtype=torch.int64, device=dev)
-        allc = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(allc, cnt)
-        max_cnt = int(max(int(c.item()) for c in allc))
-        pad = torch.empty((max_cnt, 3), dtype=torch.int32, device=dev)
-        if rank == 0:
-            gather_bufs = [torch.empty((max_cnt, 3), dtype=torch.int32, device=dev) for _ in range(world)]
+    from daachorse_b200 import shard
 
     def step():
         r = pma.scan_batch_device(D.FIND_OVERLAPPING, text_t, offs_t, out=out, out_offs=out_offs)
         if world > 1:
-            # the one exchange step: per-shard match buffers to rank 0 over NVLink
-            pad[:total_matches].copy_(r.matches)
-            dist.gather(pad, gather_bufs, dst=0)
+            # the one exchange step of the path: per-shard match buffers and offsets to rank 0 over NVLink
+            shard.gather_results(r.matches, r.offsets, dst=0)
         return r
 
     def barrier():
