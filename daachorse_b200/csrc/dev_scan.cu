@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_scan_std(ScanParams P) {
     Emitter E;
     E.begin(0);
     bool exhausted = false;
+    const unsigned long long n_items = P.n_items_dev ? *P.n_items_dev : P.n_items;
     for (;;) {
         // ---- service phase (the warp is converged here) ----
         if (L.fl & F_ACTIVE) M::drain(L, Ev, P, E);
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_scan_std(ScanParams P) {
             base = __shfl_sync(FULL, base, leader);
             if (need) {
                 const unsigned long long item = base + __popc(m & ((1u << lane) - 1u));
-                if (item < P.n_items)
+                if (item < n_items)
                     M::begin_item(L, P, Ev, E, item, nullptr);
                 else
                     exhausted = true;
@@ -239,6 +240,36 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const Scan
 
 __global__ void k_zero_offsets(unsigned long long* out_offs) { out_offs[0] = 0; }
 
+// ---- segment table (intra-haystack chunking for find_overlapping / no_suffix) --------------------
+__global__ void __launch_bounds__(256) k_seg_count(const uint64_t* offs, uint64_t n, uint32_t seg_len, uint32_t* nseg) {
+    const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n) return;
+    const uint64_t len = offs[h + 1] - offs[h];
+    const uint64_t k = (len + seg_len - 1) / seg_len;
+    nseg[h] = k ? (uint32_t)k : 1u;  // an empty haystack still is one item (ROOT's outputs at position 0)
+}
+
+__global__ void __launch_bounds__(256) k_seg_fill(const unsigned long long* seg_first, const uint32_t* nseg, uint64_t n,
+                                                   uint32_t seg_len, uint32_t* item_hay, uint32_t* item_beg,
+                                                   unsigned long long* n_items_dev) {
+    const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h == 0) *n_items_dev = seg_first[n];
+    if (h >= n) return;
+    const unsigned long long first = seg_first[h];
+    const uint32_t k = nseg[h];
+    for (uint32_t j = 0; j < k; ++j) {
+        item_hay[first + j] = (uint32_t)h;
+        item_beg[first + j] = j * seg_len;
+    }
+}
+
+// per-haystack offsets from per-item offsets
+__global__ void __launch_bounds__(256) k_hay_offsets(const unsigned long long* seg_first, const unsigned long long* item_offs,
+                                                      uint64_t n, unsigned long long* out_offs) {
+    const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h <= n) out_offs[h] = item_offs[seg_first[h]];
+}
+
 }  // namespace dach
 
 // ------------------------------------------------------------------------------------------
@@ -279,22 +310,24 @@ struct HostPinned {
 // Everything one in-flight scan needs besides the automaton image.
 struct Workspace {
     DevBuf counts, tiles, ctrl, pool;
+    DevBuf nseg, seg_first, item_hay, item_beg, item_offs, n_items_dev;  // segment table
     HostPinned* pinned = nullptr;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // host-batch slices only: device staging and the slice's stream
     DevBuf text, offs, out, out_offs;
     cudaStream_t stream = nullptr;
     bool init(bool with_stream) {
         if (!pinned && !cuda_ok(cudaMallocHost(reinterpret_cast<void**>(&pinned), sizeof(HostPinned)), "cudaMallocHost"))
             return false;
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 4; ++i)
             if (!ev[i] && !cuda_ok(cudaEventCreate(&ev[i]), "cudaEventCreate")) return false;
         if (with_stream && !stream && !cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate"))
             return false;
         return true;
     }
     void release() {
-        for (DevBuf* b : {&counts, &tiles, &ctrl, &pool, &text, &offs, &out, &out_offs})
+        for (DevBuf* b : {&counts, &tiles, &ctrl, &pool, &text, &offs, &out, &out_offs, &nseg, &seg_first, &item_hay, &item_beg,
+                          &item_offs, &n_items_dev})
             if (b->p) {
                 cudaFree(b->p);
                 b->p = nullptr;
@@ -302,7 +335,7 @@ struct Workspace {
             }
         if (pinned) cudaFreeHost(pinned);
         pinned = nullptr;
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 4; ++i)
             if (ev[i]) {
                 cudaEventDestroy(ev[i]);
                 ev[i] = nullptr;
@@ -338,6 +371,7 @@ struct dach_dev {
     Workspace ws;        // dach_dev_scan_batch
     Workspace slot[3];   // dach_scan_batch_host: slices in flight (H2D | scan | D2H)
     int64_t opt_slice_mib = 64;
+    int64_t opt_seg_len = 0;  // 0: automatic; > 0: forced segment length; < 0: no segmentation
     // options
     // Leading records staged in shared memory: -1 = as many as fit, 0 = none.  Default 0: in the
     // reference's slot order the first slots are not the hot ones and L1 caches the hot states
@@ -464,12 +498,46 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, uint
         if (needed) *needed = 0;
         return DACH_OK;
     }
-    const uint64_t n_tiles = (n + kScanTile - 1) / kScanTile;
-    uint64_t pool_blocks64 = out_cap / BLK_MATCHES + n + 1024;
+    int threads = (int)std::min<int64_t>(std::max<int64_t>(d->opt_threads, 32), kMaxThreads);
+    threads = (threads / 32) * 32;
+    int ctas_per_sm = (int)std::min<int64_t>(std::max<int64_t>(d->opt_ctas_per_sm, 1), 2048 / threads);
+    const int grid = d->sm_count * ctas_per_sm;
+    // the lane machine serves the bytewise Standard iterators; find_iter with an empty pattern
+    // (it only reports zero-length matches, src/bytewise/iter.rs:60-85) keeps the simple kernel
+    const bool v1 = d->opt_kernel >= 1 && d->d_crec && !d->charwise && mode != M_LEFTMOST && !(mode == M_FIND && d->root_opos != 0);
+
+    // Work items.  find_overlapping / no_suffix may cut haystacks into segments (exact with an
+    // (L-1)-byte warm-up) so that small batches and long haystacks still
+    // fill the machine; everything else works on whole haystacks.
+    bool seg = v1 && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX) && d->opt_seg_len >= 0;
+    uint32_t seg_len = 0;
+    uint64_t n_items_max = n;
+    if (seg) {
+        const uint64_t lanes = (uint64_t)grid * threads;
+        const uint64_t warm = d->max_pattern_len ? d->max_pattern_len - 1 : 0;
+        uint64_t want = text_bytes / (2 * lanes) + 1;            // ~2 items per lane
+        const uint64_t floor_len = std::max<uint64_t>(256, 8 * warm);  // warm-up overhead <= 1/8
+        want = std::max(want, floor_len);
+        want = (want + 255) & ~uint64_t(255);
+        if (d->opt_seg_len > 0) want = (uint64_t)d->opt_seg_len;
+        if (want >= text_bytes || want >= (1ull << 31)) {
+            seg = false;  // every haystack fits one segment
+        } else {
+            seg_len = (uint32_t)want;
+            n_items_max = n + text_bytes / seg_len + 1;
+            if (n_items_max > 0xfffffff0ull) seg = false, n_items_max = n;
+        }
+    }
+    const uint64_t n_tiles = (n_items_max + kScanTile - 1) / kScanTile;
+    uint64_t pool_blocks64 = out_cap / BLK_MATCHES + n_items_max + 1024;
     if (pool_blocks64 > 0xffffff00ull) pool_blocks64 = 0xffffff00ull;
     const uint32_t pool_blocks = (uint32_t)pool_blocks64;
-    if (!ensure(W.counts, n * 4) || !ensure(W.tiles, n_tiles * 8) || !ensure(W.ctrl, sizeof(ScanCtrl)) ||
+    if (!ensure(W.counts, n_items_max * 4) || !ensure(W.tiles, n_tiles * 8) || !ensure(W.ctrl, sizeof(ScanCtrl)) ||
         !ensure(W.pool, (size_t)pool_blocks * BLK_WORDS * 4))
+        return DACH_CUDA_ERROR;
+    if (seg && (!ensure(W.nseg, n * 4) || !ensure(W.seg_first, (n + 1) * 8) || !ensure(W.item_hay, n_items_max * 4) ||
+                !ensure(W.item_beg, n_items_max * 4) || !ensure(W.item_offs, (n_items_max + 1) * 8) ||
+                !ensure(W.n_items_dev, 8)))
         return DACH_CUDA_ERROR;
 
     ScanParams P;
@@ -494,22 +562,39 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, uint
     P.pool_blocks = pool_blocks;
     P.ctrl = static_cast<ScanCtrl*>(W.ctrl.p);
 
-    int threads = (int)std::min<int64_t>(std::max<int64_t>(d->opt_threads, 32), kMaxThreads);
-    threads = (threads / 32) * 32;
-    int ctas_per_sm = (int)std::min<int64_t>(std::max<int64_t>(d->opt_ctas_per_sm, 1), 2048 / threads);
     const size_t smem_budget = std::min<size_t>(d->smem_optin, 227 * 1024) / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
-    // the lane machine serves the bytewise Standard iterators; find_iter with an empty pattern
-    // (it only reports zero-length matches, src/bytewise/iter.rs:60-85) keeps the simple kernel
-    const bool v1 = d->opt_kernel >= 1 && d->d_crec && !d->charwise && mode != M_LEFTMOST && !(mode == M_FIND && d->root_opos != 0);
     const size_t front = v1 ? kRoot4Bytes + (size_t)LANE_Q * threads * sizeof(QEntry) : kRootBytes;
     uint64_t hot = smem_budget > front ? (smem_budget - front) / 16 : 0;
     if (d->opt_hot_records >= 0) hot = std::min<uint64_t>(hot, (uint64_t)d->opt_hot_records);
     hot = std::min<uint64_t>(hot, d->n_slots);
     P.hot_n = (uint32_t)hot;
     const size_t smem = front + (size_t)hot * 16;
-    const int grid = d->sm_count * ctas_per_sm;
 
+    unsigned long long* offs64 = reinterpret_cast<unsigned long long*>(d_out_offs);
+    unsigned long long* tiles = static_cast<unsigned long long*>(W.tiles.p);
+    unsigned long long* seg_first = static_cast<unsigned long long*>(W.seg_first.p);
+    unsigned long long* item_offs = seg ? static_cast<unsigned long long*>(W.item_offs.p) : offs64;
     if (!cuda_ok(cudaMemsetAsync(W.ctrl.p, 0, sizeof(ScanCtrl), st), "memset ctrl")) return DACH_CUDA_ERROR;
+    cudaEventRecord(W.ev[0], st);
+    if (seg) {
+        // segment table: counts per haystack -> first item per haystack -> (haystack, begin) per item
+        const unsigned hb = (unsigned)((n + 255) / 256), hb1 = (unsigned)((n + 1 + 255) / 256);
+        const uint64_t nt = (n + kScanTile - 1) / kScanTile;
+        uint32_t* nseg = static_cast<uint32_t*>(W.nseg.p);
+        cudaMemsetAsync(W.counts.p, 0, n_items_max * 4, st);  // items past the real count stay empty
+        k_seg_count<<<hb, 256, 0, st>>>(d_offs, n, seg_len, nseg);
+        k_offsets_tile_sums<<<(unsigned)nt, kScanThreads, 0, st>>>(nseg, n, tiles);
+        k_offsets_scan_tiles<<<1, kScanThreads, 0, st>>>(tiles, nt);
+        k_offsets_apply<<<(unsigned)nt, kScanThreads, 0, st>>>(nseg, n, tiles, seg_first);
+        k_seg_fill<<<hb1, 256, 0, st>>>(seg_first, nseg, n, seg_len, static_cast<uint32_t*>(W.item_hay.p),
+                                        static_cast<uint32_t*>(W.item_beg.p), static_cast<unsigned long long*>(W.n_items_dev.p));
+        d->launches += 5;
+        P.item_hay = static_cast<const uint32_t*>(W.item_hay.p);
+        P.item_beg = static_cast<const uint32_t*>(W.item_beg.p);
+        P.n_items_dev = static_cast<const unsigned long long*>(W.n_items_dev.p);
+        P.seg_len = seg_len;
+        P.warm = d->max_pattern_len ? d->max_pattern_len - 1 : 0;
+    }
     L2Window win;
     if (d->opt_l2_persist && d->l2_persist > 0 && v1) {
         // the lane-machine kernels touch the compact records, the opos table and the outputs
@@ -517,27 +602,29 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, uint
         win.bytes = std::min<size_t>(d->l2_window, (size_t)((char*)d->image_base + d->image_alloc - (char*)d->d_outputs));
         win.hit_ratio = (float)std::min(1.0, (double)d->l2_persist / (double)win.bytes);
     }
-    cudaEventRecord(W.ev[0], st);
+    cudaEventRecord(W.ev[3], st);
     if (!cuda_ok(v1 ? launch_std(mode, P, grid, threads, smem, st, win) : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
                  "k_scan launch"))
         return DACH_CUDA_ERROR;
     cudaEventRecord(W.ev[1], st);
-    unsigned long long* offs64 = reinterpret_cast<unsigned long long*>(d_out_offs);
-    unsigned long long* tiles = static_cast<unsigned long long*>(W.tiles.p);
-    k_offsets_tile_sums<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n, tiles);
+    k_offsets_tile_sums<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n_items_max, tiles);
     k_offsets_scan_tiles<<<1, kScanThreads, 0, st>>>(tiles, n_tiles);
-    k_offsets_apply<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n, tiles, offs64);
+    k_offsets_apply<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n_items_max, tiles, item_offs);
     const int gather_grid = d->sm_count * 8;
-    k_gather<<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, offs64, n, out_cap,
+    k_gather<<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, item_offs, n_items_max, out_cap,
                                          reinterpret_cast<uint32_t*>(d_out));
     d->launches += 5;
+    if (seg) {
+        k_hay_offsets<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(seg_first, item_offs, n, offs64);
+        d->launches += 1;
+    }
     if (!cuda_ok(cudaGetLastError(), "kernel launch")) return DACH_CUDA_ERROR;
     cudaEventRecord(W.ev[2], st);
     cudaMemcpyAsync(&W.pinned->total, offs64 + n, 8, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&W.pinned->ctrl, W.ctrl.p, sizeof(ScanCtrl), cudaMemcpyDeviceToHost, st);
     if (!cuda_ok(cudaStreamSynchronize(st), "scan pipeline")) return DACH_CUDA_ERROR;
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, W.ev[0], W.ev[1]) == cudaSuccess) d->last_scan_ms = ms;
+    if (cudaEventElapsedTime(&ms, W.ev[3], W.ev[1]) == cudaSuccess) d->last_scan_ms = ms;
     if (cudaEventElapsedTime(&ms, W.ev[0], W.ev[2]) == cudaSuccess) d->last_total_ms = ms;
     const uint64_t total = W.pinned->total;
     if (needed) *needed = total;
@@ -795,6 +882,8 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
         d->opt_l2_persist = value;
     else if (k == "slice_mib")
         d->opt_slice_mib = value;
+    else if (k == "seg_len")
+        d->opt_seg_len = value;
     else {
         set_error("unknown option " + k);
         return DACH_INVALID_ARGUMENT;

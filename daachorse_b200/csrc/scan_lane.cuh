@@ -92,7 +92,15 @@ struct ScanParams {
     const uint8_t* text;
     const uint8_t* text_end;  // text + total bytes: no 16-byte block starting at or past it is read
     const uint64_t* offs;
-    uint64_t n_items;
+    uint64_t n_items;  // number of work items (== haystacks unless a segment table is given)
+    // Optional segment table (find_overlapping / no_suffix only): item i covers bytes
+    // [item_beg[i], item_beg[i] + seg_len) of haystack item_hay[i]; the lane warms up on the `warm`
+    // bytes before its segment (max pattern length - 1) and reports only matches that end inside it
+    // (SURVEY.md Appendix C.1).  n_items_dev, if set, holds the item count on the device.
+    const uint32_t* item_hay;
+    const uint32_t* item_beg;
+    const unsigned long long* n_items_dev;
+    uint32_t seg_len, warm;
     // results
     uint32_t* counts;  // matches per item
     uint32_t* pool;
@@ -562,6 +570,7 @@ struct LaneStd {
     uint32_t addr;     // slot to fetch
     uint32_t qn;       // queued events
     uint32_t fl;       // F_* flags
+    uint32_t from;     // only matches ending after this position are reported (segment start)
 };
 
 struct StdEnv {
@@ -720,7 +729,7 @@ struct StdMachine {
             L.nf = r.y >> 8;
             L.nfb = r.z >> 8;
             L.sig = r.w;
-            if (r.y & CF_OUT) {
+            if ((r.y & CF_OUT) && L.pos > L.from) {
                 DACH_STAT(pushes);
                 QEntry e;
                 e.end = L.pos;
@@ -757,10 +766,24 @@ struct StdMachine {
 
     static DACH_HD void begin_item(LaneStd& L, const ScanParams& P, const StdEnv& Ev, Emitter& E, uint64_t item,
                                    const uint8_t* emu_lo) {
-        const uint64_t o0 = P.offs[item], o1 = P.offs[item + 1];
+        uint64_t hay = item;
+        uint32_t beg = 0;
+        if (P.item_hay) {
+            hay = P.item_hay[item];
+            beg = P.item_beg[item];
+        }
+        const uint64_t o0 = P.offs[hay], o1 = P.offs[hay + 1];
+        const uint32_t hay_len = (uint32_t)(o1 - o0);
         L.hay = P.text + o0;
-        L.len = (uint32_t)(o1 - o0);
-        L.pos = 0;
+        L.len = hay_len;
+        uint32_t start = 0;
+        if (P.item_hay) {
+            const uint32_t end = beg + P.seg_len;
+            L.len = end < hay_len ? end : hay_len;
+            start = beg > P.warm ? beg - P.warm : 0;  // warm-up: the state at `beg` only depends on these bytes
+        }
+        L.pos = start;
+        L.from = beg;
         L.item = (uint32_t)item;
         L.qn = 0;
         E.begin((uint32_t)item);
@@ -774,7 +797,7 @@ struct StdMachine {
         L.nf = D_ROOT;
         L.nfb = 0;
         L.fl = F_ACTIVE | F_KNOW;
-        if (MODE != M_FIND && (Ev.root_flags & CF_OUT)) {
+        if (MODE != M_FIND && (Ev.root_flags & CF_OUT) && beg == 0) {
             QEntry e;
             e.end = 0;
             e.slot = D_ROOT;

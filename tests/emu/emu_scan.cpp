@@ -120,7 +120,7 @@ static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* 
 
 extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int charwise, int mode,
                                    const uint8_t* text, const uint64_t* offs, uint64_t n, uint32_t hot_n,
-                                   int kernel_version, uint32_t pool_blocks, dach_match* out, uint64_t out_cap, uint64_t* out_offs,
+                                   int kernel_version, uint32_t seg_len, uint32_t pool_blocks, dach_match* out, uint64_t out_cap, uint64_t* out_offs,
                                    uint64_t* needed) {
     dach_pma* pma = nullptr;
     size_t used = 0;
@@ -133,7 +133,26 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     if (rc) return rc;
     if ((mode == M_LEFTMOST) != lm) return DACH_MATCH_KIND_MISMATCH;
 
-    std::vector<uint32_t> counts(n ? n : 1, 0);
+    // segment table (mirrors k_seg_count / k_seg_fill in dev_scan.cu)
+    const bool v1 = kernel_version >= 1 && !img.crec.empty() && !charwise && mode != M_LEFTMOST && !(mode == M_FIND && img.root_opos != 0);
+    const bool seg = v1 && seg_len > 0 && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX);
+    std::vector<uint32_t> item_hay, item_beg;
+    std::vector<uint64_t> seg_first(n + 1, 0);
+    uint64_t n_items = n;
+    if (seg) {
+        for (uint64_t h = 0; h < n; ++h) {
+            const uint64_t len = offs[h + 1] - offs[h];
+            uint64_t k = (len + seg_len - 1) / seg_len;
+            if (k == 0) k = 1;
+            seg_first[h + 1] = seg_first[h] + k;
+            for (uint64_t j = 0; j < k; ++j) {
+                item_hay.push_back((uint32_t)h);
+                item_beg.push_back((uint32_t)(j * seg_len));
+            }
+        }
+        n_items = seg_first[n];
+    }
+    std::vector<uint32_t> counts(n_items ? n_items : 1, 0);
     std::vector<uint32_t> pool((size_t)pool_blocks * BLK_WORDS, 0xdeadbeefu);
     ScanCtrl ctrl;
     memset(&ctrl, 0, sizeof(ctrl));
@@ -152,7 +171,13 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     P.text_end = text + (n ? offs[n] : 0);
     P.offs = offs;
     P.root4 = reinterpret_cast<const uint4*>(img.root4.data());
-    P.n_items = n;
+    P.n_items = n_items;
+    if (seg) {
+        P.item_hay = item_hay.data();
+        P.item_beg = item_beg.data();
+        P.seg_len = seg_len;
+        P.warm = img.max_pattern_len ? img.max_pattern_len - 1 : 0;
+    }
     P.counts = counts.data();
     P.pool = pool.data();
     P.pool_blocks = pool_blocks;
@@ -163,7 +188,6 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     RecView V{P.rec, reinterpret_cast<const uint4*>(hot.data()), hot_n, img.root_table.data()};
     const uint8_t* lo = text + (n ? offs[0] : 0);
     const uint8_t* hi = text + (n ? offs[n] : 0);
-    const bool v1 = kernel_version >= 1 && !img.crec.empty() && !charwise && mode != M_LEFTMOST && !(mode == M_FIND && img.root_opos != 0);
     if (v1) {
         std::vector<uint32_t> chot(img.crec.begin(), img.crec.begin() + (size_t)hot_n * 4);
         chot.resize(chot.size() + 4);
@@ -185,13 +209,11 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
         case 7: run_items<true, M_LEFTMOST>(P, V, lo, hi); break;
         default: return DACH_INVALID_ARGUMENT;
     }
-    // offsets (k_offsets_*) and gather (k_gather)
-    uint64_t run = 0;
-    for (uint64_t i = 0; i < n; ++i) {
-        out_offs[i] = run;
-        run += counts[i];
-    }
-    out_offs[n] = run;
+    // offsets (k_offsets_*), per-haystack offsets (k_hay_offsets) and gather (k_gather)
+    std::vector<uint64_t> item_offs(n_items + 1, 0);
+    for (uint64_t i = 0; i < n_items; ++i) item_offs[i + 1] = item_offs[i] + counts[i];
+    const uint64_t run = item_offs[n_items];
+    for (uint64_t h = 0; h <= n; ++h) out_offs[h] = seg ? item_offs[seg_first[h]] : item_offs[h];
     if (needed) *needed = run;
     if (ctrl.overflow || run > out_cap) return DACH_OUTPUT_OVERFLOW;
     const uint32_t used_blocks = ctrl.blk_cursor < pool_blocks ? ctrl.blk_cursor : pool_blocks;
@@ -202,7 +224,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
         const uint32_t first = seq * BLK_MATCHES;
         uint32_t nm = counts[item] - first;
         if (nm > BLK_MATCHES) nm = BLK_MATCHES;
-        uint32_t* dst = out_words + (out_offs[item] + first) * 3ull;
+        uint32_t* dst = out_words + (item_offs[item] + first) * 3ull;
         for (uint32_t w = 0; w < nm * 3; ++w) dst[w] = blk[2 + w];
     }
     return DACH_OK;

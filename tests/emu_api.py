@@ -19,13 +19,13 @@ def lib():
         subprocess.check_call(["make", "-C", EMU_DIR, "-s"])
         _lib = C.CDLL(LIB)
         _lib.emu_scan_batch_wire.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                             C.c_uint64, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64,
+                                             C.c_uint64, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
                                              C.c_void_p, C.POINTER(C.c_uint64)]
         _lib.emu_scan_batch_wire.restype = C.c_int
     return _lib
 
 
-def scan(wire, charwise, mode, text, offs, hot_n=0, pool_blocks=None, out_cap=None, kernel=1):
+def scan(wire, charwise, mode, text, offs, hot_n=0, pool_blocks=None, out_cap=None, kernel=1, seg_len=0):
     """Returns (rc, matches, out_offs, needed)."""
     wire_a = np.frombuffer(wire, dtype=np.uint8)
     text = np.ascontiguousarray(text, dtype=np.uint8)
@@ -33,13 +33,14 @@ def scan(wire, charwise, mode, text, offs, hot_n=0, pool_blocks=None, out_cap=No
     n = len(offs) - 1
     cap = int(out_cap) if out_cap is not None else 1 << 16
     while True:
-        pb = int(pool_blocks) if pool_blocks is not None else cap // 20 + n + 16
+        n_items = n + (int(text.size) // seg_len + 1 if seg_len else 0)
+        pb = int(pool_blocks) if pool_blocks is not None else cap // 20 + n_items + 16
         out = np.zeros(max(cap, 1), dtype=MATCH_DTYPE)
         oo = np.zeros(n + 1, dtype=np.uint64)
         need = C.c_uint64()
         pad = text if text.size else np.zeros(16, dtype=np.uint8)
         rc = lib().emu_scan_batch_wire(wire_a.ctypes.data, wire_a.size, int(charwise), mode, pad.ctypes.data,
-                                       offs.ctypes.data, n, hot_n, kernel, pb, out.ctypes.data, cap, oo.ctypes.data,
+                                       offs.ctypes.data, n, hot_n, kernel, seg_len, pb, out.ctypes.data, cap, oo.ctypes.data,
                                        C.byref(need))
         if rc == 6 and out_cap is None and pool_blocks is None:
             cap = max(cap * 2, int(need.value))

@@ -115,3 +115,27 @@ def test_mode_gating():
     wire = O.OraclePma.build([b"a"], match_kind=1).serialize()
     rc, *_ = E.scan(wire, False, 1, np.zeros(0, np.uint8), np.array([0, 0], dtype=np.uint64))
     assert rc == 5
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_segments_reproduce_the_sequential_scan(seed):
+    """Intra-haystack segments with an (L-1)-byte warm-up: every segment
+    length gives the sequential result, including empty patterns, empty haystacks, haystacks that
+    end exactly on a segment boundary and patterns longer than a segment."""
+    rng = np.random.default_rng(400 + seed)
+    alpha = int(rng.integers(2, 5))
+    pats = rand_patterns(rng, int(rng.integers(1, 60)), alpha, 9, allow_empty=(seed == 0))
+    pma = O.OraclePma.build(pats)
+    wire = pma.serialize()
+    lens = list(rng.integers(0, 400, size=30)) + [0, 64, 128, 1, 63, 65]
+    hays = [bytes(rng.integers(97, 97 + alpha + 1, size=int(L)).tolist()) for L in lens]
+    offs = np.zeros(len(hays) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(h) for h in hays])
+    text = np.frombuffer(b"".join(hays), dtype=np.uint8)
+    for mode in (1, 2):
+        ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
+        for seg_len in (1, 3, 16, 64, 100, 1000):
+            rc, m, oo, need = E.scan(wire, False, mode, text, offs, seg_len=seg_len)
+            assert rc == 0 and need == ref["total"], (seg_len, mode)
+            assert m.tobytes() == ref["matches"].tobytes(), (seg_len, mode)
+            assert np.array_equal(np.diff(oo.astype(np.int64)), ref["counts"].astype(np.int64))

@@ -310,3 +310,24 @@ def test_host_batch_slicing_matches_single_slice():
     lo = int(ref["counts"][:5].sum())
     assert r.matches.tobytes() == ref["matches"][lo:lo + len(out)].tobytes()
     pma.set_option("slice_mib", 64)
+
+
+def test_segmented_scan_equals_sequential():
+    """Intra-haystack segments on the device: forced tiny segments, automatic
+    segments on a few long haystacks (the C5 shape), and an empty pattern."""
+    rng = np.random.default_rng(33)
+    pats = [bytes(rng.integers(97, 101, size=int(rng.integers(1, 9))).tolist()) for _ in range(200)] + [b""]
+    pma = D.DoubleArrayAhoCorasick.new(pats)
+    opma = O.OraclePma.build(pats)
+    lens = [0, 1, 255, 256, 257, 100000, 3, 70000, 0, 512]
+    offs = np.zeros(len(lens) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    text = rng.integers(97, 102, size=int(offs[-1])).astype(np.uint8)
+    for mode in (D.FIND_OVERLAPPING, D.FIND_OVERLAPPING_NO_SUFFIX):
+        ref = opma.scan_batch(ORC[mode], text, offs, nthreads=8, want_matches=True)
+        for seg in (0, 16, 256, 4096, -1):
+            pma.set_option("seg_len", seg)
+            r = pma.scan_batch_host(mode, text, offs)
+            assert r.matches.tobytes() == ref["matches"].tobytes(), (mode, seg)
+            assert np.array_equal(np.diff(r.offsets.astype(np.int64)), ref["counts"].astype(np.int64))
+    pma.set_option("seg_len", 0)
