@@ -485,8 +485,10 @@ int check_mode(const dach_dev* d, int mode) {
 }
 
 // the device-side pipeline; caller holds d->mu and has set the device
-int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, uint64_t text_bytes, const uint64_t* d_offs,
-                uint64_t n, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs, uint64_t* needed, cudaStream_t st) {
+// d_text + d_offs[i] addresses haystack i; text_end is one past the last text byte on the device;
+// text_bytes is the number of text bytes this call covers (sizing only).
+int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, const uint8_t* text_end, uint64_t text_bytes,
+                const uint64_t* d_offs, uint64_t n, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs, uint64_t* needed, cudaStream_t st) {
     if (n > 0xfffffff0ull) {
         set_error("too many haystacks in one batch (max 2^32-16)");
         return DACH_INVALID_ARGUMENT;
@@ -554,7 +556,7 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, uint
     P.n_slots = d->n_slots;
     P.root_opos = d->root_opos;
     P.text = d_text;
-    P.text_end = d_text + text_bytes;
+    P.text_end = text_end;
     P.offs = d_offs;
     P.n_items = n;
     P.counts = static_cast<uint32_t*>(W.counts.p);
@@ -739,7 +741,8 @@ int dach_dev_scan_batch(dach_dev* d, int mode, const uint8_t* d_text, const uint
     std::lock_guard<std::mutex> lk(d->mu);
     DeviceGuard g(d->device);
     if (!g.ok) return DACH_CUDA_ERROR;
-    return scan_locked(d, d->ws, mode, d_text, text_bytes, d_offs, n, d_out, out_cap, d_out_offs, needed, static_cast<cudaStream_t>(stream));
+    return scan_locked(d, d->ws, mode, d_text, d_text + text_bytes, text_bytes, d_offs, n, d_out, out_cap, d_out_offs, needed,
+                       static_cast<cudaStream_t>(stream));
 }
 
 int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint64_t* offs, uint64_t n,
@@ -822,7 +825,7 @@ int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint6
             if (!ensure(W.out, cap * 12 + 16)) return DACH_CUDA_ERROR;
             uint64_t total = 0;
             const uint8_t* d_text = static_cast<const uint8_t*>(W.text.p) - offs[s.first];
-            rc = scan_locked(d, W, mode, d_text, offs[s.first] + tb, static_cast<const uint64_t*>(W.offs.p), ns,
+            rc = scan_locked(d, W, mode, d_text, static_cast<const uint8_t*>(W.text.p) + tb, tb, static_cast<const uint64_t*>(W.offs.p), ns,
                              static_cast<dach_match*>(W.out.p), cap, static_cast<uint64_t*>(W.out_offs.p), &total, W.stream);
             s.total = total;
             if (rc == DACH_OUTPUT_OVERFLOW && total > cap) {
