@@ -820,7 +820,7 @@ int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint6
         s.base = base;
         // device-side capacity of this slice: what is left of the caller's buffer, bounded by a
         // generous per-slice estimate that grows if a slice overflows it
-        uint64_t cap = std::max<uint64_t>(std::max<uint64_t>(tb / 4, 4096), W.out.bytes / 12);
+        uint64_t cap = std::max<uint64_t>(std::max<uint64_t>(tb / 4, 4096), W.out.bytes > 16 ? (W.out.bytes - 16) / 12 : 0);
         for (;;) {
             if (!ensure(W.out, cap * 12 + 16)) return DACH_CUDA_ERROR;
             uint64_t total = 0;
