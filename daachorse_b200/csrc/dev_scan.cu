@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_scan_std(ScanParams P) {
 
     using M = StdMachine<MODE>;
     const StdEnv Ev{P.crec,      s_hot,        P.hot_n,          s_root4, P.opos_tab, P.text_end, P.root_base, P.root_opos ? CF_OUT : 0u,
-                    s_queue + threadIdx.x, blockDim.x};
+                    s_queue + threadIdx.x, blockDim.x, P.dbg};
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     LaneStd L;
@@ -371,6 +371,7 @@ struct dach_dev {
     Workspace ws;        // dach_dev_scan_batch
     Workspace slot[3];   // dach_scan_batch_host: slices in flight (H2D | scan | D2H)
     int64_t opt_slice_mib = 64;
+    int64_t opt_dbg = 0;
     int64_t opt_seg_len = 0;  // 0: automatic; > 0: forced segment length; < 0: no segmentation
     // options
     // Leading records staged in shared memory: -1 = as many as fit, 0 = none.  Default 0: in the
@@ -563,6 +564,7 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     P.pool = static_cast<uint32_t*>(W.pool.p);
     P.pool_blocks = pool_blocks;
     P.ctrl = static_cast<ScanCtrl*>(W.ctrl.p);
+    P.dbg = (uint32_t)d->opt_dbg;
 
     const size_t smem_budget = std::min<size_t>(d->smem_optin, 227 * 1024) / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
     const size_t front = v1 ? kRoot4Bytes + (size_t)LANE_Q * threads * sizeof(QEntry) : kRootBytes;
@@ -887,6 +889,8 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
         d->opt_slice_mib = value;
     else if (k == "seg_len")
         d->opt_seg_len = value;
+    else if (k == "dbg")
+        d->opt_dbg = value;
     else {
         set_error("unknown option " + k);
         return DACH_INVALID_ARGUMENT;

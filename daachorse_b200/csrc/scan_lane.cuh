@@ -101,6 +101,8 @@ struct ScanParams {
     const uint32_t* item_beg;
     const unsigned long long* n_items_dev;
     uint32_t seg_len, warm;
+    uint32_t dbg;  // experiment switches (bench --option dbg=): 1 = count matches but do not store them,
+                   // 2 = text via ld.global.cs, 4 = text via ld.global.nc (L1 allocating)
     // results
     uint32_t* counts;  // matches per item
     uint32_t* pool;
@@ -219,7 +221,7 @@ struct Emitter {
                 P.ctrl->overflow = 1u;
             }
         }
-        if (blk) {
+        if (blk && !(P.dbg & 1u)) {
             uint32_t* q = blk + 2 + 3 * fill;
             q[0] = start;
             q[1] = end;
@@ -584,17 +586,24 @@ struct StdEnv {
     uint32_t root_flags;   // CF_OUT if ROOT has an output list (an empty pattern)
     QEntry* q;             // this lane's queue: entry j at q[j * q_stride]
     uint32_t q_stride;
+    uint32_t dbg;
 };
 
-DACH_HD uint4 ld_text16(const uint8_t* q, const uint8_t* text_end, const uint8_t* emu_lo) {
+DACH_HD uint4 ld_text16(const uint8_t* q, const uint8_t* text_end, const uint8_t* emu_lo, uint32_t dbg = 0) {
     uint4 w;
     w.x = w.y = w.z = w.w = 0;
     (void)emu_lo;
+    (void)dbg;
     if (q >= text_end) return w;  // never touch a block that starts past the text
 #if defined(__CUDA_ARCH__)
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
-                 : "l"(q));
+    if (dbg & 2u)
+        asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(q));
+    else if (dbg & 4u)
+        asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(q));
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                     : "l"(q));
 #elif defined(DACH_EMU)
     uint32_t v[4] = {0, 0, 0, 0};
     for (int i = 0; i < 16; ++i) {
@@ -626,7 +635,7 @@ struct StdMachine {
     // warp-uniform schedule: re-arm the prefetched window of the lanes that crossed since last time
     static DACH_HD void text_topup(LaneStd& L, const StdEnv& Ev, const uint8_t* emu_lo) {
         if ((L.fl & (F_ACTIVE | F_NEED_NW)) == (F_ACTIVE | F_NEED_NW)) {
-            L.nw = ld_text16(block_of(L) + 16, Ev.text_end, emu_lo);
+            L.nw = ld_text16(block_of(L) + 16, Ev.text_end, emu_lo, Ev.dbg);
             L.fl &= ~F_NEED_NW;
         }
     }
@@ -788,8 +797,8 @@ struct StdMachine {
         L.qn = 0;
         E.begin((uint32_t)item);
         const uint8_t* b0 = block_of(L);
-        L.cw = ld_text16(b0, Ev.text_end, emu_lo);
-        L.nw = ld_text16(b0 + 16, Ev.text_end, emu_lo);
+        L.cw = ld_text16(b0, Ev.text_end, emu_lo, Ev.dbg);
+        L.nw = ld_text16(b0 + 16, Ev.text_end, emu_lo, Ev.dbg);
         // the iterator starts in ROOT with ROOT's output list pending at position 0
         // (src/bytewise.rs:303-313; no-suffix variant: src/bytewise/iter.rs:196-216)
         L.cb = 0;

@@ -192,7 +192,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
         std::vector<uint32_t> chot(img.crec.begin(), img.crec.begin() + (size_t)hot_n * 4);
         chot.resize(chot.size() + 4);
         const StdEnv Ev{reinterpret_cast<const uint4*>(img.crec.data()), reinterpret_cast<const uint4*>(chot.data()), hot_n, P.root4,
-                        img.opos_tab.data(), P.text_end, img.root_base, P.root_opos ? CF_OUT : 0u, nullptr, 0};
+                        img.opos_tab.data(), P.text_end, img.root_base, P.root_opos ? CF_OUT : 0u, nullptr, 0, 0};
         const int n_warps = 3;
         if (mode == M_FIND) run_items_v1<M_FIND>(P, Ev, lo, n_warps);
         if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING>(P, Ev, lo, n_warps);
