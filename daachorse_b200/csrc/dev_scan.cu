@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_scan(ScanParams P) {
 // warp-aggregated atomic.
 constexpr uint32_t kRoot4Bytes = 4096;  // 256 x uint4 at the front of dynamic shared memory
 
-template <int MODE>
-__global__ void __launch_bounds__(kMaxThreads, 1) k_scan_std(ScanParams P) {
+template <int MODE, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_scan_std(ScanParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* s_root4 = reinterpret_cast<uint4*>(smem_raw);
     QEntry* s_queue = reinterpret_cast<QEntry*>(smem_raw + kRoot4Bytes);  // [LANE_Q][blockDim.x]
@@ -420,11 +420,11 @@ struct L2Window {
     float hit_ratio = 1.0f;
 };
 
-template <int MODE>
+template <int MODE, int MAXT, int MINB>
 cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_scan_std<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_scan_std<MODE, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -446,14 +446,20 @@ cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem
         cfg.attrs = at;
         cfg.numAttrs = 1;
     }
-    return cudaLaunchKernelEx(&cfg, k_scan_std<MODE>, P);
+    return cudaLaunchKernelEx(&cfg, k_scan_std<MODE, MAXT, MINB>, P);
 }
 
-cudaError_t launch_std(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
-    switch (mode) {
-        case M_FIND: return launch_std_t<M_FIND>(P, grid, threads, smem, st, w);
-        case M_OVERLAPPING: return launch_std_t<M_OVERLAPPING>(P, grid, threads, smem, st, w);
-        case M_NO_SUFFIX: return launch_std_t<M_NO_SUFFIX>(P, grid, threads, smem, st, w);
+cudaError_t launch_std(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w,
+                       bool dense_hint) {
+    // two register budgets: 1024 threads x 1 CTA/SM (64 regs) or up to 768 threads x 2 CTAs/SM (42 regs)
+    const bool dense = threads <= 768 && (grid % 2 == 0) && dense_hint;
+    switch (mode * 2 + (dense ? 1 : 0)) {
+        case M_FIND * 2: return launch_std_t<M_FIND, 1024, 1>(P, grid, threads, smem, st, w);
+        case M_OVERLAPPING * 2: return launch_std_t<M_OVERLAPPING, 1024, 1>(P, grid, threads, smem, st, w);
+        case M_NO_SUFFIX * 2: return launch_std_t<M_NO_SUFFIX, 1024, 1>(P, grid, threads, smem, st, w);
+        case M_FIND * 2 + 1: return launch_std_t<M_FIND, 768, 2>(P, grid, threads, smem, st, w);
+        case M_OVERLAPPING * 2 + 1: return launch_std_t<M_OVERLAPPING, 768, 2>(P, grid, threads, smem, st, w);
+        case M_NO_SUFFIX * 2 + 1: return launch_std_t<M_NO_SUFFIX, 768, 2>(P, grid, threads, smem, st, w);
     }
     return cudaErrorInvalidValue;
 }
@@ -607,7 +613,7 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
         win.hit_ratio = (float)std::min(1.0, (double)d->l2_persist / (double)win.bytes);
     }
     cudaEventRecord(W.ev[3], st);
-    if (!cuda_ok(v1 ? launch_std(mode, P, grid, threads, smem, st, win) : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
+    if (!cuda_ok(v1 ? launch_std(mode, P, grid, threads, smem, st, win, ctas_per_sm >= 2) : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
                  "k_scan launch"))
         return DACH_CUDA_ERROR;
     cudaEventRecord(W.ev[1], st);
