@@ -67,19 +67,60 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_scan(ScanParams P) {
 // warp-aggregated atomic.
 constexpr uint32_t kRoot4Bytes = 4096;  // 256 x uint4 at the front of dynamic shared memory
 
-template <int MODE, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) k_scan_std(ScanParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint4* s_root4 = reinterpret_cast<uint4*>(smem_raw);
-    QEntry* s_queue = reinterpret_cast<QEntry*>(smem_raw + kRoot4Bytes);  // [LANE_Q][blockDim.x]
-    uint4* s_hot = reinterpret_cast<uint4*>(smem_raw + kRoot4Bytes + (size_t)LANE_Q * blockDim.x * sizeof(QEntry));
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_root4[i] = P.root4[i];
-    for (uint32_t i = threadIdx.x; i < P.hot_n; i += blockDim.x) s_hot[i] = P.crec[i];
-    __syncthreads();
+// ---- TMA bulk copy global -> shared (cp.async.bulk, completion on an mbarrier) -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-    using M = StdMachine<MODE>;
-    const StdEnv Ev{P.crec,      s_hot,        P.hot_n,          s_root4, P.opos_tab, P.text_end, P.root_base, P.root_opos ? CF_OUT : 0u,
-                    s_queue + threadIdx.x, blockDim.x, P.dbg};
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+template <int MODE, int MAXT, int MINB, bool PROFILE>
+__global__ void __launch_bounds__(MAXT, MINB) k_scan_std(ScanParams P) {
+    // dynamic shared memory: [root row 4 KiB][state cache hot_entries x 16 B][event queues LANE_Q x blockDim x 8 B]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    uint4* s_root4 = reinterpret_cast<uint4*>(smem_raw);
+    uint4* s_hot = reinterpret_cast<uint4*>(smem_raw + kRoot4Bytes);
+    QEntry* s_queue = reinterpret_cast<QEntry*>(smem_raw + kRoot4Bytes + (size_t)P.hot_entries * 16);
+    // one elected thread arms the mbarrier and lets the TMA engine stage the root row and the state
+    // cache (up to ~130 KiB) while the other threads set up
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t hot_bytes = P.hot_entries * 16u;
+        mbar_expect_tx(&s_bar, kRoot4Bytes + hot_bytes);
+        tma_bulk_g2s(s_root4, P.root4, kRoot4Bytes, &s_bar);
+        for (uint32_t off = 0; off < hot_bytes; off += 32768u)
+            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_hot) + off, reinterpret_cast<const unsigned char*>(P.hot_tab) + off,
+                         min(32768u, hot_bytes - off), &s_bar);
+    }
+
+    using M = StdMachine<MODE, PROFILE>;
+    uint32_t hot_shift = 0;
+    while ((1u << hot_shift) < P.hot_entries) ++hot_shift;
+    const StdEnv Ev{P.crec,     s_hot,      P.hot_entries ? P.hot_entries - 1u : 0u, hot_shift, P.visits, s_root4, P.opos_tab,
+                    P.text_end, P.root_base, P.root_opos ? CF_OUT : 0u, s_queue + threadIdx.x, blockDim.x, P.dbg};
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     LaneStd L;
@@ -89,11 +130,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_std(ScanParams P) {
     E.begin(0);
     bool exhausted = false;
     const unsigned long long n_items = P.n_items_dev ? *P.n_items_dev : P.n_items;
+    mbar_wait(&s_bar, 0);
     for (;;) {
         // ---- service phase (the warp is converged here) ----
         if (L.fl & F_ACTIVE) M::drain(L, Ev, P, E);
         if ((L.fl & (F_ACTIVE | F_DONE)) == (F_ACTIVE | F_DONE)) {
-            E.finish(P);
+            if (!PROFILE) E.finish(P);
             L.fl = 0;
         }
         const bool need = !(L.fl & F_ACTIVE) && !exhausted;
@@ -126,6 +168,31 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_std(ScanParams P) {
             }
         }
     }
+}
+
+// ---- state cache construction from the profiling counters -------------------------------------
+// best[bin] = max over slots of that bin of (visits << 32 | slot)
+__global__ void __launch_bounds__(256) k_hot_pick(const uint32_t* visits, uint32_t n_slots, uint32_t mask,
+                                                   unsigned long long* best) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
+        const uint32_t v = visits[s];
+        if (v) atomicMax(best + (s & mask), ((unsigned long long)v << 32) | s);
+    }
+}
+__global__ void __launch_bounds__(256) k_hot_fill(const unsigned long long* best, const uint4* crec, uint32_t entries,
+                                                   uint32_t shift, uint4* tab) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= entries) return;
+    const unsigned long long v = best[b];
+    uint4 e;
+    if (v) {
+        const uint32_t slot = (uint32_t)v;
+        e = hot_entry(crec[slot], slot >> shift);
+    } else {
+        e.x = e.y = e.z = e.w = 0;
+        e = hot_entry(e, HOT_TAG_INVALID);
+    }
+    tab[b] = e;
 }
 
 // ---- exclusive scan of counts (u32) into offsets (u64) -----------------------------------
@@ -371,6 +438,12 @@ struct dach_dev {
     Workspace ws;        // dach_dev_scan_batch
     Workspace slot[3];   // dach_scan_batch_host: slices in flight (H2D | scan | D2H)
     int64_t opt_slice_mib = 64;
+    // profile-guided shared-memory state cache (lane-machine kernels)
+    DevBuf hot_tab, visits, best;
+    bool hot_ready = false;
+    uint32_t hot_tab_entries = 0;
+    int64_t opt_hot_entries = 8192;   // power of two, 0 = off
+    int64_t opt_profile_items = 2048;
     int64_t opt_dbg = 0;
     int64_t opt_seg_len = 0;  // 0: automatic; > 0: forced segment length; < 0: no segmentation
     // options
@@ -420,11 +493,11 @@ struct L2Window {
     float hit_ratio = 1.0f;
 };
 
-template <int MODE, int MAXT, int MINB>
+template <int MODE, int MAXT, int MINB, bool PROFILE>
 cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_scan_std<MODE, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_scan_std<MODE, MAXT, MINB, PROFILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -446,20 +519,28 @@ cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem
         cfg.attrs = at;
         cfg.numAttrs = 1;
     }
-    return cudaLaunchKernelEx(&cfg, k_scan_std<MODE, MAXT, MINB>, P);
+    return cudaLaunchKernelEx(&cfg, k_scan_std<MODE, MAXT, MINB, PROFILE>, P);
 }
 
 cudaError_t launch_std(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w,
-                       bool dense_hint) {
+                       bool dense_hint, bool profile) {
     // two register budgets: 1024 threads x 1 CTA/SM (64 regs) or up to 768 threads x 2 CTAs/SM (42 regs)
     const bool dense = threads <= 768 && (grid % 2 == 0) && dense_hint;
+    if (profile) {
+        switch (mode) {
+            case M_FIND: return launch_std_t<M_FIND, 1024, 1, true>(P, grid, threads, smem, st, w);
+            case M_OVERLAPPING: return launch_std_t<M_OVERLAPPING, 1024, 1, true>(P, grid, threads, smem, st, w);
+            case M_NO_SUFFIX: return launch_std_t<M_NO_SUFFIX, 1024, 1, true>(P, grid, threads, smem, st, w);
+        }
+        return cudaErrorInvalidValue;
+    }
     switch (mode * 2 + (dense ? 1 : 0)) {
-        case M_FIND * 2: return launch_std_t<M_FIND, 1024, 1>(P, grid, threads, smem, st, w);
-        case M_OVERLAPPING * 2: return launch_std_t<M_OVERLAPPING, 1024, 1>(P, grid, threads, smem, st, w);
-        case M_NO_SUFFIX * 2: return launch_std_t<M_NO_SUFFIX, 1024, 1>(P, grid, threads, smem, st, w);
-        case M_FIND * 2 + 1: return launch_std_t<M_FIND, 768, 2>(P, grid, threads, smem, st, w);
-        case M_OVERLAPPING * 2 + 1: return launch_std_t<M_OVERLAPPING, 768, 2>(P, grid, threads, smem, st, w);
-        case M_NO_SUFFIX * 2 + 1: return launch_std_t<M_NO_SUFFIX, 768, 2>(P, grid, threads, smem, st, w);
+        case M_FIND * 2: return launch_std_t<M_FIND, 1024, 1, false>(P, grid, threads, smem, st, w);
+        case M_OVERLAPPING * 2: return launch_std_t<M_OVERLAPPING, 1024, 1, false>(P, grid, threads, smem, st, w);
+        case M_NO_SUFFIX * 2: return launch_std_t<M_NO_SUFFIX, 1024, 1, false>(P, grid, threads, smem, st, w);
+        case M_FIND * 2 + 1: return launch_std_t<M_FIND, 768, 2, false>(P, grid, threads, smem, st, w);
+        case M_OVERLAPPING * 2 + 1: return launch_std_t<M_OVERLAPPING, 768, 2, false>(P, grid, threads, smem, st, w);
+        case M_NO_SUFFIX * 2 + 1: return launch_std_t<M_NO_SUFFIX, 768, 2, false>(P, grid, threads, smem, st, w);
     }
     return cudaErrorInvalidValue;
 }
@@ -573,12 +654,25 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     P.dbg = (uint32_t)d->opt_dbg;
 
     const size_t smem_budget = std::min<size_t>(d->smem_optin, 227 * 1024) / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
-    const size_t front = v1 ? kRoot4Bytes + (size_t)LANE_Q * threads * sizeof(QEntry) : kRootBytes;
-    uint64_t hot = smem_budget > front ? (smem_budget - front) / 16 : 0;
-    if (d->opt_hot_records >= 0) hot = std::min<uint64_t>(hot, (uint64_t)d->opt_hot_records);
-    hot = std::min<uint64_t>(hot, d->n_slots);
-    P.hot_n = (uint32_t)hot;
-    const size_t smem = front + (size_t)hot * 16;
+    size_t smem;
+    uint32_t hot_entries = 0;
+    if (v1) {
+        const size_t fixed = kRoot4Bytes + (size_t)LANE_Q * threads * sizeof(QEntry) + 64;
+        // largest power of two that fits next to the root row and the queues
+        uint64_t want = d->opt_hot_entries > 0 ? (uint64_t)d->opt_hot_entries : 0;
+        while (want && fixed + want * 16 > smem_budget) want >>= 1;
+        while (want & (want - 1)) want &= want - 1;
+        if (want && (uint64_t)d->n_slots > want * (uint64_t)HOT_TAG_INVALID) want = 0;  // tag would not fit
+        hot_entries = (uint32_t)want;
+        smem = kRoot4Bytes + (size_t)hot_entries * 16 + (size_t)LANE_Q * threads * sizeof(QEntry);
+        P.hot_n = 0;
+    } else {
+        uint64_t hot = smem_budget > kRootBytes ? (smem_budget - kRootBytes) / 16 : 0;
+        if (d->opt_hot_records >= 0) hot = std::min<uint64_t>(hot, (uint64_t)d->opt_hot_records);
+        hot = std::min<uint64_t>(hot, d->n_slots);
+        P.hot_n = (uint32_t)hot;
+        smem = kRootBytes + (size_t)hot * 16;
+    }
 
     unsigned long long* offs64 = reinterpret_cast<unsigned long long*>(d_out_offs);
     unsigned long long* tiles = static_cast<unsigned long long*>(W.tiles.p);
@@ -605,6 +699,37 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
         P.seg_len = seg_len;
         P.warm = d->max_pattern_len ? d->max_pattern_len - 1 : 0;
     }
+    if (v1 && hot_entries) {
+        if (!ensure(d->hot_tab, (size_t)hot_entries * 16)) return DACH_CUDA_ERROR;
+        if (!d->hot_ready || d->hot_tab_entries != hot_entries) {
+            // Profiling pass: walk a sample of the batch counting landings per slot, then keep, for
+            // every cache bin, the record of its most visited slot.
+            if (!ensure(d->visits, (size_t)d->n_slots * 4) || !ensure(d->best, (size_t)hot_entries * 8)) return DACH_CUDA_ERROR;
+            cudaMemsetAsync(d->visits.p, 0, (size_t)d->n_slots * 4, st);
+            cudaMemsetAsync(d->best.p, 0, (size_t)hot_entries * 8, st);
+            ScanParams Q = P;
+            Q.item_hay = nullptr;
+            Q.item_beg = nullptr;
+            Q.n_items_dev = nullptr;
+            Q.n_items = std::min<uint64_t>(n, (uint64_t)std::max<int64_t>(d->opt_profile_items, 1));
+            Q.hot_entries = 0;
+            Q.hot_tab = nullptr;
+            Q.visits = static_cast<uint32_t*>(d->visits.p);
+            const size_t psmem = kRoot4Bytes + (size_t)LANE_Q * threads * sizeof(QEntry);
+            if (!cuda_ok(launch_std(mode, Q, grid, threads, psmem, st, L2Window(), false, true), "profile launch")) return DACH_CUDA_ERROR;
+            uint32_t shift = 0;
+            while ((1u << shift) < hot_entries) ++shift;
+            k_hot_pick<<<d->sm_count * 4, 256, 0, st>>>(Q.visits, d->n_slots, hot_entries - 1, static_cast<unsigned long long*>(d->best.p));
+            k_hot_fill<<<(hot_entries + 255) / 256, 256, 0, st>>>(static_cast<const unsigned long long*>(d->best.p), d->d_crec, hot_entries,
+                                                               shift, static_cast<uint4*>(d->hot_tab.p));
+            cudaMemsetAsync(W.ctrl.p, 0, sizeof(ScanCtrl), st);  // the pass consumed the item counter
+            d->launches += 3;
+            d->hot_ready = true;
+            d->hot_tab_entries = hot_entries;
+        }
+        P.hot_tab = static_cast<const uint4*>(d->hot_tab.p);
+        P.hot_entries = hot_entries;
+    }
     L2Window win;
     if (d->opt_l2_persist && d->l2_persist > 0 && v1) {
         // the lane-machine kernels touch the compact records, the opos table and the outputs
@@ -613,7 +738,7 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
         win.hit_ratio = (float)std::min(1.0, (double)d->l2_persist / (double)win.bytes);
     }
     cudaEventRecord(W.ev[3], st);
-    if (!cuda_ok(v1 ? launch_std(mode, P, grid, threads, smem, st, win, ctas_per_sm >= 2) : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
+    if (!cuda_ok(v1 ? launch_std(mode, P, grid, threads, smem, st, win, ctas_per_sm >= 2, false) : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
                  "k_scan launch"))
         return DACH_CUDA_ERROR;
     cudaEventRecord(W.ev[1], st);
@@ -732,6 +857,8 @@ void dach_dev_free(dach_dev* d) {
     cudaFree(d->image_base);
     d->ws.release();
     for (Workspace& w : d->slot) w.release();
+    for (DevBuf* b : {&d->hot_tab, &d->visits, &d->best})
+        if (b->p) cudaFree(b->p);
     delete d;
 }
 
@@ -897,6 +1024,14 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
         d->opt_seg_len = value;
     else if (k == "dbg")
         d->opt_dbg = value;
+    else if (k == "hot_entries") {
+        d->opt_hot_entries = value;
+        d->hot_ready = false;
+    } else if (k == "profile_items") {
+        d->opt_profile_items = value;
+        d->hot_ready = false;
+    } else if (k == "reprofile")
+        d->hot_ready = false;
     else {
         set_error("unknown option " + k);
         return DACH_INVALID_ARGUMENT;

@@ -83,6 +83,9 @@ struct ScanParams {
     const uint4* crec;           // compact records (lane-machine kernels), nullptr if > 2^24 slots
     const uint32_t* opos_tab;    // output_pos per slot (lane-machine kernels)
     uint32_t root_base;          // BASE of ROOT
+    const uint4* hot_tab;        // state cache image (global), hot_entries records; staged into shared memory
+    uint32_t hot_entries;        // power of two, 0 = none
+    uint32_t* visits;            // per-slot landing counters (profiling pass)
     const uint32_t* mapper;
     uint32_t mapper_len;
     uint32_t n_slots;
@@ -560,6 +563,16 @@ struct QEntry {
     uint32_t end, slot;
 };
 
+// State cache entries are compact records whose spare bits carry a 14-bit tag: bits 2..7 of w1 and
+// bits 0..7 of w2.  The record's consumers ignore those bits (flags are bits 0..1 of w1).
+constexpr uint32_t HOT_TAG_INVALID = 0x3fffu;
+DACH_HD uint32_t hot_tag(const uint4& e) { return (((e.y >> 2) & 0x3fu) << 8) | (e.z & 0xffu); }
+DACH_HD uint4 hot_entry(uint4 rec, uint32_t tag) {
+    rec.y = (rec.y & ~0xfcu) | ((tag >> 8) << 2);
+    rec.z = (rec.z & ~0xffu) | (tag & 0xffu);
+    return rec;
+}
+
 struct LaneStd {
     const uint8_t* hay;
     uint32_t len, pos, item;
@@ -577,8 +590,11 @@ struct LaneStd {
 
 struct StdEnv {
     const uint4* glob;     // compact records in global memory
-    const uint4* hot;      // leading records in shared memory
-    uint32_t hot_n;
+    const uint4* hot;      // shared-memory state cache: direct-mapped, entry (slot & hot_mask) holds the
+                           // record of one hot slot with (slot >> hot_shift) stored in its spare bits
+    uint32_t hot_mask;     // entries - 1 (entries is a power of two), 0 = no cache
+    uint32_t hot_shift;    // log2(entries)
+    uint32_t* visits;      // profiling pass only: landings per slot
     const uint4* root4;    // dense root row (shared memory)
     const uint32_t* opos;  // output_pos per slot (global)
     const uint8_t* text_end;
@@ -618,7 +634,8 @@ DACH_HD uint4 ld_text16(const uint8_t* q, const uint8_t* text_end, const uint8_t
 
 #if defined(DACH_EMU)
 struct EmuStats {
-    unsigned long long steps, probes, hits, miss_known, miss_f2root, learns, root_falls, root_stay, sig_skips, pushes;
+    unsigned long long steps, probes, hits, miss_known, miss_f2root, learns, root_falls, root_stay, sig_skips, pushes,
+        cache_hits;
 };
 extern EmuStats g_emu_stats;
 #define DACH_STAT(f) (++g_emu_stats.f)
@@ -626,7 +643,7 @@ extern EmuStats g_emu_stats;
 #define DACH_STAT(f)
 #endif
 
-template <int MODE>
+template <int MODE, bool PROFILE = false>
 struct StdMachine {
     static DACH_HD const uint8_t* block_of(const LaneStd& L) {
         return reinterpret_cast<const uint8_t*>(((uintptr_t)L.hay + L.pos) & ~(uintptr_t)15);
@@ -699,7 +716,14 @@ struct StdMachine {
         // ---- phase 3: the one record fetch ---------------------------------------------------------
         if (run && !landed && (L.fl & (F_PROBE | F_LEARN)) != 0) {
             const uint32_t a = L.addr;
-            const uint4 x = a < Ev.hot_n ? Ev.hot[a] : ld_u4(Ev.glob + a);
+            uint4 x;
+            bool cached = false;
+            if (Ev.hot_mask) {
+                x = Ev.hot[a & Ev.hot_mask];
+                cached = hot_tag(x) == (a >> Ev.hot_shift);
+                if (cached) DACH_STAT(cache_hits);
+            }
+            if (!cached) x = ld_u4(Ev.glob + a);
             if (L.fl & F_PROBE) {
                 DACH_STAT(probes);
                 if ((x.x & 0xffu) == L.c) {
@@ -729,6 +753,13 @@ struct StdMachine {
         // ---- phase 4: land (the byte is consumed; the lane sits in the state described by r) ---------
         if (landed) {
             ++L.pos;
+            if (PROFILE) {
+#if defined(__CUDA_ARCH__)
+                atomicAdd(Ev.visits + slot, 1u);
+#else
+                ++Ev.visits[slot];
+#endif
+            }
             uint32_t fl = (L.fl & ~(F_PROBE | F_LEARN | F_FALL | F_PF2R)) | F_KNOW | ((r.y & CF_F2ROOT) ? F_PF2R : 0u);
             if ((((uint32_t)(uintptr_t)L.hay + L.pos) & 15u) == 0) {  // crossed into the next window
                 L.cw = L.nw;
@@ -760,6 +791,10 @@ struct StdMachine {
 
     // ---- service pieces ---------------------------------------------------------------------------
     static DACH_HD void drain(LaneStd& L, const StdEnv& Ev, const ScanParams& P, Emitter& E) {
+        if (PROFILE) {  // the profiling pass only counts landings
+            L.qn = 0;
+            return;
+        }
         for (uint32_t j = 0; j < (uint32_t)LANE_Q; ++j) {
             if (j < L.qn) {
                 const QEntry e = Ev.q[j * Ev.q_stride];
@@ -791,6 +826,7 @@ struct StdMachine {
             L.len = end < hay_len ? end : hay_len;
             start = beg > P.warm ? beg - P.warm : 0;  // warm-up: the state at `beg` only depends on these bytes
         }
+        if (PROFILE && L.len > 16384u) L.len = 16384u;  // a sample is enough
         L.pos = start;
         L.from = beg;
         L.item = (uint32_t)item;

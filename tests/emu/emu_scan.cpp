@@ -42,9 +42,9 @@ static void run_items(const ScanParams& P, const RecView& V, const uint8_t* lo, 
 
 // Warp-level driver of the v1 lane machine, mirroring k_scan_std in dev_scan.cu with the warp
 // collectives (ballot / any / shuffle) written out as loops over 32 lane states.
-template <int MODE>
+template <int MODE, bool PROFILE>
 static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* lo, int n_warps) {
-    using M = StdMachine<MODE>;
+    using M = StdMachine<MODE, PROFILE>;
     struct Warp {
         LaneStd L[32];
         Emitter E[32];
@@ -77,7 +77,7 @@ static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* 
                 if (w.L[l].fl & F_ACTIVE) M::drain(w.L[l], w.Ev[l], P, w.E[l]);
             for (int l = 0; l < 32; ++l)
                 if ((w.L[l].fl & (F_ACTIVE | F_DONE)) == (F_ACTIVE | F_DONE)) {
-                    w.E[l].finish(P);
+                    if (!PROFILE) w.E[l].finish(P);
                     w.L[l].fl = 0;
                 }
             unsigned m = 0;
@@ -189,14 +189,49 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     const uint8_t* lo = text + (n ? offs[0] : 0);
     const uint8_t* hi = text + (n ? offs[n] : 0);
     if (v1) {
-        std::vector<uint32_t> chot(img.crec.begin(), img.crec.begin() + (size_t)hot_n * 4);
-        chot.resize(chot.size() + 4);
-        const StdEnv Ev{reinterpret_cast<const uint4*>(img.crec.data()), reinterpret_cast<const uint4*>(chot.data()), hot_n, P.root4,
-                        img.opos_tab.data(), P.text_end, img.root_base, P.root_opos ? CF_OUT : 0u, nullptr, 0, 0};
+        // state cache: profiling pass over the first items, then k_hot_pick / k_hot_fill
+        uint32_t entries = hot_n;
+        while (entries & (entries - 1)) entries &= entries - 1;  // power of two
+        if (entries && (uint64_t)img.n_slots > (uint64_t)entries * HOT_TAG_INVALID) entries = 0;
+        uint32_t shift = 0;
+        while ((1u << shift) < entries) ++shift;
+        std::vector<uint32_t> visits(img.n_slots ? img.n_slots : 1, 0);
+        std::vector<uint32_t> tab((size_t)(entries ? entries : 1) * 4, 0);
+        StdEnv Ev{reinterpret_cast<const uint4*>(img.crec.data()), reinterpret_cast<const uint4*>(tab.data()), 0u, 0u, visits.data(),
+                  P.root4, img.opos_tab.data(), P.text_end, img.root_base, P.root_opos ? CF_OUT : 0u, nullptr, 0, 0};
         const int n_warps = 3;
-        if (mode == M_FIND) run_items_v1<M_FIND>(P, Ev, lo, n_warps);
-        if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING>(P, Ev, lo, n_warps);
-        if (mode == M_NO_SUFFIX) run_items_v1<M_NO_SUFFIX>(P, Ev, lo, n_warps);
+        if (entries) {
+            ScanParams Q = P;
+            Q.item_hay = nullptr;
+            Q.item_beg = nullptr;
+            Q.n_items = n < 7 ? n : 7;  // a small sample, like the device pass
+            if (mode == M_FIND) run_items_v1<M_FIND, true>(Q, Ev, lo, n_warps);
+            if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING, true>(Q, Ev, lo, n_warps);
+            if (mode == M_NO_SUFFIX) run_items_v1<M_NO_SUFFIX, true>(Q, Ev, lo, n_warps);
+            ctrl.next_item = 0;
+            std::vector<uint64_t> best(entries, 0);
+            for (uint32_t sidx = 0; sidx < img.n_slots; ++sidx)
+                if (visits[sidx]) {
+                    const uint64_t v = ((uint64_t)visits[sidx] << 32) | sidx;
+                    if (v > best[sidx & (entries - 1)]) best[sidx & (entries - 1)] = v;
+                }
+            for (uint32_t b = 0; b < entries; ++b) {
+                uint4 e;
+                if (best[b]) {
+                    const uint32_t slot = (uint32_t)best[b];
+                    e = hot_entry(reinterpret_cast<const uint4*>(img.crec.data())[slot], slot >> shift);
+                } else {
+                    e.x = e.y = e.z = e.w = 0;
+                    e = hot_entry(e, HOT_TAG_INVALID);
+                }
+                memcpy(&tab[(size_t)b * 4], &e, 16);
+            }
+            Ev.hot_mask = entries - 1;
+            Ev.hot_shift = shift;
+        }
+        if (mode == M_FIND) run_items_v1<M_FIND, false>(P, Ev, lo, n_warps);
+        if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING, false>(P, Ev, lo, n_warps);
+        if (mode == M_NO_SUFFIX) run_items_v1<M_NO_SUFFIX, false>(P, Ev, lo, n_warps);
     } else
     switch ((charwise ? 4 : 0) + mode) {
         case 0: run_items<false, M_FIND>(P, V, lo, hi); break;

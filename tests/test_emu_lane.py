@@ -35,7 +35,7 @@ def test_golden_vectors(variant, iterator, kind, t):
     wire = O.OraclePma.build(t["patterns"], charwise=cw, match_kind=O.KIND[kind]).serialize()
     hay = t["haystack"].encode()
     text = np.frombuffer(hay, dtype=np.uint8)
-    for hot, kernel in ((0, 1), (1 << 20, 1), (3, 0)):
+    for hot, kernel in ((0, 1), (64, 1), (3, 0)):
         rc, m, oo, need = E.scan(wire, cw, MODE[iterator], text, np.array([0, len(hay)], dtype=np.uint64), hot_n=hot,
                                  kernel=kernel)
         assert rc == 0
@@ -74,7 +74,7 @@ def test_random_batches(seed, kind, cw):
     modes = [3] if kind else [0, 1, 2]
     for mode in modes:
         ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
-        for hot, kernel in ((0, 1), (7, 1), (1 << 20, 1), (5, 0)):
+        for hot, kernel in ((0, 1), (2, 1), (16, 1), (1 << 12, 1), (5, 0)):
             rc, m, oo, need = E.scan(wire, cw, mode, text, offs, hot_n=hot, kernel=kernel)
             assert rc == 0
             assert need == ref["total"]
