@@ -479,7 +479,7 @@ template <bool CW, int MODE>
 cudaError_t launch_scan_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
     static bool attr_done = false;  // per instantiation
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_scan<CW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_scan<CW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -497,7 +497,7 @@ template <int MODE, int MAXT, int MINB, bool PROFILE>
 cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_scan_std<MODE, MAXT, MINB, PROFILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_scan_std<MODE, MAXT, MINB, PROFILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -653,7 +653,7 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     P.ctrl = static_cast<ScanCtrl*>(W.ctrl.p);
     P.dbg = (uint32_t)d->opt_dbg;
 
-    const size_t smem_budget = std::min<size_t>(d->smem_optin, 227 * 1024) / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
+    const size_t smem_budget = std::min<size_t>(d->smem_optin, 226 * 1024) / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
     size_t smem;
     uint32_t hot_entries = 0;
     if (v1) {
