@@ -442,7 +442,9 @@ struct dach_dev {
     DevBuf hot_tab, visits, best;
     bool hot_ready = false;
     uint32_t hot_tab_entries = 0;
-    int64_t opt_hot_entries = 8192;   // power of two, 0 = off
+    // Off by default: on the C3 workload L1 alone serves the hot states as well as this cache does
+    // (113 vs 116 GB/s, profiles/r1_cache_experiments.md); kept as an option (power of two).
+    int64_t opt_hot_entries = 0;
     int64_t opt_profile_items = 2048;
     int64_t opt_dbg = 0;
     int64_t opt_seg_len = 0;  // 0: automatic; > 0: forced segment length; < 0: no segmentation

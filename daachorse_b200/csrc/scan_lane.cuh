@@ -105,7 +105,7 @@ struct ScanParams {
     const unsigned long long* n_items_dev;
     uint32_t seg_len, warm;
     uint32_t dbg;  // experiment switches (bench --option dbg=): 1 = count matches but do not store them,
-                   // 2 = text via ld.global.cs, 4 = text via ld.global.nc (L1 allocating)
+                   // 2 = text via ld.global.cs, 4 = text via ld.global.nc.L1::no_allocate
     // results
     uint32_t* counts;  // matches per item
     uint32_t* pool;
@@ -612,14 +612,17 @@ DACH_HD uint4 ld_text16(const uint8_t* q, const uint8_t* text_end, const uint8_t
     (void)dbg;
     if (q >= text_end) return w;  // never touch a block that starts past the text
 #if defined(__CUDA_ARCH__)
+    // Default: read-only path WITH L1 allocation.  A lane comes back to the same 32-byte sector for
+    // its next 16 bytes; with L1::no_allocate every one of those loads went to DRAM (8.2 GB read per
+    // GiB scanned vs 2.5 GB, profiles/r1_cache_experiments.md).
     if (dbg & 2u)
         asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(q));
     else if (dbg & 4u)
-        asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(q));
-    else
         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
                      : "l"(q));
+    else
+        asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(q));
 #elif defined(DACH_EMU)
     uint32_t v[4] = {0, 0, 0, 0};
     for (int i = 0; i < 16; ++i) {

@@ -133,7 +133,7 @@ def test_kernel_options_do_not_change_results():
     base = pma.scan_batch_host(D.FIND_OVERLAPPING, text, offs)
     for opts in ({"hot_records": -1}, {"hot_records": 17}, {"threads": 128}, {"threads": 512, "ctas_per_sm": 2},
                  {"kernel": 0}, {"kernel": 0, "hot_records": 100}, {"l2_persist": 0}, {"hot_entries": 0},
-                 {"hot_entries": 64}, {"hot_entries": 4096, "profile_items": 3}, {"dbg": 4}, {"dbg": 2}):
+                 {"hot_entries": 64}, {"hot_entries": 8192}, {"hot_entries": 4096, "profile_items": 3}, {"dbg": 4}, {"dbg": 2}):
         for k, v in opts.items():
             pma.set_option(k, v)
         r = pma.scan_batch_host(D.FIND_OVERLAPPING, text, offs)
@@ -143,7 +143,7 @@ def test_kernel_options_do_not_change_results():
         pma.set_option("ctas_per_sm", 1)
         pma.set_option("kernel", 1)
         pma.set_option("l2_persist", 1)
-        pma.set_option("hot_entries", 8192)
+        pma.set_option("hot_entries", 0)
         pma.set_option("profile_items", 2048)
         pma.set_option("dbg", 0)
 
