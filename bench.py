@@ -147,6 +147,8 @@ def main():
     ap.add_argument("--ref-haystacks", type=int, default=262144)
     ap.add_argument("--cpu-haystacks", type=int, default=262144)
     ap.add_argument("--option", action="append", default=[], help="kernel option name=value")
+    ap.add_argument("--chunks", type=int, default=4, help="N > 1: chunks per step (gather of chunk k overlaps scan of k+1)")
+    ap.add_argument("--reserve-sms", type=int, default=8, help="N > 1: SMs left free for the concurrent NCCL gather")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -184,20 +186,50 @@ def main():
     torch.cuda.synchronize()
     setup_s = time.time() - t_setup
 
-    # sizing pass (not timed): learn the match count, allocate the output once
-    first = pma.scan_batch_device(D.FIND_OVERLAPPING, text_t, offs_t)
-    total_matches = int(first.matches.shape[0])
-    out = torch.empty((total_matches + 1024, 3), dtype=torch.int32, device=dev)
-    out_offs = torch.empty(n + 1, dtype=torch.int64, device=dev)
-    del first
+    # sizing pass (not timed): learn the match counts, allocate the outputs once.  For N > 1 the batch is
+    # scanned in chunks so that the NCCL gather of chunk k overlaps the scan of chunk k+1.
+    n_chunks = 1 if world == 1 else args.chunks
+    bounds = [n * k // n_chunks for k in range(n_chunks + 1)]
+    chunk_offs = [offs_t[bounds[k]: bounds[k + 1] + 1] for k in range(n_chunks)]
+    outs, out_offs_l, chunk_matches = [], [], []
+    for k in range(n_chunks):
+        first = pma.scan_batch_device(D.FIND_OVERLAPPING, text_t, chunk_offs[k])
+        chunk_matches.append(int(first.matches.shape[0]))
+        del first
+    total_matches = sum(chunk_matches)
+    for k in range(n_chunks):
+        outs.append(torch.empty((chunk_matches[k] + 1024, 3), dtype=torch.int32, device=dev))
+        out_offs_l.append(torch.empty(bounds[k + 1] - bounds[k] + 1, dtype=torch.int64, device=dev))
+    out_offs = out_offs_l[0]
 
-    from daachorse_b200 import shard
+    pads, gbufs, opads, gobufs = [], [], [], []
+    if world > 1:
+        if args.reserve_sms:
+            pma.set_option("reserve_sms", args.reserve_sms)
+        cm = torch.tensor(chunk_matches, dtype=torch.int64, device=dev)
+        dist.all_reduce(cm, op=dist.ReduceOp.MAX)
+        for k in range(n_chunks):
+            mx = int(cm[k].item())
+            pads.append(torch.zeros((mx, 3), dtype=torch.int32, device=dev))
+            opads.append(torch.zeros(bounds[k + 1] - bounds[k] + 1, dtype=torch.int64, device=dev))
+            gbufs.append([torch.empty_like(pads[k]) for _ in range(world)] if rank == 0 else None)
+            gobufs.append([torch.empty_like(opads[k]) for _ in range(world)] if rank == 0 else None)
 
     def step():
-        r = pma.scan_batch_device(D.FIND_OVERLAPPING, text_t, offs_t, out=out, out_offs=out_offs)
-        if world > 1:
-            # the one exchange step of the path: per-shard match buffers and offsets to rank 0 over NVLink
-            shard.gather_results(r.matches, r.offsets, dst=0)
+        works = []
+        r = None
+        for k in range(n_chunks):
+            r = pma.scan_batch_device(D.FIND_OVERLAPPING, text_t, chunk_offs[k], out=outs[k], out_offs=out_offs_l[k])
+            if world > 1:
+                # the one exchange step of the path: this chunk's match buffer and offsets go to rank 0
+                # over NVLink (padded gather; counts are known from the sizing pass) while the next
+                # chunk is being scanned
+                pads[k][: chunk_matches[k]].copy_(r.matches)
+                opads[k].copy_(r.offsets)
+                works.append(dist.gather(pads[k], gbufs[k], dst=0, async_op=True))
+                works.append(dist.gather(opads[k], gobufs[k], dst=0, async_op=True))
+        for w in works:
+            w.wait()
         return r
 
     def barrier():
@@ -298,7 +330,7 @@ def main():
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample ----------------------
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # the CPU baseline is reported on rank 0 at N = 1 only
         import oracle_api as O
 
         cores = os.cpu_count() or 1
@@ -319,7 +351,7 @@ def main():
                    nc, hay_len, ctext.size / 2**20, reps, cores, dt),
                "note": "C restatement of daachorse 4.0.0 CPU path (Rust toolchain unavailable)"}
         # parity spot check in the same run: per-haystack counts of the sample
-        oo = out_offs[: nc + 1].cpu().numpy()
+        oo = out_offs_l[0][: nc + 1].cpu().numpy()
         cpu["parity_counts_equal"] = bool(np.array_equal(np.diff(oo), ref["counts"].astype(np.int64)))
 
     line = {
@@ -333,7 +365,9 @@ def main():
                    "bytes_per_gpu": text_bytes, "matches_per_step_per_gpu": total_matches,
                    "matches_per_byte": total_matches / text_bytes,
                    "l2": "inputs (%.1f GiB per GPU) are larger than L2; no flush needed" % (text_bytes / 2**30),
-                   "parallelism": "haystack shards, one rank per GPU" + ("; NCCL gather of match buffers to rank 0 in the step" if world > 1 else ""),
+                   "parallelism": "haystack shards, one rank per GPU" + (
+                       "; NCCL gather of match buffers to rank 0 inside the step, %d chunks pipelined, %d SMs reserved" % (
+                           n_chunks, args.reserve_sms) if world > 1 else ""),
                    "setup_s": setup_s},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches2 - launches1), "launches_per_step": (launches2 - launches1) / args.steps,

@@ -446,6 +446,7 @@ struct dach_dev {
     // (113 vs 116 GB/s, profiles/r1_cache_experiments.md); kept as an option (power of two).
     int64_t opt_hot_entries = 0;
     int64_t opt_profile_items = 2048;
+    int64_t opt_reserve_sms = 0;  // SMs left free for concurrent kernels (e.g. the NCCL gather of the previous chunk)
     int64_t opt_dbg = 0;
     int64_t opt_seg_len = 0;  // 0: automatic; > 0: forced segment length; < 0: no segmentation
     // options
@@ -593,7 +594,8 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     int threads = (int)std::min<int64_t>(std::max<int64_t>(d->opt_threads, 32), kMaxThreads);
     threads = (threads / 32) * 32;
     int ctas_per_sm = (int)std::min<int64_t>(std::max<int64_t>(d->opt_ctas_per_sm, 1), 2048 / threads);
-    const int grid = d->sm_count * ctas_per_sm;
+    const int free_sms = (int)std::min<int64_t>(std::max<int64_t>(d->opt_reserve_sms, 0), d->sm_count - 1);
+    const int grid = (d->sm_count - free_sms) * ctas_per_sm;
     // the lane machine serves the bytewise Standard iterators; find_iter with an empty pattern
     // (it only reports zero-length matches, src/bytewise/iter.rs:60-85) keeps the simple kernel
     const bool v1 = d->opt_kernel >= 1 && d->d_crec && !d->charwise && mode != M_LEFTMOST && !(mode == M_FIND && d->root_opos != 0);
@@ -1026,6 +1028,8 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
         d->opt_seg_len = value;
     else if (k == "dbg")
         d->opt_dbg = value;
+    else if (k == "reserve_sms")
+        d->opt_reserve_sms = value;
     else if (k == "hot_entries") {
         d->opt_hot_entries = value;
         d->hot_ready = false;
