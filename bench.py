@@ -238,11 +238,12 @@ def main():
         torch.cuda.synchronize()
 
     launches0 = pma.stats()["launches"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    n_before = len(sampler.rows)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches1 = pma.stats()["launches"]
     scan_ms, pipe_ms = [], []
@@ -255,7 +256,9 @@ def main():
         pipe_ms.append(st["total_ms"])
     ev1.record()
     barrier()
+    time.sleep(0.25)  # let nvidia-smi flush its last samples
     clocks = sampler.stop()
+    clocks["note"] = "nvidia-smi -lms 100 from before the warm-up to the end of the timed region (%d samples before it)" % n_before
     launches2 = pma.stats()["launches"]
     ms = ev0.elapsed_time(ev1) / args.steps
     if world > 1:
@@ -314,7 +317,7 @@ def main():
     k_ms = float(np.mean(scan_ms))
     achieved = text_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_scan<false, M_OVERLAPPING>", "kernel_ms": k_ms,
+                "traffic": None, "kernel": "k_scan_std<M_OVERLAPPING, 1024, 1> (lane machine)", "kernel_ms": k_ms,
                 "pipeline_ms": float(np.mean(pipe_ms)),
                 "algorithmic_bytes_per_launch": text_bytes, "peak_source": peak_src,
                 "note": "algorithmic bytes = 1 B read per haystack byte x bytes per launch (DESIGN.md); traffic "
