@@ -65,7 +65,7 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def stop(self, skip=0):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -75,7 +75,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[skip:] if len(self.rows) > skip else self.rows
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -257,8 +258,8 @@ def main():
     ev1.record()
     barrier()
     time.sleep(0.25)  # let nvidia-smi flush its last samples
-    clocks = sampler.stop()
-    clocks["note"] = "nvidia-smi -lms 100 from before the warm-up to the end of the timed region (%d samples before it)" % n_before
+    clocks = sampler.stop(skip=n_before)
+    clocks["note"] = "nvidia-smi -lms 100 started before the warm-up; the %d samples taken before the timed region are dropped" % n_before
     launches2 = pma.stats()["launches"]
     ms = ev0.elapsed_time(ev1) / args.steps
     if world > 1:
