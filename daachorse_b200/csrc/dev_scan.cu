@@ -95,31 +95,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-template <int MODE, int MAXT, int MINB, bool PROFILE>
+template <int MODE, int MAXT, int MINB, bool PROFILE, bool HOT>
 __global__ void __launch_bounds__(MAXT, MINB) k_scan_std(ScanParams P) {
-    // dynamic shared memory: [root row 4 KiB][state cache hot_entries x 16 B][event queues LANE_Q x blockDim x 8 B]
+    // dynamic shared memory: [state cache hot_entries x 16 B (HOT only)][event queues LANE_Q x blockDim x 8 B]
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint4* s_hot = reinterpret_cast<uint4*>(smem_raw);
+    QEntry* s_queue = reinterpret_cast<QEntry*>(smem_raw + (HOT ? (size_t)P.hot_entries * 16 : 0));
     __shared__ __align__(8) uint64_t s_bar;
-    uint4* s_root4 = reinterpret_cast<uint4*>(smem_raw);
-    uint4* s_hot = reinterpret_cast<uint4*>(smem_raw + kRoot4Bytes);
-    QEntry* s_queue = reinterpret_cast<QEntry*>(smem_raw + kRoot4Bytes + (size_t)P.hot_entries * 16);
-    // one elected thread arms the mbarrier and lets the TMA engine stage the root row and the state
-    // cache (up to ~130 KiB) while the other threads set up
-    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t hot_bytes = P.hot_entries * 16u;
-        mbar_expect_tx(&s_bar, kRoot4Bytes + hot_bytes);
-        tma_bulk_g2s(s_root4, P.root4, kRoot4Bytes, &s_bar);
-        for (uint32_t off = 0; off < hot_bytes; off += 32768u)
-            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_hot) + off, reinterpret_cast<const unsigned char*>(P.hot_tab) + off,
-                         min(32768u, hot_bytes - off), &s_bar);
+    if (HOT) {
+        // one elected thread arms the mbarrier and lets the TMA engine stage the state cache
+        // (up to 128 KiB) while the other threads set up
+        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t hot_bytes = P.hot_entries * 16u;
+            mbar_expect_tx(&s_bar, hot_bytes);
+            for (uint32_t off = 0; off < hot_bytes; off += 32768u)
+                tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_hot) + off, reinterpret_cast<const unsigned char*>(P.hot_tab) + off,
+                             min(32768u, hot_bytes - off), &s_bar);
+        }
     }
 
-    using M = StdMachine<MODE, PROFILE>;
+    using M = StdMachine<MODE, PROFILE, HOT>;
     uint32_t hot_shift = 0;
     while ((1u << hot_shift) < P.hot_entries) ++hot_shift;
-    const StdEnv Ev{P.crec,     s_hot,      P.hot_entries ? P.hot_entries - 1u : 0u, hot_shift, P.visits, s_root4, P.opos_tab,
+    const StdEnv Ev{P.crec,     s_hot,      HOT ? P.hot_entries - 1u : 0u, hot_shift, P.visits, nullptr, P.opos_tab,
                     P.text_end, P.root_base, P.root_opos ? CF_OUT : 0u, s_queue + threadIdx.x, blockDim.x, P.dbg};
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_std(ScanParams P) {
     E.begin(0);
     bool exhausted = false;
     const unsigned long long n_items = P.n_items_dev ? *P.n_items_dev : P.n_items;
-    mbar_wait(&s_bar, 0);
+    if (HOT) mbar_wait(&s_bar, 0);
     for (;;) {
         // ---- service phase (the warp is converged here) ----
         if (L.fl & F_ACTIVE) M::drain(L, Ev, P, E);
@@ -290,18 +290,30 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const Scan
     if (out_offs[n_items] > out_cap) return;
     const uint32_t used = min(ctrl->blk_cursor, pool_blocks);
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warps_per_cta = blockDim.x >> 5;
-    for (uint64_t b = (uint64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); b < used;
-         b += (uint64_t)gridDim.x * warps_per_cta) {
-        const uint32_t* blk = pool + b * BLK_WORDS;
-        const uint32_t item = blk[0], seq = blk[1];
-        const uint32_t cnt = counts[item];
-        const uint32_t first = seq * BLK_MATCHES;
-        const uint32_t nm = min(BLK_MATCHES, cnt - first);
-        uint32_t* dst = out_words + (out_offs[item] + first) * 3ull;
-        const uint32_t nw = nm * 3;
-        if (lane < nw) dst[lane] = blk[2 + lane];
-        if (lane + 32 < nw) dst[lane + 32] = blk[2 + lane + 32];
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    constexpr int U = 4;  // blocks in flight per warp: the header -> (count, offset) -> data chains overlap
+    for (uint64_t b0 = warp * U; b0 < used; b0 += n_warps * U) {
+        const uint32_t* blk[U];
+        uint32_t item[U], seq[U], w0[U], w1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t b = b0 + u;
+            blk[u] = pool + (b < used ? b : b0) * BLK_WORDS;
+            item[u] = blk[u][0];
+            seq[u] = blk[u][1];
+            w0[u] = blk[u][2 + lane];
+            w1[u] = lane < 28 ? blk[u][2 + 32 + lane] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (b0 + u >= used) continue;
+            const uint32_t first = seq[u] * BLK_MATCHES;
+            const uint32_t nw = min(BLK_MATCHES, counts[item[u]] - first) * 3;
+            uint32_t* dst = out_words + (out_offs[item[u]] + first) * 3ull;
+            if (lane < nw) dst[lane] = w0[u];
+            if (lane + 32 < nw) dst[lane + 32] = w1[u];
+        }
     }
 }
 
@@ -496,11 +508,11 @@ struct L2Window {
     float hit_ratio = 1.0f;
 };
 
-template <int MODE, int MAXT, int MINB, bool PROFILE>
+template <int MODE, int MAXT, int MINB, bool PROFILE, bool HOT>
 cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_scan_std<MODE, MAXT, MINB, PROFILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_scan_std<MODE, MAXT, MINB, PROFILE, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -522,29 +534,40 @@ cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem
         cfg.attrs = at;
         cfg.numAttrs = 1;
     }
-    return cudaLaunchKernelEx(&cfg, k_scan_std<MODE, MAXT, MINB, PROFILE>, P);
+    return cudaLaunchKernelEx(&cfg, k_scan_std<MODE, MAXT, MINB, PROFILE, HOT>, P);
 }
 
 cudaError_t launch_std(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w,
                        bool dense_hint, bool profile) {
     // two register budgets: 1024 threads x 1 CTA/SM (64 regs) or up to 768 threads x 2 CTAs/SM (42 regs)
     const bool dense = threads <= 768 && (grid % 2 == 0) && dense_hint;
+    const bool hot = P.hot_entries != 0;
     if (profile) {
         switch (mode) {
-            case M_FIND: return launch_std_t<M_FIND, 1024, 1, true>(P, grid, threads, smem, st, w);
-            case M_OVERLAPPING: return launch_std_t<M_OVERLAPPING, 1024, 1, true>(P, grid, threads, smem, st, w);
-            case M_NO_SUFFIX: return launch_std_t<M_NO_SUFFIX, 1024, 1, true>(P, grid, threads, smem, st, w);
+            case M_FIND: return launch_std_t<M_FIND, 1024, 1, true, false>(P, grid, threads, smem, st, w);
+            case M_OVERLAPPING: return launch_std_t<M_OVERLAPPING, 1024, 1, true, false>(P, grid, threads, smem, st, w);
+            case M_NO_SUFFIX: return launch_std_t<M_NO_SUFFIX, 1024, 1, true, false>(P, grid, threads, smem, st, w);
         }
         return cudaErrorInvalidValue;
     }
-    switch (mode * 2 + (dense ? 1 : 0)) {
-        case M_FIND * 2: return launch_std_t<M_FIND, 1024, 1, false>(P, grid, threads, smem, st, w);
-        case M_OVERLAPPING * 2: return launch_std_t<M_OVERLAPPING, 1024, 1, false>(P, grid, threads, smem, st, w);
-        case M_NO_SUFFIX * 2: return launch_std_t<M_NO_SUFFIX, 1024, 1, false>(P, grid, threads, smem, st, w);
-        case M_FIND * 2 + 1: return launch_std_t<M_FIND, 768, 2, false>(P, grid, threads, smem, st, w);
-        case M_OVERLAPPING * 2 + 1: return launch_std_t<M_OVERLAPPING, 768, 2, false>(P, grid, threads, smem, st, w);
-        case M_NO_SUFFIX * 2 + 1: return launch_std_t<M_NO_SUFFIX, 768, 2, false>(P, grid, threads, smem, st, w);
+#define DACH_CASE(M, D, H)                                                                  \
+    case ((M)*4 + (D)*2 + (H)):                                                               \
+        return launch_std_t<M, (D) ? 768 : 1024, (D) ? 2 : 1, false, (H) != 0>(P, grid, threads, smem, st, w);
+    switch (mode * 4 + (dense ? 2 : 0) + (hot ? 1 : 0)) {
+        DACH_CASE(M_FIND, 0, 0)
+        DACH_CASE(M_FIND, 0, 1)
+        DACH_CASE(M_FIND, 1, 0)
+        DACH_CASE(M_FIND, 1, 1)
+        DACH_CASE(M_OVERLAPPING, 0, 0)
+        DACH_CASE(M_OVERLAPPING, 0, 1)
+        DACH_CASE(M_OVERLAPPING, 1, 0)
+        DACH_CASE(M_OVERLAPPING, 1, 1)
+        DACH_CASE(M_NO_SUFFIX, 0, 0)
+        DACH_CASE(M_NO_SUFFIX, 0, 1)
+        DACH_CASE(M_NO_SUFFIX, 1, 0)
+        DACH_CASE(M_NO_SUFFIX, 1, 1)
     }
+#undef DACH_CASE
     return cudaErrorInvalidValue;
 }
 
@@ -661,14 +684,14 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     size_t smem;
     uint32_t hot_entries = 0;
     if (v1) {
-        const size_t fixed = kRoot4Bytes + (size_t)LANE_Q * threads * sizeof(QEntry) + 64;
+        const size_t fixed = (size_t)LANE_Q * threads * sizeof(QEntry) + 256;
         // largest power of two that fits next to the root row and the queues
         uint64_t want = d->opt_hot_entries > 0 ? (uint64_t)d->opt_hot_entries : 0;
         while (want && fixed + want * 16 > smem_budget) want >>= 1;
         while (want & (want - 1)) want &= want - 1;
         if (want && (uint64_t)d->n_slots > want * (uint64_t)HOT_TAG_INVALID) want = 0;  // tag would not fit
         hot_entries = (uint32_t)want;
-        smem = kRoot4Bytes + (size_t)hot_entries * 16 + (size_t)LANE_Q * threads * sizeof(QEntry);
+        smem = (size_t)hot_entries * 16 + (size_t)LANE_Q * threads * sizeof(QEntry);
         P.hot_n = 0;
     } else {
         uint64_t hot = smem_budget > kRootBytes ? (smem_budget - kRootBytes) / 16 : 0;
@@ -719,7 +742,7 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
             Q.hot_entries = 0;
             Q.hot_tab = nullptr;
             Q.visits = static_cast<uint32_t*>(d->visits.p);
-            const size_t psmem = kRoot4Bytes + (size_t)LANE_Q * threads * sizeof(QEntry);
+            const size_t psmem = (size_t)LANE_Q * threads * sizeof(QEntry);
             if (!cuda_ok(launch_std(mode, Q, grid, threads, psmem, st, L2Window(), false, true), "profile launch")) return DACH_CUDA_ERROR;
             uint32_t shift = 0;
             while ((1u << shift) < hot_entries) ++shift;

@@ -556,8 +556,8 @@ constexpr uint32_t CF_OUT = 1u, CF_F2ROOT = 2u;  // flags in record word 1
 constexpr uint32_t COMPACT_MAX_SLOTS = 1u << 24;
 
 // lane flags
-constexpr uint32_t F_ACTIVE = 1u, F_DONE = 2u, F_NEED_NW = 4u, F_KNOW = 8u, F_PF2R = 16u, F_PROBE = 32u, F_LEARN = 64u,
-                   F_FALL = 128u;
+constexpr uint32_t F_ACTIVE = 1u, F_DONE = 2u, F_NEED_NW = 4u, F_OWN = 8u, F_ROOTP = 16u, F_PROBE = 32u, F_LEARN = 64u,
+                   F_FALL = 128u, F_LAND = 256u;
 
 struct QEntry {
     uint32_t end, slot;
@@ -576,16 +576,17 @@ DACH_HD uint4 hot_entry(uint4 rec, uint32_t tag) {
 struct LaneStd {
     const uint8_t* hay;
     uint32_t len, pos, item;
-    uint4 cw, nw;      // text windows
-    uint32_t c;        // byte being matched
-    uint32_t cb;       // BASE of the current candidate state
-    uint32_t sig;      // its child signature
-    uint32_t nf, nfb;  // where to fall on a miss, and its BASE (valid if F_KNOW)
-    uint32_t pend;     // failure state whose BASE is being probed (!F_KNOW)
-    uint32_t addr;     // slot to fetch
-    uint32_t qn;       // queued events
-    uint32_t fl;       // F_* flags
-    uint32_t from;     // only matches ending after this position are reported (segment start)
+    uint4 cw, nw;  // text windows
+    uint32_t c;    // byte being matched
+    // the state the lane sits in, as the fields of its compact record
+    uint32_t cb;   // BASE (0: no children)
+    uint32_t sig;  // child signature
+    uint32_t nf;   // raw word 1: efail << 8 | CF_* flags
+    uint32_t nfb;  // raw word 2: fbase << 8
+    uint32_t addr; // slot being fetched; after a landing: the slot landed on
+    uint32_t qn;   // queued events
+    uint32_t fl;   // F_* flags
+    uint32_t from; // only matches ending after this position are reported (segment start)
 };
 
 struct StdEnv {
@@ -646,7 +647,7 @@ extern EmuStats g_emu_stats;
 #define DACH_STAT(f)
 #endif
 
-template <int MODE, bool PROFILE = false>
+template <int MODE, bool PROFILE = false, bool HOT = false>
 struct StdMachine {
     static DACH_HD const uint8_t* block_of(const LaneStd& L) {
         return reinterpret_cast<const uint8_t*>(((uintptr_t)L.hay + L.pos) & ~(uintptr_t)15);
@@ -661,134 +662,133 @@ struct StdMachine {
     }
 
     // One iteration, called by all 32 lanes of the warp together.  Returns false if the lane did
-    // not step (inactive, finished, or queue full).  Phase order: next byte -> failure link ->
-    // fetch -> land.  A fetch that misses (rare once the signature filters the probes) leaves
-    // F_FALL set and takes its failure link at the start of the next iteration.
+    // not step (inactive, finished, or queue full).
+    //
+    //   phase 1  next byte; the signature decides: probe own children (F_PROBE|F_OWN) or fall (F_FALL)
+    //   phase 2  F_FALL: the next probe uses the failure state's BASE, or ROOT's BASE if the failure
+    //            state is ROOT (ROOT is probed like any other state; a miss there means "stay in ROOT")
+    //   phase 3  the one fetch; a hit adopts the record (F_LAND); a miss of a failure-state probe goes to
+    //            ROOT (CF_F2ROOT) or learns the failure state's record first (F_LEARN, rare)
+    //   phase 4  F_LAND: consume the byte, move the text window, queue an output event
+    //
+    // A lane that misses keeps its byte and retries in the next iteration; lanes never wait for each
+    // other except in the service phase.  On the C3 workload: 1.03 iterations and 1.0 fetches per byte.
     static DACH_HD bool step(LaneStd& L, const StdEnv& Ev) {
-        bool run = (L.fl & (F_ACTIVE | F_DONE)) == F_ACTIVE && L.qn != (uint32_t)LANE_Q;
+        uint32_t fl = L.fl;
+        const bool run = (fl & (F_ACTIVE | F_DONE)) == F_ACTIVE && L.qn != (uint32_t)LANE_Q;
         if (run) DACH_STAT(steps);
-        bool landed = false;
-        uint4 r;            // record the lane lands on
-        uint32_t slot = 0;  // and its slot
-        r.x = r.y = r.z = r.w = 0;
         // ---- phase 1: next byte ------------------------------------------------------------------
-        if (run && (L.fl & (F_PROBE | F_LEARN | F_FALL)) == 0) {
+        if (run && (fl & (F_PROBE | F_LEARN | F_FALL)) == 0) {
             if (L.pos >= L.len) {
-                L.fl |= F_DONE;
-                run = false;
+                fl |= F_DONE;
             } else {
                 const uint32_t o = ((uint32_t)(uintptr_t)L.hay + L.pos) & 15u;
                 const uint32_t lo = (o & 8u) ? L.cw.z : L.cw.x;
                 const uint32_t hi = (o & 8u) ? L.cw.w : L.cw.y;
-                const uint32_t word = (o & 4u) ? hi : lo;
-                L.c = (word >> ((o & 3u) * 8u)) & 0xffu;
-                L.addr = L.cb ^ L.c;
-                if ((L.sig >> (L.c & 31u)) & 1u) {
-                    L.fl |= F_PROBE;
+#if defined(__CUDA_ARCH__)
+                const uint32_t c = __byte_perm(lo, hi, (o & 7u) | 0x4440u);
+#else
+                const uint32_t c = (((o & 4u) ? hi : lo) >> ((o & 3u) * 8u)) & 0xffu;
+#endif
+                L.c = c;
+                L.addr = L.cb ^ c;
+                if ((L.sig >> (c & 31u)) & 1u) {
+                    fl |= F_PROBE | F_OWN;
                 } else {
                     DACH_STAT(sig_skips);
-                    L.fl |= F_FALL;  // certainly no child for this byte
+                    fl |= F_FALL;  // certainly no child for this byte
                 }
             }
         }
         DACH_SYNCWARP();
-        // ---- phase 2: take the failure link (nf, nfb are known) -------------------------------------
-        if (run && (L.fl & F_FALL)) {
-            L.fl &= ~F_FALL;
-            if (L.nf == D_ROOT) {
-                DACH_STAT(root_falls);
-                r = Ev.root4[L.c];  // dense ROOT row (src/bytewise.rs:1067-1069)
-                slot = Ev.root_base ^ L.c;
-                landed = true;
-                if ((r.x & 0xffu) != L.c) {  // no child: stay in ROOT
-                    DACH_STAT(root_stay);
-                    r.x = 0;
-                    r.y = Ev.root_flags;  // efail = ROOT
-                    r.z = 0;
-                    r.w = 0;
-                    slot = D_ROOT;
-                }
-            } else {
-                L.cb = L.nfb;
-                L.pend = L.nf;
-                L.fl = (L.fl & ~F_KNOW) | F_PROBE;  // F_PF2R already describes `pend`
-                L.addr = L.nfb ^ L.c;
-            }
+        // ---- phase 2: failure link ------------------------------------------------------------------
+        if (fl & F_FALL) {
+            const uint32_t f = L.nf >> 8;
+            const bool to_root = f == D_ROOT;
+            if (to_root) DACH_STAT(root_falls);
+            L.addr = (to_root ? Ev.root_base : (L.nfb >> 8)) ^ L.c;
+            fl = (fl & ~(F_FALL | F_OWN | F_ROOTP)) | F_PROBE | (to_root ? F_ROOTP : 0u);
         }
         DACH_SYNCWARP();
         // ---- phase 3: the one record fetch ---------------------------------------------------------
-        if (run && !landed && (L.fl & (F_PROBE | F_LEARN)) != 0) {
+        if (run && (fl & (F_PROBE | F_LEARN)) != 0) {
             const uint32_t a = L.addr;
             uint4 x;
             bool cached = false;
-            if (Ev.hot_mask) {
+            if (HOT) {
                 x = Ev.hot[a & Ev.hot_mask];
                 cached = hot_tag(x) == (a >> Ev.hot_shift);
                 if (cached) DACH_STAT(cache_hits);
             }
             if (!cached) x = ld_u4(Ev.glob + a);
-            if (L.fl & F_PROBE) {
+            if (fl & F_PROBE) {
                 DACH_STAT(probes);
-                if ((x.x & 0xffu) == L.c) {
+                // BASE 0 means "no children" (src/bytewise.rs:1075): a ROOT without children is never entered
+                if ((x.x & 0xffu) == L.c && !((fl & F_ROOTP) && Ev.root_base == 0)) {  // hit: adopt the record
                     DACH_STAT(hits);
-                    landed = true;
-                    r = x;
-                    slot = a;
-                } else if (L.fl & F_KNOW) {
+                    L.cb = x.x >> 8;
+                    L.nf = x.y;
+                    L.nfb = x.z;
+                    L.sig = x.w;
+                    fl = (fl & ~(F_PROBE | F_OWN | F_ROOTP)) | F_LAND;
+                } else if (fl & F_ROOTP) {  // ROOT has no child for this byte: stay in ROOT
+                    DACH_STAT(root_stay);
+                    L.cb = 0;
+                    L.sig = 0;
+                    L.nf = Ev.root_flags;  // efail = ROOT
+                    L.nfb = 0;
+                    L.addr = D_ROOT;
+                    fl = (fl & ~(F_PROBE | F_ROOTP)) | F_LAND;
+                } else if (fl & F_OWN) {  // signature false positive: take the failure link next
                     DACH_STAT(miss_known);
-                    L.fl = (L.fl & ~F_PROBE) | F_FALL;
-                } else if (L.fl & F_PF2R) {
+                    fl = (fl & ~(F_PROBE | F_OWN)) | F_FALL;
+                } else if (L.nf & CF_F2ROOT) {  // the failure state's own failure target is ROOT
                     DACH_STAT(miss_f2root);
-                    L.nf = D_ROOT;
-                    L.fl = (L.fl & ~F_PROBE) | F_KNOW | F_FALL;
-                } else {
-                    L.fl = (L.fl & ~F_PROBE) | F_LEARN;
-                    L.addr = L.pend;
+                    L.nf = 0;  // efail = ROOT
+                    fl = (fl & ~F_PROBE) | F_FALL;
+                } else {  // need the failure state's record to go on
+                    fl = (fl & ~F_PROBE) | F_LEARN;
+                    L.addr = L.nf >> 8;
                 }
-            } else {  // F_LEARN: x is the record of `pend`
+            } else {  // F_LEARN: x is the failure state's record
                 DACH_STAT(learns);
-                L.nf = x.y >> 8;
-                L.nfb = x.z >> 8;
-                L.fl = (L.fl & ~(F_LEARN | F_PF2R)) | F_KNOW | F_FALL | ((x.y & CF_F2ROOT) ? F_PF2R : 0u);
+                L.nf = x.y;
+                L.nfb = x.z;
+                fl = (fl & ~F_LEARN) | F_FALL;
             }
         }
         DACH_SYNCWARP();
-        // ---- phase 4: land (the byte is consumed; the lane sits in the state described by r) ---------
-        if (landed) {
+        // ---- phase 4: land (the byte is consumed; the lane sits in the adopted state) ------------------
+        if (fl & F_LAND) {
+            fl &= ~F_LAND;
             ++L.pos;
             if (PROFILE) {
 #if defined(__CUDA_ARCH__)
-                atomicAdd(Ev.visits + slot, 1u);
+                atomicAdd(Ev.visits + L.addr, 1u);
 #else
-                ++Ev.visits[slot];
+                ++Ev.visits[L.addr];
 #endif
             }
-            uint32_t fl = (L.fl & ~(F_PROBE | F_LEARN | F_FALL | F_PF2R)) | F_KNOW | ((r.y & CF_F2ROOT) ? F_PF2R : 0u);
             if ((((uint32_t)(uintptr_t)L.hay + L.pos) & 15u) == 0) {  // crossed into the next window
                 L.cw = L.nw;
                 fl |= F_NEED_NW;
             }
-            L.cb = r.x >> 8;
-            L.nf = r.y >> 8;
-            L.nfb = r.z >> 8;
-            L.sig = r.w;
-            if ((r.y & CF_OUT) && L.pos > L.from) {
+            if ((L.nf & CF_OUT) && L.pos > L.from) {
                 DACH_STAT(pushes);
                 QEntry e;
                 e.end = L.pos;
-                e.slot = slot;
+                e.slot = L.addr;
                 Ev.q[L.qn * Ev.q_stride] = e;
                 ++L.qn;
                 if (MODE == M_FIND) {  // every next() restarts at ROOT (src/bytewise/iter.rs:87)
                     L.cb = 0;
                     L.sig = 0;
-                    L.nf = D_ROOT;
+                    L.nf = 0;
                     L.nfb = 0;
-                    fl &= ~F_PF2R;
                 }
             }
-            L.fl = fl;
         }
+        L.fl = fl;
         return run;
     }
 
@@ -842,9 +842,9 @@ struct StdMachine {
         // (src/bytewise.rs:303-313; no-suffix variant: src/bytewise/iter.rs:196-216)
         L.cb = 0;
         L.sig = 0;
-        L.nf = D_ROOT;
+        L.nf = 0;  // efail = ROOT
         L.nfb = 0;
-        L.fl = F_ACTIVE | F_KNOW;
+        L.fl = F_ACTIVE;
         if (MODE != M_FIND && (Ev.root_flags & CF_OUT) && beg == 0) {
             QEntry e;
             e.end = 0;

@@ -42,9 +42,9 @@ static void run_items(const ScanParams& P, const RecView& V, const uint8_t* lo, 
 
 // Warp-level driver of the v1 lane machine, mirroring k_scan_std in dev_scan.cu with the warp
 // collectives (ballot / any / shuffle) written out as loops over 32 lane states.
-template <int MODE, bool PROFILE>
+template <int MODE, bool PROFILE, bool HOT>
 static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* lo, int n_warps) {
-    using M = StdMachine<MODE, PROFILE>;
+    using M = StdMachine<MODE, PROFILE, HOT>;
     struct Warp {
         LaneStd L[32];
         Emitter E[32];
@@ -205,9 +205,9 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
             Q.item_hay = nullptr;
             Q.item_beg = nullptr;
             Q.n_items = n < 7 ? n : 7;  // a small sample, like the device pass
-            if (mode == M_FIND) run_items_v1<M_FIND, true>(Q, Ev, lo, n_warps);
-            if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING, true>(Q, Ev, lo, n_warps);
-            if (mode == M_NO_SUFFIX) run_items_v1<M_NO_SUFFIX, true>(Q, Ev, lo, n_warps);
+            if (mode == M_FIND) run_items_v1<M_FIND, true, false>(Q, Ev, lo, n_warps);
+            if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING, true, false>(Q, Ev, lo, n_warps);
+            if (mode == M_NO_SUFFIX) run_items_v1<M_NO_SUFFIX, true, false>(Q, Ev, lo, n_warps);
             ctrl.next_item = 0;
             std::vector<uint64_t> best(entries, 0);
             for (uint32_t sidx = 0; sidx < img.n_slots; ++sidx)
@@ -229,9 +229,15 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
             Ev.hot_mask = entries - 1;
             Ev.hot_shift = shift;
         }
-        if (mode == M_FIND) run_items_v1<M_FIND, false>(P, Ev, lo, n_warps);
-        if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING, false>(P, Ev, lo, n_warps);
-        if (mode == M_NO_SUFFIX) run_items_v1<M_NO_SUFFIX, false>(P, Ev, lo, n_warps);
+        if (entries) {
+            if (mode == M_FIND) run_items_v1<M_FIND, false, true>(P, Ev, lo, n_warps);
+            if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING, false, true>(P, Ev, lo, n_warps);
+            if (mode == M_NO_SUFFIX) run_items_v1<M_NO_SUFFIX, false, true>(P, Ev, lo, n_warps);
+        } else {
+            if (mode == M_FIND) run_items_v1<M_FIND, false, false>(P, Ev, lo, n_warps);
+            if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING, false, false>(P, Ev, lo, n_warps);
+            if (mode == M_NO_SUFFIX) run_items_v1<M_NO_SUFFIX, false, false>(P, Ev, lo, n_warps);
+        }
     } else
     switch ((charwise ? 4 : 0) + mode) {
         case 0: run_items<false, M_FIND>(P, V, lo, hi); break;
