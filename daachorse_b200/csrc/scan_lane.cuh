@@ -686,7 +686,7 @@ struct StdMachine {
                 const uint32_t lo = (o & 8u) ? L.cw.z : L.cw.x;
                 const uint32_t hi = (o & 8u) ? L.cw.w : L.cw.y;
 #if defined(__CUDA_ARCH__)
-                const uint32_t c = __byte_perm(lo, hi, (o & 7u) | 0x4440u);
+                const uint32_t c = __byte_perm(lo, hi, o & 7u) & 0xffu;  // byte (o & 7) of the 8-byte half
 #else
                 const uint32_t c = (((o & 4u) ? hi : lo) >> ((o & 3u) * 8u)) & 0xffu;
 #endif
