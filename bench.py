@@ -198,23 +198,22 @@ def main():
         chunk_matches.append(int(first.matches.shape[0]))
         del first
     total_matches = sum(chunk_matches)
-    for k in range(n_chunks):
-        outs.append(torch.empty((chunk_matches[k] + 1024, 3), dtype=torch.int32, device=dev))
-        out_offs_l.append(torch.empty(bounds[k + 1] - bounds[k] + 1, dtype=torch.int64, device=dev))
-    out_offs = out_offs_l[0]
-
-    pads, gbufs, opads, gobufs = [], [], [], []
+    chunk_cap = list(chunk_matches)
     if world > 1:
         if args.reserve_sms:
             pma.set_option("reserve_sms", args.reserve_sms)
+        # every rank gathers equally sized buffers: the largest chunk count over the ranks
         cm = torch.tensor(chunk_matches, dtype=torch.int64, device=dev)
         dist.all_reduce(cm, op=dist.ReduceOp.MAX)
-        for k in range(n_chunks):
-            mx = int(cm[k].item())
-            pads.append(torch.zeros((mx, 3), dtype=torch.int32, device=dev))
-            opads.append(torch.zeros(bounds[k + 1] - bounds[k] + 1, dtype=torch.int64, device=dev))
-            gbufs.append([torch.empty_like(pads[k]) for _ in range(world)] if rank == 0 else None)
-            gobufs.append([torch.empty_like(opads[k]) for _ in range(world)] if rank == 0 else None)
+        chunk_cap = [int(x) for x in cm.tolist()]
+    gbufs, gobufs = [], []
+    for k in range(n_chunks):
+        outs.append(torch.zeros((chunk_cap[k] + 1024, 3), dtype=torch.int32, device=dev))
+        out_offs_l.append(torch.empty(bounds[k + 1] - bounds[k] + 1, dtype=torch.int64, device=dev))
+        if world > 1:
+            gbufs.append([torch.empty((chunk_cap[k], 3), dtype=torch.int32, device=dev) for _ in range(world)] if rank == 0 else None)
+            gobufs.append([torch.empty_like(out_offs_l[k]) for _ in range(world)] if rank == 0 else None)
+    out_offs = out_offs_l[0]
 
     def step():
         works = []
@@ -223,12 +222,10 @@ def main():
             r = pma.scan_batch_device(D.FIND_OVERLAPPING, text_t, chunk_offs[k], out=outs[k], out_offs=out_offs_l[k])
             if world > 1:
                 # the one exchange step of the path: this chunk's match buffer and offsets go to rank 0
-                # over NVLink (padded gather; counts are known from the sizing pass) while the next
-                # chunk is being scanned
-                pads[k][: chunk_matches[k]].copy_(r.matches)
-                opads[k].copy_(r.offsets)
-                works.append(dist.gather(pads[k], gbufs[k], dst=0, async_op=True))
-                works.append(dist.gather(opads[k], gobufs[k], dst=0, async_op=True))
+                # over NVLink straight from the scan's output buffer (all ranks send chunk_cap[k] rows; the
+                # rows past a rank's own count are ignored through its offsets) while the next chunk is scanned
+                works.append(dist.gather(outs[k][: chunk_cap[k]], gbufs[k], dst=0, async_op=True))
+                works.append(dist.gather(out_offs_l[k], gobufs[k], dst=0, async_op=True))
         for w in works:
             w.wait()
         return r
