@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "libdaachorse_b200.so")
+LIB_PATH = os.environ.get("DACH_LIB") or os.path.join(_DIR, "libdaachorse_b200.so")  # DACH_LIB: experiment builds
 
 (OK, INVALID_ARGUMENT, AUTOMATON_SCALE, INVALID_CONVERSION, INVALID_AUTOMATON, MATCH_KIND_MISMATCH,
  OUTPUT_OVERFLOW, CUDA_ERROR) = range(8)

@@ -550,7 +550,10 @@ DACH_HD void scan_leftmost(const ScanParams& P, const RecView& V, TextWin& T, Em
 // TEXT_TOPUP iterations), early enough because a lane consumes at most one byte per iteration.
 // =============================================================================================
 
-constexpr int LANE_Q = 6;      // queued output events per lane (shared memory)
+#ifndef DACH_LANE_Q
+#define DACH_LANE_Q 10
+#endif
+constexpr int LANE_Q = DACH_LANE_Q;  // queued output events per lane (shared memory)
 constexpr int TEXT_TOPUP = 8;  // iterations between window top-ups (must be < 16)
 constexpr uint32_t CF_OUT = 1u, CF_F2ROOT = 2u;  // flags in record word 1
 constexpr uint32_t COMPACT_MAX_SLOTS = 1u << 24;
@@ -560,7 +563,7 @@ constexpr uint32_t F_ACTIVE = 1u, F_DONE = 2u, F_NEED_NW = 4u, F_OWN = 8u, F_ROO
                    F_FALL = 128u, F_LAND = 256u;
 
 struct QEntry {
-    uint32_t end, slot;
+    uint32_t end, opos;  // opos is filled asynchronously (cp.async from the side table) when the event is queued
 };
 
 // State cache entries are compact records whose spare bits carry a 14-bit tag: bits 2..7 of w1 and
@@ -775,10 +778,17 @@ struct StdMachine {
             }
             if ((L.nf & CF_OUT) && L.pos > L.from) {
                 DACH_STAT(pushes);
-                QEntry e;
-                e.end = L.pos;
-                e.slot = L.addr;
-                Ev.q[L.qn * Ev.q_stride] = e;
+                QEntry* qe = Ev.q + L.qn * Ev.q_stride;
+                qe->end = L.pos;
+                // output_pos of the slot goes from the side table straight into the queue entry, off the
+                // critical path; the service phase waits for these copies before it reads the entries
+#if defined(__CUDA_ARCH__)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(&qe->opos)),
+                             "l"(Ev.opos + L.addr)
+                             : "memory");
+#else
+                qe->opos = Ev.opos[L.addr];
+#endif
                 ++L.qn;
                 if (MODE == M_FIND) {  // every next() restarts at ROOT (src/bytewise/iter.rs:87)
                     L.cb = 0;
@@ -794,6 +804,9 @@ struct StdMachine {
 
     // ---- service pieces ---------------------------------------------------------------------------
     static DACH_HD void drain(LaneStd& L, const StdEnv& Ev, const ScanParams& P, Emitter& E) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
         if (PROFILE) {  // the profiling pass only counts landings
             L.qn = 0;
             return;
@@ -801,11 +814,10 @@ struct StdMachine {
         for (uint32_t j = 0; j < (uint32_t)LANE_Q; ++j) {
             if (j < L.qn) {
                 const QEntry e = Ev.q[j * Ev.q_stride];
-                const uint32_t op = ld_u32(Ev.opos + e.slot);
                 if (MODE == M_OVERLAPPING)
-                    emit_chain(P, E, op, e.end);
+                    emit_chain(P, E, e.opos, e.end);
                 else
-                    emit_head(P, E, op, e.end);
+                    emit_head(P, E, e.opos, e.end);
             }
         }
         L.qn = 0;
@@ -848,7 +860,7 @@ struct StdMachine {
         if (MODE != M_FIND && (Ev.root_flags & CF_OUT) && beg == 0) {
             QEntry e;
             e.end = 0;
-            e.slot = D_ROOT;
+            e.opos = ld_u32(Ev.opos + D_ROOT);
             Ev.q[0] = e;
             L.qn = 1;
         }
