@@ -54,7 +54,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -139,7 +139,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 1 Mi x 4 KiB batch (debug only)")
@@ -256,7 +256,7 @@ def main():
     barrier()
     time.sleep(0.25)  # let nvidia-smi flush its last samples
     clocks = sampler.stop(skip=n_before)
-    clocks["note"] = "nvidia-smi -lms 100 started before the warm-up; the %d samples taken before the timed region are dropped" % n_before
+    clocks["note"] = "nvidia-smi -lms 50 started before the warm-up; the %d samples taken before the timed region are dropped" % n_before
     launches2 = pma.stats()["launches"]
     ms = ev0.elapsed_time(ev1) / args.steps
     if world > 1:
