@@ -80,7 +80,6 @@ int build_image(const dach_pma* p, HostImage* img) {
             }
         }
         // compact image for the lane-machine kernels (Standard automata of at most 2^24 slots)
-        img->root4.assign(1024, 0);
         img->root_base = n ? p->base[kRoot] : 0;
         if (!lm && n <= (size_t(1) << 24) && p->outputs.size() < (size_t(1) << 24)) {
             img->crec.resize(n * 4);
@@ -101,16 +100,6 @@ int build_image(const dach_pma* p, HostImage* img) {
                 r[3] = sig;
                 img->opos_tab[s] = opos;
             }
-            // dense root row: entry c = compact record of ROOT's child for byte c; "no child" is an
-            // entry whose CHECK byte differs from the label
-            for (uint32_t c = 0; c < 256; ++c) {
-                const uint32_t ci = img->root_table[c];
-                if (ci == kRoot) {
-                    img->root4[c * 4 + 0] = (c ^ 1u) & 0xffu;
-                    continue;
-                }
-                for (int k = 0; k < 4; ++k) img->root4[c * 4 + k] = img->crec[size_t(ci) * 4 + k];
-            }
         }
     } else {
         for (size_t s = 0; s < n; ++s) {
@@ -121,7 +110,6 @@ int build_image(const dach_pma* p, HostImage* img) {
             r[3] = p->output_pos[s];
         }
         img->root_table.assign(256, kRoot);  // unused by the charwise kernels
-        img->root4.assign(1024, 0);
         img->mapper = p->mapper_table;
     }
     img->outputs.resize(p->outputs.size() * 4);

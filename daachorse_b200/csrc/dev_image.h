@@ -17,7 +17,6 @@ struct HostImage {
     std::vector<uint32_t> rec;         // 4 words per slot
     std::vector<uint32_t> outputs;     // 4 words per output
     std::vector<uint32_t> root_table;  // 256 words (bytewise)
-    std::vector<uint32_t> root4;       // 256 x compact record of ROOT's child for that byte (bytewise Standard)
     std::vector<uint32_t> crec;        // compact records, 4 words per slot (bytewise Standard, <= 2^24 slots)
     std::vector<uint32_t> opos_tab;    // output_pos per slot (with crec)
     uint32_t root_base = 0;

@@ -65,7 +65,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_scan(ScanParams P) {
 // event queue is full or its haystack is finished, the whole warp runs the service phase: drain
 // all queues (output-list walks, match stores), close finished items, pull new items with one
 // warp-aggregated atomic.
-constexpr uint32_t kRoot4Bytes = 4096;  // 256 x uint4 at the front of dynamic shared memory
 
 // ---- TMA bulk copy global -> shared (cp.async.bulk, completion on an mbarrier) -----------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -119,7 +118,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_std(ScanParams P) {
     using M = StdMachine<MODE, PROFILE, HOT>;
     uint32_t hot_shift = 0;
     while ((1u << hot_shift) < P.hot_entries) ++hot_shift;
-    const StdEnv Ev{P.crec,     s_hot,      HOT ? P.hot_entries - 1u : 0u, hot_shift, P.visits, nullptr, P.opos_tab,
+    const StdEnv Ev{P.crec,     s_hot,      HOT ? P.hot_entries - 1u : 0u, hot_shift, P.visits, P.opos_tab,
                     P.text_end, P.root_base, P.root_opos ? CF_OUT : 0u, s_queue + threadIdx.x, blockDim.x, P.dbg};
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
@@ -438,7 +437,6 @@ struct dach_dev {
     uint4* d_rec = nullptr;
     uint4* d_outputs = nullptr;
     uint32_t* d_root = nullptr;
-    uint4* d_root4 = nullptr;
     uint4* d_crec = nullptr;
     uint32_t* d_opos = nullptr;
     uint32_t root_base = 0;
@@ -662,7 +660,6 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     P.rec = d->d_rec;
     P.outputs = d->d_outputs;
     P.root_table = d->d_root;
-    P.root4 = d->d_root4;
     P.crec = d->d_crec;
     P.opos_tab = d->d_opos;
     P.root_base = d->root_base;
@@ -837,16 +834,16 @@ int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
     d->smem_optin = prop.sharedMemPerBlockOptin;
     // one allocation for the whole image (records | outputs | root rows | mapper), 256-byte aligned
     // parts, so that a single L2 access-policy window can cover it
-    const std::vector<uint32_t>* parts[7] = {&img.rec, &img.outputs, &img.root_table, &img.root4, &img.mapper, &img.crec, &img.opos_tab};
-    size_t part_off[7], total = 0;
-    for (int i = 0; i < 7; ++i) {
+    const std::vector<uint32_t>* parts[6] = {&img.rec, &img.outputs, &img.root_table, &img.mapper, &img.crec, &img.opos_tab};
+    size_t part_off[6], total = 0;
+    for (int i = 0; i < 6; ++i) {
         part_off[i] = total;
         total += (std::max<size_t>(parts[i]->size() * 4, 16) + 255) & ~size_t(255);
         d->image_bytes += parts[i]->size() * 4;
     }
     bool ok = cuda_ok(cudaMalloc(&d->image_base, total), "cudaMalloc image");
     d->image_alloc = total;
-    for (int i = 0; ok && i < 7; ++i)
+    for (int i = 0; ok && i < 6; ++i)
         if (!parts[i]->empty())
             ok = cuda_ok(cudaMemcpy(static_cast<char*>(d->image_base) + part_off[i], parts[i]->data(), parts[i]->size() * 4,
                                     cudaMemcpyHostToDevice),
@@ -856,11 +853,10 @@ int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
         d->d_rec = reinterpret_cast<uint4*>(b + part_off[0]);
         d->d_outputs = reinterpret_cast<uint4*>(b + part_off[1]);
         d->d_root = reinterpret_cast<uint32_t*>(b + part_off[2]);
-        d->d_root4 = reinterpret_cast<uint4*>(b + part_off[3]);
-        d->d_mapper = reinterpret_cast<uint32_t*>(b + part_off[4]);
+        d->d_mapper = reinterpret_cast<uint32_t*>(b + part_off[3]);
         if (!img.crec.empty()) {
-            d->d_crec = reinterpret_cast<uint4*>(b + part_off[5]);
-            d->d_opos = reinterpret_cast<uint32_t*>(b + part_off[6]);
+            d->d_crec = reinterpret_cast<uint4*>(b + part_off[4]);
+            d->d_opos = reinterpret_cast<uint32_t*>(b + part_off[5]);
         }
         d->root_base = img.root_base;
         // let the automaton persist in L2 while text and match streams pass through it

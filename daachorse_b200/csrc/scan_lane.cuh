@@ -79,7 +79,6 @@ struct ScanParams {
     const uint4* rec;
     const uint4* outputs;
     const uint32_t* root_table;  // global copy (kernels stage it in shared memory)
-    const uint4* root4;          // dense root row, compact records (lane-machine kernels)
     const uint4* crec;           // compact records (lane-machine kernels), nullptr if > 2^24 slots
     const uint32_t* opos_tab;    // output_pos per slot (lane-machine kernels)
     uint32_t root_base;          // BASE of ROOT
@@ -528,22 +527,17 @@ DACH_HD void scan_leftmost(const ScanParams& P, const RecView& V, TextWin& T, Em
 //     w2 = fbase << 8                             BASE of efail
 //     w3 = child signature: bit (c & 31) is set iff the state has a child labelled c
 // The signature answers "no child for this byte" without touching the child slot: on the C3
-// workload 0.31 of the 1.28 probes per byte were misses of the state's own children
-// ("Iteration statistics"); with it almost every fetch is a successful probe.
-// output_pos lives in a side table (opos[slot]) that only the drain phase reads.
+// workload 0.31 of the 1.28 probes per byte were misses of the state's own children; with it
+// almost every fetch is a successful probe (1.03 iterations, 0.99 fetches per byte).
+// output_pos lives in a side table (opos[slot]) that is only read when an event is queued.
 //
-//   F_PROBE   fetch rec[addr], addr = BASE ^ c; CHECK decides hit / miss
-//   F_LEARN   fetch rec[pend] to learn (efail, fbase) of a failure state whose probe missed
-//   neither   the lane sits in a state and needs the next byte
-//
-// One iteration = [next byte] | [one fetch] | [fall: failure link / dense root row] | [land],
-// the four phases separated by warp barriers so that each runs once per iteration for all lanes
-// that need it.  ROOT is the record "no children, fail to ROOT", which sends every byte through
-// the dense root row (shared memory; entry c = record of ROOT's child for byte c).
+// ROOT is not special-cased by a dense row: a lane that falls to ROOT probes rec[BASE(ROOT) ^ c]
+// like any other state (those ~40 records live in L1) and a miss there means "stay in ROOT".
 //
 // Matches are not expanded in the loop: a lane that lands on a state with an output list stores
-// (end, slot) in its shared-memory queue.  The warp drains all queues together (service phase),
-// so the output walk -- a divergent pointer chase -- runs with many lanes at once.
+// (end, output_pos) in its shared-memory queue -- output_pos arrives by cp.async.  The warp drains
+// all queues together (service phase), so the output walk -- a divergent pointer chase -- runs
+// with many lanes at once.
 //
 // Text: two 16-byte register windows per lane (current, next).  Crossing into the next window is
 // four predicated moves; the load that re-arms `next` is issued on a warp-uniform schedule (every
@@ -599,7 +593,6 @@ struct StdEnv {
     uint32_t hot_mask;     // entries - 1 (entries is a power of two), 0 = no cache
     uint32_t hot_shift;    // log2(entries)
     uint32_t* visits;      // profiling pass only: landings per slot
-    const uint4* root4;    // dense root row (shared memory)
     const uint32_t* opos;  // output_pos per slot (global)
     const uint8_t* text_end;
     uint32_t root_base;    // BASE of ROOT: the child for byte c sits in slot root_base ^ c

@@ -170,7 +170,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     P.text = text;
     P.text_end = text + (n ? offs[n] : 0);
     P.offs = offs;
-    P.root4 = reinterpret_cast<const uint4*>(img.root4.data());
+
     P.n_items = n_items;
     if (seg) {
         P.item_hay = item_hay.data();
@@ -198,7 +198,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
         std::vector<uint32_t> visits(img.n_slots ? img.n_slots : 1, 0);
         std::vector<uint32_t> tab((size_t)(entries ? entries : 1) * 4, 0);
         StdEnv Ev{reinterpret_cast<const uint4*>(img.crec.data()), reinterpret_cast<const uint4*>(tab.data()), 0u, 0u, visits.data(),
-                  P.root4, img.opos_tab.data(), P.text_end, img.root_base, P.root_opos ? CF_OUT : 0u, nullptr, 0, 0};
+                  img.opos_tab.data(), P.text_end, img.root_base, P.root_opos ? CF_OUT : 0u, nullptr, 0, 0};
         const int n_warps = 3;
         if (entries) {
             ScanParams Q = P;
