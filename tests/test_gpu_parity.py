@@ -335,3 +335,19 @@ def test_segmented_scan_equals_sequential():
             assert r.matches.tobytes() == ref["matches"].tobytes(), (mode, seg)
             assert np.array_equal(np.diff(r.offsets.astype(np.int64)), ref["counts"].astype(np.int64))
     pma.set_option("seg_len", 0)
+
+
+def test_config_c5_shape_long_records_reduced():
+    """BASELINE.json configs[4] shape: a large automaton (here 200k patterns of the C5 generator) over
+    a few long records; the scan cuts them into segments automatically.  Full tuple compare."""
+    cfg = S.config("C5")
+    ps = S.make_patterns(cfg, 200000)
+    pool, b = S.make_pool(cfg, ps, 16 << 20)
+    n, hay_len = 24, 1 << 19
+    starts = S.window_starts(b, len(pool), n, hay_len)
+    text, offs = S.materialise_host(pool, starts, hay_len)
+    pma = D.DoubleArrayAhoCorasick.new(ps.as_list())
+    opma = O.OraclePma.build_packed(ps.blob, ps.offs)
+    assert pma.serialize() == opma.serialize()
+    check_batch(pma, opma, D.FIND_OVERLAPPING, text, offs)
+    check_batch(pma, opma, D.FIND_OVERLAPPING_NO_SUFFIX, text, offs)
