@@ -215,20 +215,32 @@ def main():
             gobufs.append([torch.empty_like(out_offs_l[k]) for _ in range(world)] if rank == 0 else None)
     out_offs = out_offs_l[0]
 
+    pending = [None] * n_chunks
+
     def step():
-        works = []
         r = None
         for k in range(n_chunks):
+            if pending[k] is not None:
+                # the gather of this chunk issued one step ago must be done before its buffer is rewritten
+                for w in pending[k]:
+                    w.wait()
+                pending[k] = None
             r = pma.scan_batch_device(D.FIND_OVERLAPPING, text_t, chunk_offs[k], out=outs[k], out_offs=out_offs_l[k])
             if world > 1:
                 # the one exchange step of the path: this chunk's match buffer and offsets go to rank 0
                 # over NVLink straight from the scan's output buffer (all ranks send chunk_cap[k] rows; the
-                # rows past a rank's own count are ignored through its offsets) while the next chunk is scanned
-                works.append(dist.gather(outs[k][: chunk_cap[k]], gbufs[k], dst=0, async_op=True))
-                works.append(dist.gather(out_offs_l[k], gobufs[k], dst=0, async_op=True))
-        for w in works:
-            w.wait()
+                # rows past a rank's own count are ignored through its offsets).  The gather is asynchronous:
+                # it overlaps the scan of the following chunks, also across the step boundary.
+                pending[k] = [dist.gather(outs[k][: chunk_cap[k]], gbufs[k], dst=0, async_op=True),
+                              dist.gather(out_offs_l[k], gobufs[k], dst=0, async_op=True)]
         return r
+
+    def drain():
+        for k in range(n_chunks):
+            if pending[k] is not None:
+                for w in pending[k]:
+                    w.wait()
+                pending[k] = None
 
     def barrier():
         if world > 1:
@@ -240,6 +252,7 @@ def main():
     sampler.start()
     for _ in range(args.warmup):
         step()
+    drain()
     barrier()
     n_before = len(sampler.rows)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -252,6 +265,7 @@ def main():
         st = pma.stats()
         scan_ms.append(st["scan_kernel_ms"])
         pipe_ms.append(st["total_ms"])
+    drain()  # every gather issued inside the timed region completes inside it
     ev1.record()
     barrier()
     time.sleep(0.25)  # let nvidia-smi flush its last samples
