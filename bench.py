@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--ref-haystacks", type=int, default=262144)
     ap.add_argument("--cpu-haystacks", type=int, default=262144)
     ap.add_argument("--option", action="append", default=[], help="kernel option name=value")
-    ap.add_argument("--chunks", type=int, default=4, help="N > 1: chunks per step (gather of chunk k overlaps scan of k+1)")
+    ap.add_argument("--chunks", type=int, default=2, help="N > 1: chunks per step (gather of chunk k overlaps scan of k+1)")
     ap.add_argument("--reserve-sms", type=int, default=8, help="N > 1: SMs left free for the concurrent NCCL gather")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -81,7 +81,7 @@ int build_image(const dach_pma* p, HostImage* img) {
         }
         // compact image for the lane-machine kernels (Standard automata of at most 2^24 slots)
         img->root_base = n ? p->base[kRoot] : 0;
-        if (!lm && n <= (size_t(1) << 24) && p->outputs.size() < (size_t(1) << 24)) {
+        if (n <= (size_t(1) << 24) && p->outputs.size() < (size_t(1) << 24)) {
             img->crec.resize(n * 4);
             img->opos_tab.resize(n);
             for (size_t s = 0; s < n; ++s) {
@@ -94,8 +94,17 @@ int build_image(const dach_pma* p, HostImage* img) {
                     }
                 uint32_t* r = &img->crec[s * 4];
                 const uint32_t opos = p->opos_ch[s] >> 8;
+                const uint32_t f = w[1];
+                uint32_t flags = opos ? 1u : 0u;
+                if (!lm) {
+                    if (w[2] & 0x80000000u) flags |= 2u;  // CF_F2ROOT
+                } else if (f != kRoot && f != kDead) {
+                    const uint32_t f2 = skip_leaves(p->fail[f]);
+                    if (f2 == kRoot) flags |= 2u;  // CF_F2ROOT
+                    if (f2 == kDead) flags |= 4u;  // CF_F2DEAD
+                }
                 r[0] = (w[0] << 8) | (p->opos_ch[s] & 0xff);
-                r[1] = (w[1] << 8) | (opos ? 1u : 0u) | ((w[2] & 0x80000000u) ? 2u : 0u);
+                r[1] = (f << 8) | flags;
                 r[2] = (w[2] & 0x7fffffffu) << 8;
                 r[3] = sig;
                 img->opos_tab[s] = opos;

@@ -94,8 +94,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-template <int MODE, int MAXT, int MINB, bool PROFILE, bool HOT>
-__global__ void __launch_bounds__(MAXT, MINB) k_scan_std(ScanParams P) {
+// M: the lane machine (StdMachine<...> or LmMachine), LANE: its per-lane state
+template <class M, class LANE, int MAXT, int MINB, bool PROFILE, bool HOT>
+__global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
     // dynamic shared memory: [state cache hot_entries x 16 B (HOT only)][event queues LANE_Q x blockDim x 8 B]
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* s_hot = reinterpret_cast<uint4*>(smem_raw);
@@ -115,14 +116,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_std(ScanParams P) {
         }
     }
 
-    using M = StdMachine<MODE, PROFILE, HOT>;
     uint32_t hot_shift = 0;
     while ((1u << hot_shift) < P.hot_entries) ++hot_shift;
     const StdEnv Ev{P.crec,     s_hot,      HOT ? P.hot_entries - 1u : 0u, hot_shift, P.visits, P.opos_tab,
                     P.text_end, P.root_base, P.root_opos ? CF_OUT : 0u, s_queue + threadIdx.x, blockDim.x, P.dbg};
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
-    LaneStd L;
+    LANE L;
     L.fl = 0;
     L.qn = 0;
     Emitter E;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_std(ScanParams P) {
             M::text_topup(L, Ev, nullptr);
 #pragma unroll 1
             for (int k = 0; k < TEXT_TOPUP; ++k) {
-                const bool ok = M::step(L, Ev);
+                const bool ok = M::step(L, Ev, nullptr);
                 if (__any_sync(FULL, !ok && (L.fl & F_ACTIVE))) {
                     stop = true;
                     break;
@@ -506,11 +506,11 @@ struct L2Window {
     float hit_ratio = 1.0f;
 };
 
-template <int MODE, int MAXT, int MINB, bool PROFILE, bool HOT>
-cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
+template <class M, class LANE, int MAXT, int MINB, bool PROFILE, bool HOT>
+cudaError_t launch_machine_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_scan_std<MODE, MAXT, MINB, PROFILE, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_scan_machine<M, LANE, MAXT, MINB, PROFILE, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -532,7 +532,16 @@ cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem
         cfg.attrs = at;
         cfg.numAttrs = 1;
     }
-    return cudaLaunchKernelEx(&cfg, k_scan_std<MODE, MAXT, MINB, PROFILE, HOT>, P);
+    return cudaLaunchKernelEx(&cfg, k_scan_machine<M, LANE, MAXT, MINB, PROFILE, HOT>, P);
+}
+
+template <int MODE, int MAXT, int MINB, bool PROFILE, bool HOT>
+cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
+    return launch_machine_t<StdMachine<MODE, PROFILE, HOT>, LaneStd, MAXT, MINB, PROFILE, HOT>(P, grid, threads, smem, st, w);
+}
+
+cudaError_t launch_lm(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
+    return launch_machine_t<LmMachine, LaneLm, 1024, 1, false, false>(P, grid, threads, smem, st, w);
 }
 
 cudaError_t launch_std(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w,
@@ -619,7 +628,8 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     const int grid = (d->sm_count - free_sms) * ctas_per_sm;
     // the lane machine serves the bytewise Standard iterators; find_iter with an empty pattern
     // (it only reports zero-length matches, src/bytewise/iter.rs:60-85) keeps the simple kernel
-    const bool v1 = d->opt_kernel >= 1 && d->d_crec && !d->charwise && mode != M_LEFTMOST && !(mode == M_FIND && d->root_opos != 0);
+    const bool v1 = d->opt_kernel >= 1 && d->d_crec && !d->charwise && !(mode == M_FIND && d->root_opos != 0);
+    const bool lm_machine = v1 && mode == M_LEFTMOST;
 
     // Work items.  find_overlapping / no_suffix may cut haystacks into segments (exact with an
     // (L-1)-byte warm-up) so that small batches and long haystacks still
@@ -683,7 +693,7 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     if (v1) {
         const size_t fixed = (size_t)LANE_Q * threads * sizeof(QEntry) + 256;
         // largest power of two that fits next to the root row and the queues
-        uint64_t want = d->opt_hot_entries > 0 ? (uint64_t)d->opt_hot_entries : 0;
+        uint64_t want = (d->opt_hot_entries > 0 && !lm_machine) ? (uint64_t)d->opt_hot_entries : 0;
         while (want && fixed + want * 16 > smem_budget) want >>= 1;
         while (want & (want - 1)) want &= want - 1;
         if (want && (uint64_t)d->n_slots > want * (uint64_t)HOT_TAG_INVALID) want = 0;  // tag would not fit
@@ -762,7 +772,9 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
         win.hit_ratio = (float)std::min(1.0, (double)d->l2_persist / (double)win.bytes);
     }
     cudaEventRecord(W.ev[3], st);
-    if (!cuda_ok(v1 ? launch_std(mode, P, grid, threads, smem, st, win, ctas_per_sm >= 2, false) : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
+    if (!cuda_ok(lm_machine ? launch_lm(P, grid, std::min(threads, 1024), smem, st, win)
+                 : v1       ? launch_std(mode, P, grid, threads, smem, st, win, ctas_per_sm >= 2, false)
+                            : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
                  "k_scan launch"))
         return DACH_CUDA_ERROR;
     cudaEventRecord(W.ev[1], st);

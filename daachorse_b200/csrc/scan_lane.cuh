@@ -669,7 +669,8 @@ struct StdMachine {
     //
     // A lane that misses keeps its byte and retries in the next iteration; lanes never wait for each
     // other except in the service phase.  On the C3 workload: 1.03 iterations and 1.0 fetches per byte.
-    static DACH_HD bool step(LaneStd& L, const StdEnv& Ev) {
+    static DACH_HD bool step(LaneStd& L, const StdEnv& Ev, const uint8_t* emu_lo = nullptr) {
+        (void)emu_lo;
         uint32_t fl = L.fl;
         const bool run = (fl & (F_ACTIVE | F_DONE)) == F_ACTIVE && L.qn != (uint32_t)LANE_Q;
         if (run) DACH_STAT(steps);
@@ -857,6 +858,231 @@ struct StdMachine {
             Ev.q[0] = e;
             L.qn = 1;
         }
+    }
+};
+
+
+// =============================================================================================
+// Lane machine for the bytewise leftmost iterator (LeftmostFindIterator,
+// src/bytewise/iter.rs:272-340, transitions src/bytewise.rs:1094-1128).
+//
+// Same four phases and the same compact records as StdMachine; what differs:
+//   * a failure link to DEAD ends the chase at ROOT without probing ROOT's children
+//     (flags CF_FDEAD-style information travels as efail == DEAD and CF_F2DEAD);
+//   * the landing phase runs the iterator's bookkeeping: remember the last state with an output
+//     (`last`, `self_pos`), and when the automaton falls back to ROOT report that match (its list
+//     head only) and re-scan from the end of the match -- the cursor can move backwards, the text
+//     windows are then simply reloaded (those sectors are still in L1);
+//   * the empty-pattern rules (`init`, `skip_empty`) and the end-of-input rules of the reference,
+//     including the terminating extension documented in DESIGN.md section 1.
+// =============================================================================================
+
+constexpr uint32_t CF_F2DEAD = 4u;  // leftmost records: efail(efail) == DEAD
+// leftmost iterator flags (LaneLm::it)
+constexpr uint32_t IT_INIT = 1u;          // init_output_pos is Some (an empty pattern exists and is still reportable)
+constexpr uint32_t IT_HAVE_LAST = 2u;     // last_output_pos is Some
+constexpr uint32_t IT_LAST_IS_INIT = 4u;  // ... and it is the empty pattern's
+constexpr uint32_t IT_SKIP_EMPTY = 8u;
+
+struct LaneLm : LaneStd {
+    uint32_t self_pos;  // self.pos of the iterator
+    uint32_t last;      // slot of the last state seen with an output (D_ROOT for the empty pattern)
+    uint32_t it;        // IT_* flags
+};
+
+struct LmMachine {
+    using Std = StdMachine<M_LEFTMOST, false, false>;
+
+    static DACH_HD void seek(LaneLm& L, const StdEnv& Ev, uint32_t pos, const uint8_t* emu_lo) {
+        L.pos = pos;
+        const uint8_t* b0 = Std::block_of(L);
+        L.cw = ld_text16(b0, Ev.text_end, emu_lo, Ev.dbg);
+        L.nw = ld_text16(b0 + 16, Ev.text_end, emu_lo, Ev.dbg);
+        L.fl &= ~F_NEED_NW;
+    }
+
+    // start of one next() call: ROOT, last = init, scan from self.pos
+    static DACH_HD void restart(LaneLm& L, const StdEnv& Ev, const uint8_t* emu_lo) {
+        L.cb = 0;
+        L.sig = 0;
+        L.nf = 0;
+        L.nfb = 0;
+        L.last = D_ROOT;
+        L.it = (L.it & (IT_INIT | IT_SKIP_EMPTY)) | ((L.it & IT_INIT) ? (IT_HAVE_LAST | IT_LAST_IS_INIT) : 0u);
+        seek(L, Ev, L.self_pos, emu_lo);
+    }
+
+    static DACH_HD void push(LaneLm& L, const StdEnv& Ev, uint32_t end, uint32_t slot) {
+        QEntry* qe = Ev.q + L.qn * Ev.q_stride;
+        qe->end = end;
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(&qe->opos)), "l"(Ev.opos + slot)
+                     : "memory");
+#else
+        qe->opos = Ev.opos[slot];
+#endif
+        ++L.qn;
+    }
+
+    // The automaton is back in ROOT (or the input ended) with a match pending: the report rules of
+    // iter.rs:283-306.  `unit` = bytes consumed by the unit that led here (1 for bytes).
+    static DACH_HD void report(LaneLm& L, const StdEnv& Ev, const uint8_t* emu_lo) {
+        const uint32_t end = L.self_pos;
+        bool emit = true;
+        if (L.it & IT_LAST_IS_INIT) {
+            L.self_pos += 1;
+            if (L.it & IT_SKIP_EMPTY) {
+                L.it &= ~IT_SKIP_EMPTY;
+                emit = false;  // continue 'a: re-scan from the new self.pos without yielding
+            }
+        } else {
+            L.it |= IT_SKIP_EMPTY;
+        }
+        if (emit) push(L, Ev, end, L.last);
+        restart(L, Ev, emu_lo);
+    }
+
+    static DACH_HD bool step(LaneLm& L, const StdEnv& Ev, const uint8_t* emu_lo) {
+        uint32_t fl = L.fl;
+        const bool run = (fl & (F_ACTIVE | F_DONE)) == F_ACTIVE && L.qn != (uint32_t)LANE_Q;
+        // ---- phase 1: next byte, or the end-of-input rules (iter.rs:320-339) -----------------------
+        if (run && (fl & (F_PROBE | F_LEARN | F_FALL)) == 0) {
+            if (L.pos >= L.len) {
+                if (L.self_pos == L.len) L.it &= ~IT_INIT;
+                if (L.it & IT_HAVE_LAST) {
+                    if (L.self_pos < L.len && (L.it & IT_LAST_IS_INIT)) {
+                        // input ended inside a partial match with only the empty pattern pending: the
+                        // reference never terminates here; treated like the fall-back-to-ROOT branch
+                        L.fl = fl;
+                        report(L, Ev, emu_lo);
+                        fl = L.fl;
+                    } else {
+                        push(L, Ev, L.self_pos, L.last);
+                        L.fl = fl;
+                        restart(L, Ev, emu_lo);
+                        fl = L.fl;
+                    }
+                } else {
+                    fl |= F_DONE;
+                }
+            } else {
+                const uint32_t o = ((uint32_t)(uintptr_t)L.hay + L.pos) & 15u;
+                const uint32_t lo = (o & 8u) ? L.cw.z : L.cw.x;
+                const uint32_t hi = (o & 8u) ? L.cw.w : L.cw.y;
+#if defined(__CUDA_ARCH__)
+                const uint32_t c = __byte_perm(lo, hi, o & 7u) & 0xffu;
+#else
+                const uint32_t c = (((o & 4u) ? hi : lo) >> ((o & 3u) * 8u)) & 0xffu;
+#endif
+                L.c = c;
+                L.addr = L.cb ^ c;
+                fl |= ((L.sig >> (c & 31u)) & 1u) ? (F_PROBE | F_OWN) : F_FALL;
+            }
+        }
+        DACH_SYNCWARP();
+        // ---- phase 2: failure link; DEAD ends at ROOT without a probe (src/bytewise.rs:1120-1123) ----
+        if (fl & F_FALL) {
+            const uint32_t f = L.nf >> 8;
+            if (f == D_DEAD) {
+                L.cb = 0;
+                L.sig = 0;
+                L.nf = 0;
+                L.nfb = 0;
+                L.addr = D_ROOT;
+                fl = (fl & ~(F_FALL | F_OWN | F_ROOTP)) | F_LAND;
+            } else {
+                const bool to_root = f == D_ROOT;
+                L.addr = (to_root ? Ev.root_base : (L.nfb >> 8)) ^ L.c;
+                fl = (fl & ~(F_FALL | F_OWN | F_ROOTP)) | F_PROBE | (to_root ? F_ROOTP : 0u);
+            }
+        }
+        DACH_SYNCWARP();
+        // ---- phase 3: the one record fetch ---------------------------------------------------------
+        if (run && (fl & (F_PROBE | F_LEARN)) != 0) {
+            const uint4 x = ld_u4(Ev.glob + L.addr);
+            if (fl & F_PROBE) {
+                if ((x.x & 0xffu) == L.c && !((fl & F_ROOTP) && Ev.root_base == 0)) {
+                    L.cb = x.x >> 8;
+                    L.nf = x.y;
+                    L.nfb = x.z;
+                    L.sig = x.w;
+                    fl = (fl & ~(F_PROBE | F_OWN | F_ROOTP)) | F_LAND;
+                } else if ((fl & F_ROOTP) || (!(fl & F_OWN) && (L.nf & CF_F2DEAD))) {
+                    // ROOT has no such child, or the failure state's own failure link is DEAD: ROOT
+                    L.cb = 0;
+                    L.sig = 0;
+                    L.nf = 0;
+                    L.nfb = 0;
+                    L.addr = D_ROOT;
+                    fl = (fl & ~(F_PROBE | F_ROOTP)) | F_LAND;
+                } else if (fl & F_OWN) {
+                    fl = (fl & ~(F_PROBE | F_OWN)) | F_FALL;
+                } else if (L.nf & CF_F2ROOT) {
+                    L.nf = 0;
+                    fl = (fl & ~F_PROBE) | F_FALL;
+                } else {
+                    fl = (fl & ~F_PROBE) | F_LEARN;
+                    L.addr = L.nf >> 8;
+                }
+            } else {  // F_LEARN
+                L.nf = x.y;
+                L.nfb = x.z;
+                fl = (fl & ~F_LEARN) | F_FALL;
+            }
+        }
+        DACH_SYNCWARP();
+        // ---- phase 4: land and run the iterator's bookkeeping (iter.rs:282-315) -----------------------
+        if (fl & F_LAND) {
+            fl &= ~F_LAND;
+            ++L.pos;
+            if ((((uint32_t)(uintptr_t)L.hay + L.pos) & 15u) == 0) {
+                L.cw = L.nw;
+                fl |= F_NEED_NW;
+            }
+            if (L.addr == D_ROOT) {
+                if (L.it & IT_HAVE_LAST) {
+                    L.fl = fl;
+                    report(L, Ev, emu_lo);
+                    fl = L.fl;
+                }
+            } else if (L.nf & CF_OUT) {
+                L.last = L.addr;
+                L.it = (L.it | IT_HAVE_LAST) & ~IT_LAST_IS_INIT;
+                L.self_pos = L.pos;
+            }
+        }
+        L.fl = fl;
+        return run;
+    }
+
+    static DACH_HD void drain(LaneLm& L, const StdEnv& Ev, const ScanParams& P, Emitter& E) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+        for (uint32_t j = 0; j < (uint32_t)LANE_Q; ++j) {
+            if (j < L.qn) {
+                const QEntry e = Ev.q[j * Ev.q_stride];
+                emit_head(P, E, e.opos, e.end);
+            }
+        }
+        L.qn = 0;
+    }
+
+    static DACH_HD void text_topup(LaneLm& L, const StdEnv& Ev, const uint8_t* emu_lo) { Std::text_topup(L, Ev, emu_lo); }
+
+    static DACH_HD void begin_item(LaneLm& L, const ScanParams& P, const StdEnv& Ev, Emitter& E, uint64_t item,
+                                   const uint8_t* emu_lo) {
+        const uint64_t o0 = P.offs[item], o1 = P.offs[item + 1];
+        L.hay = P.text + o0;
+        L.len = (uint32_t)(o1 - o0);
+        L.from = 0;
+        L.item = (uint32_t)item;
+        L.qn = 0;
+        L.fl = F_ACTIVE;
+        L.self_pos = 0;
+        L.it = (Ev.root_flags & CF_OUT) ? IT_INIT : 0u;
+        E.begin((uint32_t)item);
+        restart(L, Ev, emu_lo);
     }
 };
 

@@ -5,6 +5,8 @@
 // blocks, exclusive scan of counts, gather), so that lane-logic bugs surface on the CPU box
 // before GPU minutes are spent.  It is never loaded by the product.
 #include <cstdint>
+#include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -42,11 +44,10 @@ static void run_items(const ScanParams& P, const RecView& V, const uint8_t* lo, 
 
 // Warp-level driver of the v1 lane machine, mirroring k_scan_std in dev_scan.cu with the warp
 // collectives (ballot / any / shuffle) written out as loops over 32 lane states.
-template <int MODE, bool PROFILE, bool HOT>
-static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* lo, int n_warps) {
-    using M = StdMachine<MODE, PROFILE, HOT>;
+template <class M, class LANE, bool PROFILE>
+static void run_machine(const ScanParams& P, const StdEnv& Ev0, const uint8_t* lo, int n_warps) {
     struct Warp {
-        LaneStd L[32];
+        LANE L[32];
         Emitter E[32];
         StdEnv Ev[32];
         std::vector<QEntry> queue;
@@ -108,7 +109,7 @@ static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* 
                 for (int k = 0; k < TEXT_TOPUP && !stop; ++k) {
                     bool need_service = false;
                     for (int l = 0; l < 32; ++l) {
-                        const bool ok = M::step(w.L[l], w.Ev[l]);
+                        const bool ok = M::step(w.L[l], w.Ev[l], lo);
                         if (!ok && (w.L[l].fl & F_ACTIVE)) need_service = true;
                     }
                     if (need_service) stop = true;
@@ -116,6 +117,11 @@ static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* 
             }
         }
     }
+}
+
+template <int MODE, bool PROFILE, bool HOT>
+static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* lo, int n_warps) {
+    run_machine<StdMachine<MODE, PROFILE, HOT>, LaneStd, PROFILE>(P, Ev0, lo, n_warps);
 }
 
 extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int charwise, int mode,
@@ -134,7 +140,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     if ((mode == M_LEFTMOST) != lm) return DACH_MATCH_KIND_MISMATCH;
 
     // segment table (mirrors k_seg_count / k_seg_fill in dev_scan.cu)
-    const bool v1 = kernel_version >= 1 && !img.crec.empty() && !charwise && mode != M_LEFTMOST && !(mode == M_FIND && img.root_opos != 0);
+    const bool v1 = kernel_version >= 1 && !img.crec.empty() && !charwise && !(mode == M_FIND && img.root_opos != 0);
     const bool seg = v1 && seg_len > 0 && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX);
     std::vector<uint32_t> item_hay, item_beg;
     std::vector<uint64_t> seg_first(n + 1, 0);
@@ -190,7 +196,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     const uint8_t* hi = text + (n ? offs[n] : 0);
     if (v1) {
         // state cache: profiling pass over the first items, then k_hot_pick / k_hot_fill
-        uint32_t entries = hot_n;
+        uint32_t entries = mode == M_LEFTMOST ? 0 : hot_n;
         while (entries & (entries - 1)) entries &= entries - 1;  // power of two
         if (entries && (uint64_t)img.n_slots > (uint64_t)entries * HOT_TAG_INVALID) entries = 0;
         uint32_t shift = 0;
@@ -229,7 +235,10 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
             Ev.hot_mask = entries - 1;
             Ev.hot_shift = shift;
         }
-        if (entries) {
+        if (mode == M_LEFTMOST) {
+            if (getenv("DACH_EMU_TRACE")) fprintf(stderr, "emu: leftmost lane machine\n");
+            run_machine<LmMachine, LaneLm, false>(P, Ev, lo, n_warps);
+        } else if (entries) {
             if (mode == M_FIND) run_items_v1<M_FIND, false, true>(P, Ev, lo, n_warps);
             if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING, false, true>(P, Ev, lo, n_warps);
             if (mode == M_NO_SUFFIX) run_items_v1<M_NO_SUFFIX, false, true>(P, Ev, lo, n_warps);

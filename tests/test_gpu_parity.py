@@ -241,6 +241,33 @@ def test_config_c4_reduced_charwise_leftmost_longest():
     check_batch(pmb, opmb, D.LEFTMOST_FIND, text, offs)
 
 
+@pytest.mark.parametrize("kind", [1, 2])
+def test_bytewise_leftmost_lane_machine(kind):
+    """The leftmost lane machine (LmMachine) against the oracle and against the lane-per-haystack
+    kernel it replaces, on dictionary-like data with an empty pattern in the set (init / skip_empty
+    rules) and haystacks that end inside partial matches."""
+    cfg = S.config("C3")
+    ps = S.make_patterns(cfg, n=60000)
+    pats = ps.as_list() + ([b""] if kind == 1 else [])
+    pool, b = S.make_pool(cfg, ps, 8 << 20)
+    rng = np.random.default_rng(5 + kind)
+    n = 6000
+    lens = rng.integers(0, 700, size=n)
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    text = np.ascontiguousarray(pool[: int(offs[-1])])
+    pma = D.DoubleArrayAhoCorasickBuilder.new().match_kind(kind).build(pats)
+    opma = O.OraclePma.build(pats, match_kind=kind)
+    r1 = check_batch(pma, opma, D.LEFTMOST_FIND, text, offs)
+    pma.set_option("kernel", 0)
+    r0 = pma.scan_batch_host(D.LEFTMOST_FIND, text, offs)
+    pma.set_option("kernel", 1)
+    pma.set_option("threads", 256)
+    r2 = pma.scan_batch_host(D.LEFTMOST_FIND, text, offs)
+    assert r0.matches.tobytes() == r1.matches.tobytes() == r2.matches.tobytes()
+    assert np.array_equal(r0.offsets, r1.offsets) and np.array_equal(r2.offsets, r1.offsets)
+
+
 def test_full_size_properties_c3():
     """Size-independent properties at a larger batch (1 GiB of the C3 workload, device resident):
     (1) find_iter output == greedy filter of the find_overlapping_iter output (SURVEY C.2);
