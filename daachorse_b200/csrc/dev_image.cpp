@@ -120,6 +120,41 @@ int build_image(const dach_pma* p, HostImage* img) {
         }
         img->root_table.assign(256, kRoot);  // unused by the charwise kernels
         img->mapper = p->mapper_table;
+        // compact image for the charwise lane machine (scan_lane.cuh, CwMachine)
+        img->root_base = n ? p->base[kRoot] : 0;
+        if (n < (size_t(1) << 24) && p->outputs.size() < (size_t(1) << 24)) {
+            auto skip_leaves = [&](uint32_t f) {  // failure target with child-less states skipped
+                while (f != kRoot && f != kDead && p->base[f] == 0) f = p->fail[f];
+                return f;
+            };
+            // child signatures: bit (mapped code & 15) of the parent for every occupied slot
+            std::vector<uint32_t> sig(n, 0);
+            for (size_t s = 0; s < n; ++s) {
+                const uint32_t par = p->check[s];
+                if (par >= n || p->base[par] == 0) continue;
+                const uint32_t code = uint32_t(s) ^ p->base[par];
+                if (code < p->alphabet_size) sig[par] |= 1u << (code & 15);
+            }
+            img->crec.resize(n * 4);
+            img->opos_tab.resize(n);
+            for (size_t s = 0; s < n; ++s) {
+                const uint32_t f = skip_leaves(p->fail[s]);
+                const bool terminal = f == kRoot || f == kDead;
+                uint32_t flags = p->output_pos[s] ? 1u : 0u;
+                if (!terminal) {
+                    const uint32_t f2 = skip_leaves(p->fail[f]);
+                    if (f2 == kRoot) flags |= 2u;  // CF_F2ROOT
+                    if (f2 == kDead) flags |= 4u;  // CF_F2DEAD
+                }
+                const uint32_t chk = p->check[s] < n ? p->check[s] : 0xffffffu;  // vacant: matches no state id
+                uint32_t* r = &img->crec[s * 4];
+                r[0] = (p->base[s] << 8) | (sig[s] & 0xffu);
+                r[1] = (f << 8) | flags;
+                r[2] = ((terminal ? 0u : p->base[f]) << 8) | (sig[s] >> 8);
+                r[3] = chk << 8;
+                img->opos_tab[s] = p->output_pos[s];
+            }
+        }
     }
     img->outputs.resize(p->outputs.size() * 4);
     for (size_t i = 0; i < p->outputs.size(); ++i) {

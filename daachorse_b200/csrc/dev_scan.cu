@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
     uint32_t hot_shift = 0;
     while ((1u << hot_shift) < P.hot_entries) ++hot_shift;
     const StdEnv Ev{P.crec,     s_hot,      HOT ? P.hot_entries - 1u : 0u, hot_shift, P.visits, P.opos_tab,
-                    P.text_end, P.root_base, P.root_opos ? CF_OUT : 0u, s_queue + threadIdx.x, blockDim.x, P.dbg};
+                    P.text_end, P.root_base, P.root_opos ? CF_OUT : 0u, s_queue + threadIdx.x, blockDim.x, P.dbg, P.mapper, P.mapper_len};
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     LANE L;
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
         while (!stop) {
             M::text_topup(L, Ev, nullptr);
 #pragma unroll 1
-            for (int k = 0; k < TEXT_TOPUP; ++k) {
+            for (int k = 0; k < M::TOPUP; ++k) {
                 const bool ok = M::step(L, Ev, nullptr);
                 if (__any_sync(FULL, !ok && (L.fl & F_ACTIVE))) {
                     stop = true;
@@ -540,6 +540,15 @@ cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem
     return launch_machine_t<StdMachine<MODE, PROFILE, HOT>, LaneStd, MAXT, MINB, PROFILE, HOT>(P, grid, threads, smem, st, w);
 }
 
+cudaError_t launch_cw(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
+    switch (mode) {
+        case M_FIND: return launch_machine_t<CwMachine<M_FIND>, LaneCw, 1024, 1, false, false>(P, grid, threads, smem, st, w);
+        case M_OVERLAPPING: return launch_machine_t<CwMachine<M_OVERLAPPING>, LaneCw, 1024, 1, false, false>(P, grid, threads, smem, st, w);
+        case M_NO_SUFFIX: return launch_machine_t<CwMachine<M_NO_SUFFIX>, LaneCw, 1024, 1, false, false>(P, grid, threads, smem, st, w);
+        default: return launch_machine_t<CwMachine<M_LEFTMOST>, LaneCw, 1024, 1, false, false>(P, grid, threads, smem, st, w);
+    }
+}
+
 cudaError_t launch_lm(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
     return launch_machine_t<LmMachine, LaneLm, 1024, 1, false, false>(P, grid, threads, smem, st, w);
 }
@@ -626,15 +635,16 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     int ctas_per_sm = (int)std::min<int64_t>(std::max<int64_t>(d->opt_ctas_per_sm, 1), 2048 / threads);
     const int free_sms = (int)std::min<int64_t>(std::max<int64_t>(d->opt_reserve_sms, 0), d->sm_count - 1);
     const int grid = (d->sm_count - free_sms) * ctas_per_sm;
-    // the lane machine serves the bytewise Standard iterators; find_iter with an empty pattern
-    // (it only reports zero-length matches, src/bytewise/iter.rs:60-85) keeps the simple kernel
-    const bool v1 = d->opt_kernel >= 1 && d->d_crec && !d->charwise && !(mode == M_FIND && d->root_opos != 0);
-    const bool lm_machine = v1 && mode == M_LEFTMOST;
+    // the lane machines serve every iterator of both automata except find_iter with an empty pattern
+    // (it only reports zero-length matches, src/bytewise/iter.rs:60-85), which keeps the simple kernel
+    const bool v1 = d->opt_kernel >= 1 && d->d_crec && !(mode == M_FIND && d->root_opos != 0);
+    const bool cw_machine = v1 && d->charwise;
+    const bool lm_machine = v1 && !d->charwise && mode == M_LEFTMOST;
 
     // Work items.  find_overlapping / no_suffix may cut haystacks into segments (exact with an
     // (L-1)-byte warm-up) so that small batches and long haystacks still
     // fill the machine; everything else works on whole haystacks.
-    bool seg = v1 && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX) && d->opt_seg_len >= 0;
+    bool seg = v1 && !d->charwise && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX) && d->opt_seg_len >= 0;
     uint32_t seg_len = 0;
     uint64_t n_items_max = n;
     if (seg) {
@@ -693,7 +703,7 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     if (v1) {
         const size_t fixed = (size_t)LANE_Q * threads * sizeof(QEntry) + 256;
         // largest power of two that fits next to the root row and the queues
-        uint64_t want = (d->opt_hot_entries > 0 && !lm_machine) ? (uint64_t)d->opt_hot_entries : 0;
+        uint64_t want = (d->opt_hot_entries > 0 && !lm_machine && !cw_machine) ? (uint64_t)d->opt_hot_entries : 0;
         while (want && fixed + want * 16 > smem_budget) want >>= 1;
         while (want & (want - 1)) want &= want - 1;
         if (want && (uint64_t)d->n_slots > want * (uint64_t)HOT_TAG_INVALID) want = 0;  // tag would not fit
@@ -772,7 +782,8 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
         win.hit_ratio = (float)std::min(1.0, (double)d->l2_persist / (double)win.bytes);
     }
     cudaEventRecord(W.ev[3], st);
-    if (!cuda_ok(lm_machine ? launch_lm(P, grid, std::min(threads, 1024), smem, st, win)
+    if (!cuda_ok(cw_machine   ? launch_cw(mode, P, grid, std::min(threads, 1024), smem, st, win)
+                 : lm_machine ? launch_lm(P, grid, std::min(threads, 1024), smem, st, win)
                  : v1       ? launch_std(mode, P, grid, threads, smem, st, win, ctas_per_sm >= 2, false)
                             : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
                  "k_scan launch"))

@@ -458,6 +458,9 @@ DACH_HD void scan_leftmost(const ScanParams& P, const RecView& V, TextWin& T, Em
                     const uint32_t end = self_pos;
                     if (last == init_opos) {
                         self_pos += i - unit_start;  // one byte / one char
+                        if (CHARWISE) {  // never stop inside a char ("Reference divergences")
+                            for (int k = 0; k < 3 && self_pos < len && (T.at(self_pos) & 0xC0u) == 0x80u; ++k) ++self_pos;
+                        }
                         if (skip_empty) {
                             skip_empty = false;
                             i = self_pos;  // continue 'a: rescan from the new self.pos
@@ -479,7 +482,7 @@ DACH_HD void scan_leftmost(const ScanParams& P, const RecView& V, TextWin& T, Em
             }
         }
         if (yielded) continue;
-        if (self_pos == len) init_opos = 0;
+        if (self_pos >= len) init_opos = 0;
         if (last != 0) {
             if (self_pos < len && last == init_opos) {
                 // The input ended inside a partial match with only the empty pattern pending.  The
@@ -600,6 +603,8 @@ struct StdEnv {
     QEntry* q;             // this lane's queue: entry j at q[j * q_stride]
     uint32_t q_stride;
     uint32_t dbg;
+    const uint32_t* mapper;  // charwise: code point -> mapped code (D_INVALID_CODE = unmapped)
+    uint32_t mapper_len;
 };
 
 DACH_HD uint4 ld_text16(const uint8_t* q, const uint8_t* text_end, const uint8_t* emu_lo, uint32_t dbg = 0) {
@@ -645,6 +650,7 @@ extern EmuStats g_emu_stats;
 
 template <int MODE, bool PROFILE = false, bool HOT = false>
 struct StdMachine {
+    static constexpr int TOPUP = TEXT_TOPUP;
     static DACH_HD const uint8_t* block_of(const LaneStd& L) {
         return reinterpret_cast<const uint8_t*>(((uintptr_t)L.hay + L.pos) & ~(uintptr_t)15);
     }
@@ -891,6 +897,7 @@ struct LaneLm : LaneStd {
 };
 
 struct LmMachine {
+    static constexpr int TOPUP = TEXT_TOPUP;
     using Std = StdMachine<M_LEFTMOST, false, false>;
 
     static DACH_HD void seek(LaneLm& L, const StdEnv& Ev, uint32_t pos, const uint8_t* emu_lo) {
@@ -1083,6 +1090,296 @@ struct LmMachine {
         L.it = (Ev.root_flags & CF_OUT) ? IT_INIT : 0u;
         E.begin((uint32_t)item);
         restart(L, Ev, emu_lo);
+    }
+};
+
+// =============================================================================================
+// Lane machine for the charwise automaton, all four iterators (src/charwise/iter.rs:115-399,
+// transitions src/charwise.rs:1022-1092).
+//
+// One iteration consumes one char.  Phase 1 decodes it from the register windows (up to four bytes,
+// src/charwise/iter.rs:71-97) and maps the code point (src/charwise/mapper.rs:36-42; an unmapped
+// char sends the automaton straight to ROOT); phases 2-4 are those of the bytewise machines.
+// CHECK of a charwise state is its parent's id, so a probe hits when the fetched record names the
+// state the probe was made from (the lane's own state, the failure state, or ROOT).
+//
+// Compact record (at most 2^24 - 1 slots), 16 bytes:
+//     w0 = BASE << 8  | signature bits 0..7        src/charwise.rs:1132-1160
+//     w1 = efail << 8 | flags (CF_OUT, CF_F2ROOT, CF_F2DEAD)
+//     w2 = fbase << 8 | signature bits 8..15
+//     w3 = CHECK << 8
+// signature: bit (mapped code & 15) is set iff the state has a child with that code.
+//
+// The windows are re-armed every TOPUP = 4 iterations: a lane consumes at most 16 bytes in between,
+// i.e. crosses at most one 16-byte block, and after the crossing the next three decodes stay inside
+// the block that became current.
+// =============================================================================================
+
+struct LaneCw : LaneLm {
+    uint32_t cur;   // slot of the state the lane sits in
+    uint32_t ulen;  // bytes of the char being matched
+};
+
+template <int MODE>
+struct CwMachine {
+    static constexpr int TOPUP = 4;
+    static constexpr bool LM = MODE == M_LEFTMOST;
+    using Std = StdMachine<M_OVERLAPPING, false, false>;
+
+    // the four bytes at L.pos, little endian (bytes past the windows' 32 are never needed)
+    static DACH_HD uint32_t peek4(const LaneCw& L) {
+        const uint32_t o = ((uint32_t)(uintptr_t)L.hay + L.pos) & 15u;
+        const uint32_t a = (o & 8u) ? L.cw.z : L.cw.x;
+        const uint32_t b = (o & 8u) ? L.cw.w : L.cw.y;
+        const uint32_t d = (o & 8u) ? L.nw.x : L.cw.z;
+        const uint32_t lo = (o & 4u) ? b : a;
+        const uint32_t hi = (o & 4u) ? d : b;
+        const uint32_t sh = (o & 3u) * 8u;
+#if defined(__CUDA_ARCH__)
+        return __funnelshift_r(lo, hi, sh);
+#else
+        return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+    }
+    static DACH_HD uint32_t utf8_len(uint32_t first) { return first < 0x80u ? 1u : first < 0xe0u ? 2u : first < 0xf0u ? 3u : 4u; }
+    static DACH_HD uint32_t utf8_cp(uint32_t u, uint32_t n) {
+        const uint32_t first = u & 0xffu, b1 = (u >> 8) & 0x3fu, b2 = (u >> 16) & 0x3fu, b3 = (u >> 24) & 0x3fu;
+        const uint32_t c2 = ((first & 0x1fu) << 6) | b1;
+        const uint32_t c3 = ((first & 0x0fu) << 12) | (b1 << 6) | b2;
+        const uint32_t c4 = ((first & 0x07u) << 18) | (b1 << 12) | (b2 << 6) | b3;
+        return n == 1u ? first : n == 2u ? c2 : n == 3u ? c3 : c4;
+    }
+
+    static DACH_HD void set_root(LaneCw& L, const StdEnv& Ev) {
+        L.cb = 0;
+        L.sig = 0;
+        L.nf = LM ? 0u : Ev.root_flags;  // efail = ROOT
+        L.nfb = 0;
+        L.addr = D_ROOT;
+    }
+
+    static DACH_HD void seek(LaneCw& L, const StdEnv& Ev, uint32_t pos, const uint8_t* emu_lo) {
+        L.pos = pos;
+        const uint8_t* b0 = Std::block_of(L);
+        L.cw = ld_text16(b0, Ev.text_end, emu_lo, Ev.dbg);
+        L.nw = ld_text16(b0 + 16, Ev.text_end, emu_lo, Ev.dbg);
+        L.fl &= ~F_NEED_NW;
+    }
+
+    static DACH_HD void restart(LaneCw& L, const StdEnv& Ev, const uint8_t* emu_lo) {
+        L.cb = 0;
+        L.sig = 0;
+        L.nf = 0;
+        L.nfb = 0;
+        L.cur = D_ROOT;
+        L.last = D_ROOT;
+        L.it = (L.it & (IT_INIT | IT_SKIP_EMPTY)) | ((L.it & IT_INIT) ? (IT_HAVE_LAST | IT_LAST_IS_INIT) : 0u);
+        seek(L, Ev, L.self_pos, emu_lo);
+    }
+
+    static DACH_HD void push(LaneCw& L, const StdEnv& Ev, uint32_t end, uint32_t slot) {
+        QEntry* qe = Ev.q + L.qn * Ev.q_stride;
+        qe->end = end;
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(&qe->opos)), "l"(Ev.opos + slot)
+                     : "memory");
+#else
+        qe->opos = Ev.opos[slot];
+#endif
+        ++L.qn;
+    }
+
+    // src/charwise/iter.rs:345-366; `adv` = bytes of the char that led back to ROOT
+    static DACH_HD void report(LaneCw& L, const StdEnv& Ev, uint32_t adv, const uint8_t* emu_lo) {
+        const uint32_t end = L.self_pos;
+        bool emit = true;
+        bool snap = false;
+        if (L.it & IT_LAST_IS_INIT) {
+            L.self_pos += adv;
+            snap = true;
+            if (L.it & IT_SKIP_EMPTY) {
+                L.it &= ~IT_SKIP_EMPTY;
+                emit = false;
+            }
+        } else {
+            L.it |= IT_SKIP_EMPTY;
+        }
+        if (emit) push(L, Ev, end, L.last);
+        restart(L, Ev, emu_lo);
+        if (snap && L.self_pos < L.len) {
+            // `adv` belongs to the char that fell back to ROOT, not to the one at self_pos: never stop
+            // inside a char ("Reference divergences") -- skip at most 3 continuation bytes
+            const uint32_t u = peek4(L);
+            uint32_t k = 0;
+            while (k < 3u && L.self_pos + k < L.len && ((u >> (8u * k)) & 0xC0u) == 0x80u) ++k;
+            if (k) {
+                L.self_pos += k;
+                seek(L, Ev, L.self_pos, emu_lo);
+            }
+        }
+    }
+
+    static DACH_HD bool step(LaneCw& L, const StdEnv& Ev, const uint8_t* emu_lo) {
+        (void)emu_lo;
+        uint32_t fl = L.fl;
+        const bool run = (fl & (F_ACTIVE | F_DONE)) == F_ACTIVE && L.qn != (uint32_t)LANE_Q;
+        // ---- phase 1: next char ----------------------------------------------------------------------
+        if (run && (fl & (F_PROBE | F_LEARN | F_FALL)) == 0) {
+            if (L.pos >= L.len) {
+                if (!LM) {
+                    fl |= F_DONE;
+                } else {  // end-of-input rules (src/charwise/iter.rs:381-398), as in LmMachine
+                    if (L.self_pos >= L.len) L.it &= ~IT_INIT;
+                    if (L.it & IT_HAVE_LAST) {
+                        L.fl = fl;
+                        if (L.self_pos < L.len && (L.it & IT_LAST_IS_INIT)) {
+                            seek(L, Ev, L.self_pos, emu_lo);
+                            report(L, Ev, utf8_len(peek4(L) & 0xffu), emu_lo);
+                        } else {
+                            push(L, Ev, L.self_pos, L.last);
+                            restart(L, Ev, emu_lo);
+                        }
+                        fl = L.fl;
+                    } else {
+                        fl |= F_DONE;
+                    }
+                }
+            } else {
+                const uint32_t u = peek4(L);
+                const uint32_t n = utf8_len(u & 0xffu);
+                const uint32_t cp = utf8_cp(u, n);
+                L.ulen = n;
+                const uint32_t mc = cp < Ev.mapper_len ? ld_u32(Ev.mapper + cp) : D_INVALID_CODE;
+                if (mc == D_INVALID_CODE) {  // unmapped char: ROOT (src/charwise.rs:1030-1032)
+                    set_root(L, Ev);
+                    fl |= F_LAND;
+                } else {
+                    L.c = mc;
+                    L.addr = L.cb ^ mc;
+                    fl |= ((L.sig >> (mc & 15u)) & 1u) ? (F_PROBE | F_OWN) : F_FALL;
+                }
+            }
+        }
+        DACH_SYNCWARP();
+        // ---- phase 2: failure link; DEAD ends at ROOT without a probe ------------------------------------
+        if (fl & F_FALL) {
+            const uint32_t f = L.nf >> 8;
+            if (f == D_DEAD) {
+                set_root(L, Ev);
+                fl = (fl & ~(F_FALL | F_OWN | F_ROOTP)) | F_LAND;
+            } else {
+                const bool to_root = f == D_ROOT;
+                L.addr = (to_root ? Ev.root_base : (L.nfb >> 8)) ^ L.c;
+                fl = (fl & ~(F_FALL | F_OWN | F_ROOTP)) | F_PROBE | (to_root ? F_ROOTP : 0u);
+            }
+        }
+        DACH_SYNCWARP();
+        // ---- phase 3: the one record fetch ---------------------------------------------------------
+        if (run && (fl & (F_PROBE | F_LEARN)) != 0) {
+            const uint4 x = ld_u4(Ev.glob + L.addr);
+            if (fl & F_PROBE) {
+                const uint32_t expect = (fl & F_OWN) ? L.cur : (fl & F_ROOTP) ? D_ROOT : (L.nf >> 8);
+                if ((x.w >> 8) == expect && !((fl & F_ROOTP) && Ev.root_base == 0)) {
+                    L.cb = x.x >> 8;
+                    L.sig = (x.x & 0xffu) | ((x.z & 0xffu) << 8);
+                    L.nf = x.y;
+                    L.nfb = x.z;
+                    fl = (fl & ~(F_PROBE | F_OWN | F_ROOTP)) | F_LAND;
+                } else if ((fl & F_ROOTP) || (!(fl & F_OWN) && (L.nf & CF_F2DEAD))) {
+                    set_root(L, Ev);
+                    fl = (fl & ~(F_PROBE | F_ROOTP)) | F_LAND;
+                } else if (fl & F_OWN) {
+                    fl = (fl & ~(F_PROBE | F_OWN)) | F_FALL;
+                } else if (L.nf & CF_F2ROOT) {
+                    L.nf = 0;
+                    fl = (fl & ~F_PROBE) | F_FALL;
+                } else {
+                    fl = (fl & ~F_PROBE) | F_LEARN;
+                    L.addr = L.nf >> 8;
+                }
+            } else {  // F_LEARN
+                L.nf = x.y;
+                L.nfb = x.z;
+                fl = (fl & ~F_LEARN) | F_FALL;
+            }
+        }
+        DACH_SYNCWARP();
+        // ---- phase 4: land ------------------------------------------------------------------------------
+        if (fl & F_LAND) {
+            fl &= ~F_LAND;
+            const uint32_t a0 = (uint32_t)(uintptr_t)L.hay + L.pos;
+            L.pos += L.ulen;
+            if ((a0 ^ (a0 + L.ulen)) & 16u) {  // crossed into the next window
+                L.cw = L.nw;
+                fl |= F_NEED_NW;
+            }
+            L.cur = L.addr;
+            if (LM) {
+                if (L.addr == D_ROOT) {
+                    if (L.it & IT_HAVE_LAST) {
+                        L.fl = fl;
+                        report(L, Ev, L.ulen, emu_lo);
+                        fl = L.fl;
+                    }
+                } else if (L.nf & CF_OUT) {
+                    L.last = L.addr;
+                    L.it = (L.it | IT_HAVE_LAST) & ~IT_LAST_IS_INIT;
+                    L.self_pos = L.pos;
+                }
+            } else if (L.nf & CF_OUT) {
+                push(L, Ev, L.pos, L.addr);
+                if (MODE == M_FIND) {  // every next() restarts at ROOT (src/charwise/iter.rs:150)
+                    L.cb = 0;
+                    L.sig = 0;
+                    L.nf = 0;
+                    L.nfb = 0;
+                    L.cur = D_ROOT;
+                }
+            }
+        }
+        L.fl = fl;
+        return run;
+    }
+
+    static DACH_HD void drain(LaneCw& L, const StdEnv& Ev, const ScanParams& P, Emitter& E) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+        for (uint32_t j = 0; j < (uint32_t)LANE_Q; ++j) {
+            if (j < L.qn) {
+                const QEntry e = Ev.q[j * Ev.q_stride];
+                if (MODE == M_OVERLAPPING)
+                    emit_chain(P, E, e.opos, e.end);
+                else
+                    emit_head(P, E, e.opos, e.end);
+            }
+        }
+        L.qn = 0;
+    }
+
+    static DACH_HD void text_topup(LaneCw& L, const StdEnv& Ev, const uint8_t* emu_lo) { Std::text_topup(L, Ev, emu_lo); }
+
+    static DACH_HD void begin_item(LaneCw& L, const ScanParams& P, const StdEnv& Ev, Emitter& E, uint64_t item,
+                                   const uint8_t* emu_lo) {
+        const uint64_t o0 = P.offs[item], o1 = P.offs[item + 1];
+        L.hay = P.text + o0;
+        L.len = (uint32_t)(o1 - o0);
+        L.from = 0;
+        L.item = (uint32_t)item;
+        L.qn = 0;
+        L.fl = F_ACTIVE;
+        L.ulen = 0;
+        L.self_pos = 0;
+        L.it = (LM && (Ev.root_flags & CF_OUT)) ? IT_INIT : 0u;
+        E.begin((uint32_t)item);
+        restart(L, Ev, emu_lo);
+        if (!LM && MODE != M_FIND && (Ev.root_flags & CF_OUT)) {  // ROOT's output list is pending at position 0
+            QEntry e;
+            e.end = 0;
+            e.opos = ld_u32(Ev.opos + D_ROOT);
+            Ev.q[0] = e;
+            L.qn = 1;
+        }
     }
 };
 

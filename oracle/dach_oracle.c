@@ -1417,6 +1417,15 @@ static void scan_leftmost(const orc_pma *p, const uint8_t *hay, size_t len, sink
                     if (last == init_output_pos) {
                         /* bytewise: self.pos += 1; charwise: self.pos += c.len_utf8() */
                         self_pos += unit_end - unit_start;
+                        /* DOCUMENTED DIVERGENCE (DESIGN.md "Reference divergences"): c is the char that
+                         * fell back to ROOT, not the char at self.pos, so with chars of mixed byte
+                         * lengths self.pos can land inside a char; the reference then slices the &str
+                         * off a char boundary (charwise/iter.rs:334, undefined behaviour).  We move on
+                         * to the next char boundary (at most 3 continuation bytes). */
+                        if (p->charwise) {
+                            int k = 0;
+                            while (k < 3 && self_pos < len && (hay[self_pos] & 0xC0) == 0x80) ++self_pos, ++k;
+                        }
                         if (skip_empty) {
                             skip_empty = 0;
                             goto restart;
@@ -1439,7 +1448,7 @@ static void scan_leftmost(const orc_pma *p, const uint8_t *hay, size_t len, sink
     }
         if (yielded) continue;
         /* after the loop (iter.rs:320-339) */
-        if (self_pos == len) init_output_pos = 0;
+        if (self_pos >= len) init_output_pos = 0; /* > only on invalid UTF-8 (a char cut off by the end) */
         if (last != 0) {
             if (self_pos < len && last == init_output_pos) {
                 /* DOCUMENTED DIVERGENCE (DESIGN.md "Reference divergences"): the input ended inside

@@ -106,7 +106,7 @@ static void run_machine(const ScanParams& P, const StdEnv& Ev0, const uint8_t* l
             bool stop = false;
             while (!stop) {
                 for (int l = 0; l < 32; ++l) M::text_topup(w.L[l], w.Ev[l], lo);
-                for (int k = 0; k < TEXT_TOPUP && !stop; ++k) {
+                for (int k = 0; k < M::TOPUP && !stop; ++k) {
                     bool need_service = false;
                     for (int l = 0; l < 32; ++l) {
                         const bool ok = M::step(w.L[l], w.Ev[l], lo);
@@ -140,8 +140,8 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     if ((mode == M_LEFTMOST) != lm) return DACH_MATCH_KIND_MISMATCH;
 
     // segment table (mirrors k_seg_count / k_seg_fill in dev_scan.cu)
-    const bool v1 = kernel_version >= 1 && !img.crec.empty() && !charwise && !(mode == M_FIND && img.root_opos != 0);
-    const bool seg = v1 && seg_len > 0 && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX);
+    const bool v1 = kernel_version >= 1 && !img.crec.empty() && !(mode == M_FIND && img.root_opos != 0);
+    const bool seg = v1 && !charwise && seg_len > 0 && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX);
     std::vector<uint32_t> item_hay, item_beg;
     std::vector<uint64_t> seg_first(n + 1, 0);
     uint64_t n_items = n;
@@ -196,7 +196,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     const uint8_t* hi = text + (n ? offs[n] : 0);
     if (v1) {
         // state cache: profiling pass over the first items, then k_hot_pick / k_hot_fill
-        uint32_t entries = mode == M_LEFTMOST ? 0 : hot_n;
+        uint32_t entries = (mode == M_LEFTMOST || charwise) ? 0 : hot_n;
         while (entries & (entries - 1)) entries &= entries - 1;  // power of two
         if (entries && (uint64_t)img.n_slots > (uint64_t)entries * HOT_TAG_INVALID) entries = 0;
         uint32_t shift = 0;
@@ -204,7 +204,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
         std::vector<uint32_t> visits(img.n_slots ? img.n_slots : 1, 0);
         std::vector<uint32_t> tab((size_t)(entries ? entries : 1) * 4, 0);
         StdEnv Ev{reinterpret_cast<const uint4*>(img.crec.data()), reinterpret_cast<const uint4*>(tab.data()), 0u, 0u, visits.data(),
-                  img.opos_tab.data(), P.text_end, img.root_base, P.root_opos ? CF_OUT : 0u, nullptr, 0, 0};
+                  img.opos_tab.data(), P.text_end, img.root_base, P.root_opos ? CF_OUT : 0u, nullptr, 0, 0, P.mapper, P.mapper_len};
         const int n_warps = 3;
         if (entries) {
             ScanParams Q = P;
@@ -235,7 +235,13 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
             Ev.hot_mask = entries - 1;
             Ev.hot_shift = shift;
         }
-        if (mode == M_LEFTMOST) {
+        if (charwise) {
+            if (getenv("DACH_EMU_TRACE")) fprintf(stderr, "emu: charwise lane machine\n");
+            if (mode == M_FIND) run_machine<CwMachine<M_FIND>, LaneCw, false>(P, Ev, lo, n_warps);
+            if (mode == M_OVERLAPPING) run_machine<CwMachine<M_OVERLAPPING>, LaneCw, false>(P, Ev, lo, n_warps);
+            if (mode == M_NO_SUFFIX) run_machine<CwMachine<M_NO_SUFFIX>, LaneCw, false>(P, Ev, lo, n_warps);
+            if (mode == M_LEFTMOST) run_machine<CwMachine<M_LEFTMOST>, LaneCw, false>(P, Ev, lo, n_warps);
+        } else if (mode == M_LEFTMOST) {
             if (getenv("DACH_EMU_TRACE")) fprintf(stderr, "emu: leftmost lane machine\n");
             run_machine<LmMachine, LaneLm, false>(P, Ev, lo, n_warps);
         } else if (entries) {

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 import emu_api as E
+from cases import mixed_width_case
 import oracle_api as O
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -139,3 +140,33 @@ def test_segments_reproduce_the_sequential_scan(seed):
             assert rc == 0 and need == ref["total"], (seg_len, mode)
             assert m.tobytes() == ref["matches"].tobytes(), (seg_len, mode)
             assert np.array_equal(np.diff(oo.astype(np.int64)), ref["counts"].astype(np.int64))
+
+
+@pytest.mark.parametrize("seed", range(45))
+def test_charwise_mixed_width_chars(seed):
+    kind, pats, text, offs = mixed_width_case(seed)
+    pma = O.OraclePma.build(pats, charwise=True, match_kind=kind)
+    wire = pma.serialize()
+    for mode in ([3] if kind else [0, 1, 2]):
+        ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
+        for kernel in (1, 0):
+            rc, m, oo, need = E.scan(wire, True, mode, text, offs, kernel=kernel)
+            assert rc == 0 and need == ref["total"]
+            assert m.tobytes() == ref["matches"].tobytes(), (pats, mode, kernel)
+            assert np.array_equal(np.diff(oo.astype(np.int64)), ref["counts"].astype(np.int64))
+
+
+def test_charwise_leftmost_empty_pattern_never_stops_inside_a_char():
+    """The reference advances self.pos by the length of the char that fell back to ROOT
+    (src/charwise/iter.rs:345-346); with an empty pattern and chars of mixed widths that lands inside
+    a char (undefined behaviour in the crate).  Oracle and kernels move on to the next boundary."""
+    pats = ["ca", "", "𝄞𝄞c"]
+    pma = O.OraclePma.build(pats, charwise=True, match_kind=2)
+    hay = "bc𝄞".encode()
+    text = np.frombuffer(hay, dtype=np.uint8)
+    offs = np.array([0, len(hay)], dtype=np.uint64)
+    ref = pma.scan_batch(O.LEFTMOST_FIND, text, offs, want_matches=True)
+    assert triples(ref["matches"]) == [(0, 0, 1), (1, 1, 1), (6, 6, 1)]
+    for kernel in (1, 0):
+        rc, m, oo, need = E.scan(pma.serialize(), True, 3, text, offs, kernel=kernel)
+        assert rc == 0 and triples(m) == triples(ref["matches"])

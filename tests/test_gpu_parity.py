@@ -9,6 +9,7 @@ import pytest
 
 import daachorse_b200 as D
 import oracle_api as O
+from cases import mixed_width_case
 from daachorse_b200 import synth as S
 
 pytestmark = pytest.mark.gpu
@@ -124,6 +125,28 @@ def test_random_batches(seed, cw, kind):
     opma = O.OraclePma.build(pats, charwise=cw, match_kind=kind)
     for mode in ([D.LEFTMOST_FIND] if kind else [D.FIND, D.FIND_OVERLAPPING, D.FIND_OVERLAPPING_NO_SUFFIX]):
         check_batch(pma, opma, mode, text, offs)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_charwise_mixed_width_chars(seed):
+    """Chars of 1-4 bytes, unmapped chars, empty patterns: lane machine and lane-per-haystack kernel."""
+    kind, pats, text, offs = mixed_width_case(seed)
+    pma = D.CharwiseDoubleArrayAhoCorasickBuilder.new().match_kind(kind).build(pats)
+    opma = O.OraclePma.build(pats, charwise=True, match_kind=kind)
+    for mode in ([D.LEFTMOST_FIND] if kind else [D.FIND, D.FIND_OVERLAPPING, D.FIND_OVERLAPPING_NO_SUFFIX]):
+        r1 = check_batch(pma, opma, mode, text, offs)
+        pma.set_option("kernel", 0)
+        r0 = pma.scan_batch_host(mode, text, offs)
+        pma.set_option("kernel", 1)
+        assert r0.matches.tobytes() == r1.matches.tobytes() and np.array_equal(r0.offsets, r1.offsets)
+
+
+def test_charwise_leftmost_empty_pattern_never_stops_inside_a_char():
+    pma = D.CharwiseDoubleArrayAhoCorasickBuilder.new().match_kind(D.MatchKind.LeftmostFirst).build(["ca", "", "𝄞𝄞c"])
+    r = pma.leftmost_find_batch(["bc𝄞", "𝄞", ""])
+    assert r.triples(0) == [(0, 0, 1), (1, 1, 1), (6, 6, 1)]
+    assert r.triples(1) == [(0, 0, 1), (4, 4, 1)]
+    assert r.triples(2) == [(0, 0, 1)]
 
 
 def test_kernel_options_do_not_change_results():
