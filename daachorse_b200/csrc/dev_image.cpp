@@ -96,8 +96,10 @@ int build_image(const dach_pma* p, HostImage* img) {
                 const uint32_t opos = p->opos_ch[s] >> 8;
                 const uint32_t f = w[1];
                 uint32_t flags = opos ? 1u : 0u;
+                uint32_t fbase = w[2] & 0x7fffffffu;
                 if (!lm) {
                     if (w[2] & 0x80000000u) flags |= 2u;  // CF_F2ROOT
+                    if (f == kRoot) flags |= 8u, fbase = img->root_base;  // CF_FROOT: fbase pre-resolved to BASE(ROOT)
                 } else if (f != kRoot && f != kDead) {
                     const uint32_t f2 = skip_leaves(p->fail[f]);
                     if (f2 == kRoot) flags |= 2u;  // CF_F2ROOT
@@ -105,7 +107,7 @@ int build_image(const dach_pma* p, HostImage* img) {
                 }
                 r[0] = (w[0] << 8) | (p->opos_ch[s] & 0xff);
                 r[1] = (f << 8) | flags;
-                r[2] = (w[2] & 0x7fffffffu) << 8;
+                r[2] = fbase << 8;
                 r[3] = sig;
                 img->opos_tab[s] = opos;
             }

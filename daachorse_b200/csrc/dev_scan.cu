@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
     uint32_t hot_shift = 0;
     while ((1u << hot_shift) < P.hot_entries) ++hot_shift;
     const StdEnv Ev{P.crec,     s_hot,      HOT ? P.hot_entries - 1u : 0u, hot_shift, P.visits, P.opos_tab,
-                    P.text_end, P.root_base, P.root_opos ? CF_OUT : 0u, s_queue + threadIdx.x, blockDim.x, P.dbg, P.mapper, P.mapper_len};
+                    P.text_end, P.root_base, P.root_opos ? CF_OUT : 0u, s_queue + threadIdx.x, blockDim.x, P.dbg, P.mapper, P.mapper_len, ld_u4(P.crec + D_ROOT)};
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     LANE L;
@@ -157,12 +157,22 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
         bool stop = false;
         while (!stop) {
             M::text_topup(L, Ev, nullptr);
+            if (M::LAZY) {  // look for lanes that need service once per top-up period, not per iteration
+                bool need_service = false;
 #pragma unroll 1
-            for (int k = 0; k < M::TOPUP; ++k) {
-                const bool ok = M::step(L, Ev, nullptr);
-                if (__any_sync(FULL, !ok && (L.fl & F_ACTIVE))) {
-                    stop = true;
-                    break;
+                for (int k = 0; k < M::TOPUP; ++k) {
+                    const bool ok = M::step(L, Ev, nullptr);
+                    need_service |= !ok;
+                }
+                stop = __any_sync(FULL, need_service && (L.fl & F_ACTIVE));
+            } else {
+#pragma unroll 1
+                for (int k = 0; k < M::TOPUP; ++k) {
+                    const bool ok = M::step(L, Ev, nullptr);
+                    if (__any_sync(FULL, !ok && (L.fl & F_ACTIVE))) {
+                        stop = true;
+                        break;
+                    }
                 }
             }
         }
@@ -540,6 +550,14 @@ cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem
     return launch_machine_t<StdMachine<MODE, PROFILE, HOT>, LaneStd, MAXT, MINB, PROFILE, HOT>(P, grid, threads, smem, st, w);
 }
 
+cudaError_t launch_std2(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
+    switch (mode) {
+        case M_FIND: return launch_machine_t<StdMachine2<M_FIND>, Lane2, 1024, 1, false, false>(P, grid, threads, smem, st, w);
+        case M_NO_SUFFIX: return launch_machine_t<StdMachine2<M_NO_SUFFIX>, Lane2, 1024, 1, false, false>(P, grid, threads, smem, st, w);
+        default: return launch_machine_t<StdMachine2<M_OVERLAPPING>, Lane2, 1024, 1, false, false>(P, grid, threads, smem, st, w);
+    }
+}
+
 cudaError_t launch_cw(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
     switch (mode) {
         case M_FIND: return launch_machine_t<CwMachine<M_FIND>, LaneCw, 1024, 1, false, false>(P, grid, threads, smem, st, w);
@@ -640,6 +658,8 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     const bool v1 = d->opt_kernel >= 1 && d->d_crec && !(mode == M_FIND && d->root_opos != 0);
     const bool cw_machine = v1 && d->charwise;
     const bool lm_machine = v1 && !d->charwise && mode == M_LEFTMOST;
+    // StdMachine2 keeps ROOT's record in registers and probes it like any state: needs BASE(ROOT) != 0
+    const bool std2 = v1 && !d->charwise && mode != M_LEFTMOST && d->opt_kernel >= 2 && d->root_base != 0 && d->opt_hot_entries <= 0;
 
     // Work items.  find_overlapping / no_suffix may cut haystacks into segments (exact with an
     // (L-1)-byte warm-up) so that small batches and long haystacks still
@@ -784,6 +804,7 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     cudaEventRecord(W.ev[3], st);
     if (!cuda_ok(cw_machine   ? launch_cw(mode, P, grid, std::min(threads, 1024), smem, st, win)
                  : lm_machine ? launch_lm(P, grid, std::min(threads, 1024), smem, st, win)
+                 : std2       ? launch_std2(mode, P, grid, std::min(threads, 1024), smem, st, win)
                  : v1       ? launch_std(mode, P, grid, threads, smem, st, win, ctas_per_sm >= 2, false)
                             : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
                  "k_scan launch"))

@@ -31,6 +31,9 @@
 struct uint4 {
     uint32_t x, y, z, w;
 };
+struct uint2 {
+    uint32_t x, y;
+};
 #endif
 #endif
 
@@ -605,6 +608,7 @@ struct StdEnv {
     uint32_t dbg;
     const uint32_t* mapper;  // charwise: code point -> mapped code (D_INVALID_CODE = unmapped)
     uint32_t mapper_len;
+    uint4 root_rec;          // StdMachine2: ROOT's compact record
 };
 
 DACH_HD uint4 ld_text16(const uint8_t* q, const uint8_t* text_end, const uint8_t* emu_lo, uint32_t dbg = 0) {
@@ -651,6 +655,7 @@ extern EmuStats g_emu_stats;
 template <int MODE, bool PROFILE = false, bool HOT = false>
 struct StdMachine {
     static constexpr int TOPUP = TEXT_TOPUP;
+    static constexpr bool LAZY = false;
     static DACH_HD const uint8_t* block_of(const LaneStd& L) {
         return reinterpret_cast<const uint8_t*>(((uintptr_t)L.hay + L.pos) & ~(uintptr_t)15);
     }
@@ -898,6 +903,7 @@ struct LaneLm : LaneStd {
 
 struct LmMachine {
     static constexpr int TOPUP = TEXT_TOPUP;
+    static constexpr bool LAZY = false;
     using Std = StdMachine<M_LEFTMOST, false, false>;
 
     static DACH_HD void seek(LaneLm& L, const StdEnv& Ev, uint32_t pos, const uint8_t* emu_lo) {
@@ -1123,6 +1129,7 @@ struct LaneCw : LaneLm {
 template <int MODE>
 struct CwMachine {
     static constexpr int TOPUP = 4;
+    static constexpr bool LAZY = false;
     static constexpr bool LM = MODE == M_LEFTMOST;
     using Std = StdMachine<M_OVERLAPPING, false, false>;
 
@@ -1374,6 +1381,215 @@ struct CwMachine {
         E.begin((uint32_t)item);
         restart(L, Ev, emu_lo);
         if (!LM && MODE != M_FIND && (Ev.root_flags & CF_OUT)) {  // ROOT's output list is pending at position 0
+            QEntry e;
+            e.end = 0;
+            e.opos = ld_u32(Ev.opos + D_ROOT);
+            Ev.q[0] = e;
+            L.qn = 1;
+        }
+    }
+};
+
+// =============================================================================================
+// StdMachine2: the bytewise Standard machine again, cut for instruction count (the kernel is
+// issue-bound as much as latency-bound: profiles/r1_final_summary.md, 4.9 warp instructions per byte).
+//
+//   * three phases instead of four: a miss computes the address of its next probe on the spot;
+//     fbase of a state whose failure target is ROOT is ROOT's BASE (pre-resolved in the image,
+//     flag CF_FROOT), so "sig says no child" is one select: probe (own ? BASE : fbase) ^ c;
+//   * ROOT is an ordinary state: its compact record is kept in registers and adopted when the
+//     chase ends there (needs BASE(ROOT) != 0; otherwise the launcher keeps StdMachine);
+//   * text: a 64-bit shift register (current 8 bytes, low byte = the byte being matched -- it feeds
+//     the signature shift, the address XOR and the CHECK compare without being extracted) plus the
+//     next 8 bytes, re-armed on the same warp-uniform schedule.
+// =============================================================================================
+
+constexpr uint32_t CF_FROOT = 8u;  // efail == ROOT (Standard records)
+constexpr uint32_t S2_OWN = 0x10u, S2_FAIL = 0x20u, S2_ROOT = 0x40u, S2_LEARN = 0x80u, S2_BUSY = 0xf0u, S2_LAND = 0x100u,
+                   S2_FULL = 0x200u;
+
+struct Lane2 {
+    const uint8_t* hay;
+    uint32_t len, pos, item;
+    uint32_t w0, w1, n0, n1;  // text: current 8 bytes (shifted), next 8 bytes
+    uint32_t r0, nf, r2, sig; // the state the lane sits in: raw words of its compact record
+    uint32_t addr, qn, fl, from;
+};
+
+DACH_HD uint2 ld_text8(const uint8_t* q, const uint8_t* text_end, const uint8_t* emu_lo) {
+    uint2 w;
+    w.x = w.y = 0;
+    (void)emu_lo;
+    if (q >= text_end) return w;
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(q));
+#elif defined(DACH_EMU)
+    uint32_t v[2] = {0, 0};
+    for (int i = 0; i < 8; ++i) {
+        const uint8_t* qi = q + i;
+        uint32_t b = (qi >= emu_lo && qi < text_end) ? *qi : 0;
+        v[i >> 2] |= b << ((i & 3) * 8);
+    }
+    w.x = v[0], w.y = v[1];
+#endif
+    return w;
+}
+
+template <int MODE>
+struct StdMachine2 {
+    static constexpr int TOPUP = 8;
+    static constexpr bool LAZY = true;
+
+    static DACH_HD const uint8_t* block_of(const Lane2& L) {
+        return reinterpret_cast<const uint8_t*>(((uintptr_t)L.hay + L.pos) & ~(uintptr_t)7);
+    }
+    static DACH_HD void text_topup(Lane2& L, const StdEnv& Ev, const uint8_t* emu_lo) {
+        if ((L.fl & (F_ACTIVE | F_NEED_NW)) == (F_ACTIVE | F_NEED_NW)) {
+            const uint2 n = ld_text8(block_of(L) + 8, Ev.text_end, emu_lo);
+            L.n0 = n.x;
+            L.n1 = n.y;
+            L.fl &= ~F_NEED_NW;
+        }
+    }
+    static DACH_HD void to_root(Lane2& L, const StdEnv& Ev) {
+        L.r0 = Ev.root_rec.x;
+        L.nf = Ev.root_rec.y;
+        L.r2 = Ev.root_rec.z;
+        L.sig = Ev.root_rec.w;
+    }
+
+    // the byte is consumed; the lane sits in the state whose record it just adopted
+    static DACH_HD void land(Lane2& L, const StdEnv& Ev, uint32_t& fl) {
+        ++L.pos;
+        L.w0 = (L.w0 >> 8) | (L.w1 << 24);
+        L.w1 >>= 8;
+        if ((((uint32_t)(uintptr_t)L.hay + L.pos) & 7u) == 0) {  // the next 8 bytes become current
+            L.w0 = L.n0;
+            L.w1 = L.n1;
+            fl |= F_NEED_NW;
+        }
+        if ((L.nf & CF_OUT) && L.pos > L.from) {
+            QEntry* qe = Ev.q + L.qn * Ev.q_stride;
+            qe->end = L.pos;
+#if defined(__CUDA_ARCH__)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(&qe->opos)),
+                         "l"(Ev.opos + L.addr)
+                         : "memory");
+#else
+            qe->opos = Ev.opos[L.addr];
+#endif
+            ++L.qn;
+            if (L.qn == (uint32_t)LANE_Q) fl |= S2_FULL;
+            if (MODE == M_FIND) to_root(L, Ev);  // every next() restarts at ROOT (src/bytewise/iter.rs:87)
+        }
+    }
+
+    static DACH_HD bool step(Lane2& L, const StdEnv& Ev, const uint8_t* emu_lo = nullptr) {
+        (void)emu_lo;
+        uint32_t fl = L.fl;
+        const bool run = (fl & (F_ACTIVE | F_DONE | S2_FULL)) == F_ACTIVE;
+        // ---- phase A: next byte, first probe address ---------------------------------------------------
+        if (run && (fl & S2_BUSY) == 0) {
+            if (L.pos >= L.len) {
+                fl |= F_DONE;
+            } else {
+                const uint32_t own = (L.sig >> (L.w0 & 31u)) & 1u;
+                L.addr = ((own ? L.r0 : L.r2) >> 8) ^ (L.w0 & 0xffu);
+                fl |= S2_FAIL >> own;  // S2_OWN == S2_FAIL >> 1
+            }
+        }
+        DACH_SYNCWARP();
+        // ---- phase B: the one record fetch; a hit lands at once ----------------------------------------
+        if (run && (fl & S2_BUSY) != 0) {
+            const uint4 x = ld_u4(Ev.glob + L.addr);
+            if ((((x.x ^ L.w0) & 0xffu) | (fl & S2_LEARN)) == 0) {  // CHECK == c: adopt the record
+                L.r0 = x.x;
+                L.nf = x.y;
+                L.r2 = x.z;
+                L.sig = x.w;
+                fl &= ~S2_BUSY;
+                land(L, Ev, fl);
+            } else {
+                const uint32_t c = L.w0 & 0xffu;
+                if (fl & S2_LEARN) {  // x is the failure state's record
+                    L.nf = x.y;
+                    L.r2 = x.z;
+                    L.addr = (x.z >> 8) ^ c;
+                    fl ^= S2_LEARN | S2_FAIL;
+                } else if (fl & S2_OWN) {  // signature false positive: probe the failure state's children
+                    L.addr = (L.r2 >> 8) ^ c;
+                    fl ^= S2_OWN | S2_FAIL;
+                } else if ((fl & S2_ROOT) || (L.nf & CF_FROOT)) {  // ROOT has no such child: stay in ROOT
+                    to_root(L, Ev);
+                    L.addr = D_ROOT;
+                    fl &= ~S2_BUSY;
+                    land(L, Ev, fl);
+                } else if (L.nf & CF_F2ROOT) {  // the failure state's own failure target is ROOT
+                    L.addr = Ev.root_base ^ c;
+                    fl ^= S2_FAIL | S2_ROOT;
+                } else {  // need the failure state's record to go on
+                    L.addr = L.nf >> 8;
+                    fl ^= S2_FAIL | S2_LEARN;
+                }
+            }
+        }
+        L.fl = fl;
+        return run;
+    }
+
+    static DACH_HD void drain(Lane2& L, const StdEnv& Ev, const ScanParams& P, Emitter& E) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+        for (uint32_t j = 0; j < (uint32_t)LANE_Q; ++j) {
+            if (j < L.qn) {
+                const QEntry e = Ev.q[j * Ev.q_stride];
+                if (MODE == M_OVERLAPPING)
+                    emit_chain(P, E, e.opos, e.end);
+                else
+                    emit_head(P, E, e.opos, e.end);
+            }
+        }
+        L.qn = 0;
+        L.fl &= ~S2_FULL;
+    }
+
+    static DACH_HD void begin_item(Lane2& L, const ScanParams& P, const StdEnv& Ev, Emitter& E, uint64_t item,
+                                   const uint8_t* emu_lo) {
+        uint64_t hay = item;
+        uint32_t beg = 0;
+        if (P.item_hay) {
+            hay = P.item_hay[item];
+            beg = P.item_beg[item];
+        }
+        const uint64_t o0 = P.offs[hay], o1 = P.offs[hay + 1];
+        const uint32_t hay_len = (uint32_t)(o1 - o0);
+        L.hay = P.text + o0;
+        L.len = hay_len;
+        uint32_t start = 0;
+        if (P.item_hay) {
+            const uint32_t end = beg + P.seg_len;
+            L.len = end < hay_len ? end : hay_len;
+            start = beg > P.warm ? beg - P.warm : 0;
+        }
+        L.pos = start;
+        L.from = beg;
+        L.item = (uint32_t)item;
+        L.qn = 0;
+        E.begin((uint32_t)item);
+        const uint8_t* b0 = block_of(L);
+        const uint2 a = ld_text8(b0, Ev.text_end, emu_lo);
+        const uint2 n = ld_text8(b0 + 8, Ev.text_end, emu_lo);
+        const uint32_t sh = (((uint32_t)(uintptr_t)L.hay + L.pos) & 7u) * 8u;  // the byte at pos goes to bit 0
+        const uint64_t cur = (((uint64_t)a.y << 32) | a.x) >> sh;
+        L.w0 = (uint32_t)cur;
+        L.w1 = (uint32_t)(cur >> 32);
+        L.n0 = n.x;
+        L.n1 = n.y;
+        to_root(L, Ev);
+        L.addr = D_ROOT;
+        L.fl = F_ACTIVE;
+        if (MODE != M_FIND && (Ev.root_flags & CF_OUT) && beg == 0) {
             QEntry e;
             e.end = 0;
             e.opos = ld_u32(Ev.opos + D_ROOT);

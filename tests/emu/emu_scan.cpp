@@ -106,14 +106,19 @@ static void run_machine(const ScanParams& P, const StdEnv& Ev0, const uint8_t* l
             bool stop = false;
             while (!stop) {
                 for (int l = 0; l < 32; ++l) M::text_topup(w.L[l], w.Ev[l], lo);
+                bool lazy_need = false;
                 for (int k = 0; k < M::TOPUP && !stop; ++k) {
                     bool need_service = false;
                     for (int l = 0; l < 32; ++l) {
                         const bool ok = M::step(w.L[l], w.Ev[l], lo);
                         if (!ok && (w.L[l].fl & F_ACTIVE)) need_service = true;
                     }
-                    if (need_service) stop = true;
+                    if (M::LAZY)
+                        lazy_need |= need_service;
+                    else if (need_service)
+                        stop = true;
                 }
+                if (M::LAZY && lazy_need) stop = true;
             }
         }
     }
@@ -204,7 +209,8 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
         std::vector<uint32_t> visits(img.n_slots ? img.n_slots : 1, 0);
         std::vector<uint32_t> tab((size_t)(entries ? entries : 1) * 4, 0);
         StdEnv Ev{reinterpret_cast<const uint4*>(img.crec.data()), reinterpret_cast<const uint4*>(tab.data()), 0u, 0u, visits.data(),
-                  img.opos_tab.data(), P.text_end, img.root_base, P.root_opos ? CF_OUT : 0u, nullptr, 0, 0, P.mapper, P.mapper_len};
+                  img.opos_tab.data(), P.text_end, img.root_base, P.root_opos ? CF_OUT : 0u, nullptr, 0, 0, P.mapper, P.mapper_len,
+                  reinterpret_cast<const uint4*>(img.crec.data())[D_ROOT]};
         const int n_warps = 3;
         if (entries) {
             ScanParams Q = P;
@@ -241,6 +247,11 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
             if (mode == M_OVERLAPPING) run_machine<CwMachine<M_OVERLAPPING>, LaneCw, false>(P, Ev, lo, n_warps);
             if (mode == M_NO_SUFFIX) run_machine<CwMachine<M_NO_SUFFIX>, LaneCw, false>(P, Ev, lo, n_warps);
             if (mode == M_LEFTMOST) run_machine<CwMachine<M_LEFTMOST>, LaneCw, false>(P, Ev, lo, n_warps);
+        } else if (mode != M_LEFTMOST && kernel_version >= 2 && img.root_base != 0 && entries == 0) {
+            if (getenv("DACH_EMU_TRACE")) fprintf(stderr, "emu: StdMachine2\n");
+            if (mode == M_FIND) run_machine<StdMachine2<M_FIND>, Lane2, false>(P, Ev, lo, n_warps);
+            if (mode == M_OVERLAPPING) run_machine<StdMachine2<M_OVERLAPPING>, Lane2, false>(P, Ev, lo, n_warps);
+            if (mode == M_NO_SUFFIX) run_machine<StdMachine2<M_NO_SUFFIX>, Lane2, false>(P, Ev, lo, n_warps);
         } else if (mode == M_LEFTMOST) {
             if (getenv("DACH_EMU_TRACE")) fprintf(stderr, "emu: leftmost lane machine\n");
             run_machine<LmMachine, LaneLm, false>(P, Ev, lo, n_warps);

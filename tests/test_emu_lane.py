@@ -36,7 +36,7 @@ def test_golden_vectors(variant, iterator, kind, t):
     wire = O.OraclePma.build(t["patterns"], charwise=cw, match_kind=O.KIND[kind]).serialize()
     hay = t["haystack"].encode()
     text = np.frombuffer(hay, dtype=np.uint8)
-    for hot, kernel in ((0, 1), (64, 1), (3, 0)):
+    for hot, kernel in ((0, 1), (64, 1), (3, 0), (0, 2)):
         rc, m, oo, need = E.scan(wire, cw, MODE[iterator], text, np.array([0, len(hay)], dtype=np.uint64), hot_n=hot,
                                  kernel=kernel)
         assert rc == 0
@@ -75,7 +75,7 @@ def test_random_batches(seed, kind, cw):
     modes = [3] if kind else [0, 1, 2]
     for mode in modes:
         ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
-        for hot, kernel in ((0, 1), (2, 1), (16, 1), (1 << 12, 1), (5, 0)):
+        for hot, kernel in ((0, 1), (2, 1), (16, 1), (1 << 12, 1), (5, 0), (0, 2)):
             rc, m, oo, need = E.scan(wire, cw, mode, text, offs, hot_n=hot, kernel=kernel)
             assert rc == 0
             assert need == ref["total"]
@@ -93,7 +93,7 @@ def test_unaligned_offsets_and_long_chains():
         text = np.frombuffer(b"x" * shift + b"a" * 70 + b"b" + b"a" * 40, dtype=np.uint8)
         offs = np.array([shift, shift + 50, shift + 50, shift + 111], dtype=np.uint64)
         ref = pma.scan_batch(O.FIND_OVERLAPPING, text, offs, want_matches=True)
-        for kernel in (0, 1):
+        for kernel in (0, 1, 2):
             rc, m, oo, need = E.scan(wire, False, 1, text, offs, kernel=kernel)
             assert rc == 0 and m.tobytes() == ref["matches"].tobytes()
             assert list(oo) == [0] + list(np.cumsum(ref["counts"]))
@@ -136,10 +136,11 @@ def test_segments_reproduce_the_sequential_scan(seed):
     for mode in (1, 2):
         ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
         for seg_len in (1, 3, 16, 64, 100, 1000):
-            rc, m, oo, need = E.scan(wire, False, mode, text, offs, seg_len=seg_len)
-            assert rc == 0 and need == ref["total"], (seg_len, mode)
-            assert m.tobytes() == ref["matches"].tobytes(), (seg_len, mode)
-            assert np.array_equal(np.diff(oo.astype(np.int64)), ref["counts"].astype(np.int64))
+            for kernel in (1, 2):
+                rc, m, oo, need = E.scan(wire, False, mode, text, offs, seg_len=seg_len, kernel=kernel)
+                assert rc == 0 and need == ref["total"], (seg_len, mode)
+                assert m.tobytes() == ref["matches"].tobytes(), (seg_len, mode)
+                assert np.array_equal(np.diff(oo.astype(np.int64)), ref["counts"].astype(np.int64))
 
 
 @pytest.mark.parametrize("seed", range(45))
