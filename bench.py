@@ -329,7 +329,7 @@ def main():
     k_ms = float(np.mean(scan_ms))
     achieved = text_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_scan_std<M_OVERLAPPING, 1024, 1> (lane machine)", "kernel_ms": k_ms,
+                "traffic": None, "kernel": "k_scan_machine<StdMachine2<M_OVERLAPPING>, Lane2, 1024, 1> (lane machine)", "kernel_ms": k_ms,
                 "pipeline_ms": float(np.mean(pipe_ms)),
                 "algorithmic_bytes_per_launch": text_bytes, "peak_source": peak_src,
                 "note": "algorithmic bytes = 1 B read per haystack byte x bytes per launch (DESIGN.md); traffic "

@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(kScanThreads) k_offsets_apply(const uint32_t* 
 
 // ---- gather pooled blocks into the final, ordered match array ----------------------------
 // One warp per block.  Skipped entirely when the batch overflowed the pool or out_cap.
+template <int U>
 __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const ScanCtrl* ctrl, uint32_t pool_blocks,
                                                  const uint32_t* counts, const unsigned long long* out_offs,
                                                  uint64_t n_items, unsigned long long out_cap, uint32_t* out_words) {
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const Scan
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    constexpr int U = 4;  // blocks in flight per warp: the header -> (count, offset) -> data chains overlap
+    // U blocks in flight per warp: the header -> (count, offset) -> data chains overlap
     for (uint64_t b0 = warp * U; b0 < used; b0 += n_warps * U) {
         const uint32_t* blk[U];
         uint32_t item[U], seq[U], w0[U], w1[U];
@@ -466,6 +467,7 @@ struct dach_dev {
     // (113 vs 116 GB/s, profiles/r1_cache_experiments.md); kept as an option (power of two).
     int64_t opt_hot_entries = 0;
     int64_t opt_profile_items = 2048;
+    int64_t opt_gather_u = 4;     // pooled blocks in flight per warp of k_gather (2, 4 or 8)
     int64_t opt_reserve_sms = 0;  // SMs left free for concurrent kernels (e.g. the NCCL gather of the previous chunk)
     int64_t opt_dbg = 0;
     int64_t opt_seg_len = 0;  // 0: automatic; > 0: forced segment length; < 0: no segmentation
@@ -477,7 +479,8 @@ struct dach_dev {
     int64_t opt_threads = 1024;
     int64_t opt_ctas_per_sm = 1;
     int64_t opt_l2_persist = 1;  // 1: access-policy window over the image during the scan kernel
-    int64_t opt_kernel = 1;  // 1: warp-synchronous lane machine where it applies; 0: always the v0 kernels
+    int64_t opt_kernel = 2;  // 2: lane machines, StdMachine2 for the bytewise Standard iterators; 1: StdMachine instead;
+                             // 0: always the lane-per-haystack kernels
     // stats
     uint64_t launches = 0;
     double last_scan_ms = 0, last_total_ms = 0;
@@ -814,8 +817,15 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     k_offsets_scan_tiles<<<1, kScanThreads, 0, st>>>(tiles, n_tiles);
     k_offsets_apply<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n_items_max, tiles, item_offs);
     const int gather_grid = d->sm_count * 8;
-    k_gather<<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, item_offs, n_items_max, out_cap,
-                                         reinterpret_cast<uint32_t*>(d_out));
+    if (d->opt_gather_u >= 8)
+        k_gather<8><<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, item_offs, n_items_max, out_cap,
+                                                reinterpret_cast<uint32_t*>(d_out));
+    else if (d->opt_gather_u <= 2)
+        k_gather<2><<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, item_offs, n_items_max, out_cap,
+                                                reinterpret_cast<uint32_t*>(d_out));
+    else
+        k_gather<4><<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, item_offs, n_items_max, out_cap,
+                                                reinterpret_cast<uint32_t*>(d_out));
     d->launches += 5;
     if (seg) {
         k_hay_offsets<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(seg_first, item_offs, n, offs64);
@@ -1091,6 +1101,8 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
         d->opt_seg_len = value;
     else if (k == "dbg")
         d->opt_dbg = value;
+    else if (k == "gather_u")
+        d->opt_gather_u = value;
     else if (k == "reserve_sms")
         d->opt_reserve_sms = value;
     else if (k == "hot_entries") {

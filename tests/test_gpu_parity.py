@@ -13,7 +13,7 @@ from cases import mixed_width_case
 from daachorse_b200 import synth as S
 
 pytestmark = pytest.mark.gpu
-DEFAULT_KERNEL = 1
+DEFAULT_KERNEL = 2
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "search_tests.json"), encoding="utf-8"))
