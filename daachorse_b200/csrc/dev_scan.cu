@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -553,7 +554,15 @@ cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem
     return launch_machine_t<StdMachine<MODE, PROFILE, HOT>, LaneStd, MAXT, MINB, PROFILE, HOT>(P, grid, threads, smem, st, w);
 }
 
-cudaError_t launch_std2(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
+cudaError_t launch_std2(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w,
+                        bool dense) {
+    if (dense) {  // two CTAs of up to 768 threads per SM (40 registers)
+        switch (mode) {
+            case M_FIND: return launch_machine_t<StdMachine2<M_FIND>, Lane2, 768, 2, false, false>(P, grid, threads, smem, st, w);
+            case M_NO_SUFFIX: return launch_machine_t<StdMachine2<M_NO_SUFFIX>, Lane2, 768, 2, false, false>(P, grid, threads, smem, st, w);
+            default: return launch_machine_t<StdMachine2<M_OVERLAPPING>, Lane2, 768, 2, false, false>(P, grid, threads, smem, st, w);
+        }
+    }
     switch (mode) {
         case M_FIND: return launch_machine_t<StdMachine2<M_FIND>, Lane2, 1024, 1, false, false>(P, grid, threads, smem, st, w);
         case M_NO_SUFFIX: return launch_machine_t<StdMachine2<M_NO_SUFFIX>, Lane2, 1024, 1, false, false>(P, grid, threads, smem, st, w);
@@ -807,7 +816,7 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     cudaEventRecord(W.ev[3], st);
     if (!cuda_ok(cw_machine   ? launch_cw(mode, P, grid, std::min(threads, 1024), smem, st, win)
                  : lm_machine ? launch_lm(P, grid, std::min(threads, 1024), smem, st, win)
-                 : std2       ? launch_std2(mode, P, grid, std::min(threads, 1024), smem, st, win)
+                 : std2       ? launch_std2(mode, P, grid, threads, smem, st, win, ctas_per_sm >= 2 && threads <= 768)
                  : v1       ? launch_std(mode, P, grid, threads, smem, st, win, ctas_per_sm >= 2, false)
                             : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
                  "k_scan launch"))
@@ -892,7 +901,7 @@ int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
     size_t part_off[6], total = 0;
     for (int i = 0; i < 6; ++i) {
         part_off[i] = total;
-        total += (std::max<size_t>(parts[i]->size() * 4, 16) + 255) & ~size_t(255);
+        total += (std::max<size_t>(parts[i]->size() * 4, 16) + 511) & ~size_t(511);
         d->image_bytes += parts[i]->size() * 4;
     }
     bool ok = cuda_ok(cudaMalloc(&d->image_base, total), "cudaMalloc image");

@@ -21,7 +21,10 @@ rows = list(csv.reader(io.StringIO(raw)))
 if len(rows) > 2:
     d = dict(zip(rows[0], rows[2]))
     for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_sectors_srcunit_tex_op_read.sum',
-              'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'smsp__inst_executed.sum'):
+              'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'smsp__inst_executed.sum',
+              'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+              'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+              'smsp__issue_active.avg.pct_of_peak_sustained_active'):
         if k in d:
             print("%-55s %s" % (k, d[k]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
