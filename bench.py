@@ -326,12 +326,13 @@ def main():
 
     # ---- roofline of the dominant kernel (k_scan) ---------------------------------------------
     peak, peak_src = measured_peaks()
-    k_ms = float(np.mean(scan_ms))
-    achieved = text_bytes / (k_ms * 1e-3) / 1e9
+    k_ms = float(np.mean(scan_ms))  # the library times its last launch: the last chunk of the step
+    launch_bytes = (bounds[-1] - bounds[-2]) * hay_len
+    achieved = launch_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "k_scan_machine<StdMachine2<M_OVERLAPPING>, Lane2, 1024, 1> (lane machine)", "kernel_ms": k_ms,
                 "pipeline_ms": float(np.mean(pipe_ms)),
-                "algorithmic_bytes_per_launch": text_bytes, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": launch_bytes, "peak_source": peak_src,
                 "note": "algorithmic bytes = 1 B read per haystack byte x bytes per launch (DESIGN.md); traffic "
                         "from profiles/ ncu capture when present"}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -339,7 +340,7 @@ def main():
         try:
             roofline["traffic"] = json.load(open(tpath)).get("dram_bytes_per_byte_scanned")
             if roofline["traffic"] is not None:
-                roofline["traffic"] = roofline["traffic"] * text_bytes
+                roofline["traffic"] = roofline["traffic"] * launch_bytes
         except Exception:
             pass
 

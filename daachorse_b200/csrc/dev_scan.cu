@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kScanThreads) k_offsets_apply(const uint32_t* 
 template <int U>
 __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const ScanCtrl* ctrl, uint32_t pool_blocks,
                                                  const uint32_t* counts, const unsigned long long* out_offs,
-                                                 uint64_t n_items, unsigned long long out_cap, uint32_t* out_words) {
+                                                 uint64_t n_items, unsigned long long out_cap, uint32_t* out_words, uint32_t dbg) {
     if (ctrl->overflow) return;
     if (out_offs[n_items] > out_cap) return;
     const uint32_t used = min(ctrl->blk_cursor, pool_blocks);
@@ -322,6 +322,10 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const Scan
             const uint32_t first = seq[u] * BLK_MATCHES;
             const uint32_t nw = min(BLK_MATCHES, counts[item[u]] - first) * 3;
             uint32_t* dst = out_words + (out_offs[item[u]] + first) * 3ull;
+            if (dbg & 32u) {  // timing experiment: sequential (wrong) placement
+                if ((b0 + u + 1) * (uint64_t)BLK_MATCHES > out_cap) continue;
+                dst = out_words + (b0 + u) * (uint64_t)(BLK_MATCHES * 3);
+            }
             if (lane < nw) dst[lane] = w0[u];
             if (lane + 32 < nw) dst[lane + 32] = w1[u];
         }
@@ -331,11 +335,12 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const Scan
 __global__ void k_zero_offsets(unsigned long long* out_offs) { out_offs[0] = 0; }
 
 // ---- segment table (intra-haystack chunking for find_overlapping / no_suffix) --------------------
-__global__ void __launch_bounds__(256) k_seg_count(const uint64_t* offs, uint64_t n, uint32_t seg_len, uint32_t* nseg) {
+__global__ void __launch_bounds__(256) k_seg_count(const uint64_t* offs, uint64_t n, uint32_t seg_len, uint32_t seg_from,
+                                                    uint32_t* nseg) {
     const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= n) return;
     const uint64_t len = offs[h + 1] - offs[h];
-    const uint64_t k = (len + seg_len - 1) / seg_len;
+    const uint64_t k = h < seg_from ? 1 : (len + seg_len - 1) / seg_len;
     nseg[h] = k ? (uint32_t)k : 1u;  // an empty haystack still is one item (ROOT's outputs at position 0)
 }
 
@@ -395,6 +400,7 @@ bool ensure(DevBuf& b, size_t bytes) {
 struct HostPinned {
     unsigned long long total;
     ScanCtrl ctrl;
+    unsigned long long tail_offs[2];  // offs[seg_from], offs[n]: exact size of the segmented tail
 };
 
 // Everything one in-flight scan needs besides the automaton image.
@@ -677,21 +683,36 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     // (L-1)-byte warm-up) so that small batches and long haystacks still
     // fill the machine; everything else works on whole haystacks.
     bool seg = v1 && !d->charwise && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX) && d->opt_seg_len >= 0;
-    uint32_t seg_len = 0;
+    uint32_t seg_len = 0, seg_from = 0;
     uint64_t n_items_max = n;
     if (seg) {
         const uint64_t lanes = (uint64_t)grid * threads;
         const uint64_t warm = d->max_pattern_len ? d->max_pattern_len - 1 : 0;
-        uint64_t want = text_bytes / (2 * lanes) + 1;            // ~2 items per lane
         const uint64_t floor_len = std::max<uint64_t>(256, 8 * warm);  // warm-up overhead <= 1/8
-        want = std::max(want, floor_len);
+        uint64_t want;
+        uint64_t tail_bytes = text_bytes;
+        if (d->opt_seg_len > 0) {
+            want = (uint64_t)d->opt_seg_len;
+        } else if (n >= 4 * lanes && n < 0xffffffffull) {
+            // plenty of haystacks per lane: only the tail of the batch is cut, so that lanes that finish
+            // early find short items instead of idling through the last wave
+            const uint64_t n_tail = 2 * lanes;
+            seg_from = (uint32_t)(n - n_tail);
+            want = std::max(text_bytes / n / 8 + 1, floor_len);
+            // the item tables are sized from the exact byte count of the tail (two 8-byte reads)
+            cudaMemcpyAsync(&W.pinned->tail_offs[0], d_offs + seg_from, 8, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(&W.pinned->tail_offs[1], d_offs + n, 8, cudaMemcpyDeviceToHost, st);
+            if (!cuda_ok(cudaStreamSynchronize(st), "read tail size")) return DACH_CUDA_ERROR;
+            tail_bytes = W.pinned->tail_offs[1] - W.pinned->tail_offs[0];
+        } else {
+            want = std::max(text_bytes / (2 * lanes) + 1, floor_len);  // ~2 items per lane
+        }
         want = (want + 255) & ~uint64_t(255);
-        if (d->opt_seg_len > 0) want = (uint64_t)d->opt_seg_len;
         if (want >= text_bytes || want >= (1ull << 31)) {
             seg = false;  // every haystack fits one segment
         } else {
             seg_len = (uint32_t)want;
-            n_items_max = n + text_bytes / seg_len + 1;
+            n_items_max = n + tail_bytes / seg_len + 1;
             if (n_items_max > 0xfffffff0ull) seg = false, n_items_max = n;
         }
     }
@@ -762,7 +783,7 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
         const uint64_t nt = (n + kScanTile - 1) / kScanTile;
         uint32_t* nseg = static_cast<uint32_t*>(W.nseg.p);
         cudaMemsetAsync(W.counts.p, 0, n_items_max * 4, st);  // items past the real count stay empty
-        k_seg_count<<<hb, 256, 0, st>>>(d_offs, n, seg_len, nseg);
+        k_seg_count<<<hb, 256, 0, st>>>(d_offs, n, seg_len, seg_from, nseg);
         k_offsets_tile_sums<<<(unsigned)nt, kScanThreads, 0, st>>>(nseg, n, tiles);
         k_offsets_scan_tiles<<<1, kScanThreads, 0, st>>>(tiles, nt);
         k_offsets_apply<<<(unsigned)nt, kScanThreads, 0, st>>>(nseg, n, tiles, seg_first);
@@ -773,6 +794,7 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
         P.item_beg = static_cast<const uint32_t*>(W.item_beg.p);
         P.n_items_dev = static_cast<const unsigned long long*>(W.n_items_dev.p);
         P.seg_len = seg_len;
+        P.seg_from = seg_from;
         P.warm = d->max_pattern_len ? d->max_pattern_len - 1 : 0;
     }
     if (v1 && hot_entries) {
@@ -828,13 +850,13 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     const int gather_grid = d->sm_count * 8;
     if (d->opt_gather_u >= 8)
         k_gather<8><<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, item_offs, n_items_max, out_cap,
-                                                reinterpret_cast<uint32_t*>(d_out));
+                                                reinterpret_cast<uint32_t*>(d_out), P.dbg);
     else if (d->opt_gather_u <= 2)
         k_gather<2><<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, item_offs, n_items_max, out_cap,
-                                                reinterpret_cast<uint32_t*>(d_out));
+                                                reinterpret_cast<uint32_t*>(d_out), P.dbg);
     else
         k_gather<4><<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, item_offs, n_items_max, out_cap,
-                                                reinterpret_cast<uint32_t*>(d_out));
+                                                reinterpret_cast<uint32_t*>(d_out), P.dbg);
     d->launches += 5;
     if (seg) {
         k_hay_offsets<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(seg_first, item_offs, n, offs64);

@@ -106,6 +106,7 @@ struct ScanParams {
     const uint32_t* item_beg;
     const unsigned long long* n_items_dev;
     uint32_t seg_len, warm;
+    uint32_t seg_from;  // haystacks below this index stay whole (one item each): only the tail of a batch is cut
     uint32_t dbg;  // experiment switches (bench --option dbg=): 1 = count matches but do not store them,
                    // 2 = text via ld.global.cs, 4 = text via ld.global.nc.L1::no_allocate
     // results
@@ -841,7 +842,7 @@ struct StdMachine {
         L.hay = P.text + o0;
         L.len = hay_len;
         uint32_t start = 0;
-        if (P.item_hay) {
+        if (P.item_hay && hay >= P.seg_from) {
             const uint32_t end = beg + P.seg_len;
             L.len = end < hay_len ? end : hay_len;
             start = beg > P.warm ? beg - P.warm : 0;  // warm-up: the state at `beg` only depends on these bytes
@@ -1567,7 +1568,7 @@ struct StdMachine2 {
         L.hay = P.text + o0;
         L.len = hay_len;
         uint32_t start = 0;
-        if (P.item_hay) {
+        if (P.item_hay && hay >= P.seg_from) {
             const uint32_t end = beg + P.seg_len;
             L.len = end < hay_len ? end : hay_len;
             start = beg > P.warm ? beg - P.warm : 0;

@@ -131,7 +131,7 @@ static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* 
 
 extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int charwise, int mode,
                                    const uint8_t* text, const uint64_t* offs, uint64_t n, uint32_t hot_n,
-                                   int kernel_version, uint32_t seg_len, uint32_t pool_blocks, dach_match* out, uint64_t out_cap, uint64_t* out_offs,
+                                   int kernel_version, uint32_t seg_len, uint32_t seg_from, uint32_t pool_blocks, dach_match* out, uint64_t out_cap, uint64_t* out_offs,
                                    uint64_t* needed) {
     dach_pma* pma = nullptr;
     size_t used = 0;
@@ -153,7 +153,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     if (seg) {
         for (uint64_t h = 0; h < n; ++h) {
             const uint64_t len = offs[h + 1] - offs[h];
-            uint64_t k = (len + seg_len - 1) / seg_len;
+            uint64_t k = h < seg_from ? 1 : (len + seg_len - 1) / seg_len;
             if (k == 0) k = 1;
             seg_first[h + 1] = seg_first[h] + k;
             for (uint64_t j = 0; j < k; ++j) {
@@ -187,6 +187,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
         P.item_hay = item_hay.data();
         P.item_beg = item_beg.data();
         P.seg_len = seg_len;
+        P.seg_from = seg_from;
         P.warm = img.max_pattern_len ? img.max_pattern_len - 1 : 0;
     }
     P.counts = counts.data();

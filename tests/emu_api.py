@@ -19,13 +19,13 @@ def lib():
         subprocess.check_call(["make", "-C", EMU_DIR, "-s"])
         _lib = C.CDLL(LIB)
         _lib.emu_scan_batch_wire.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                             C.c_uint64, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
+                                             C.c_uint64, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
                                              C.c_void_p, C.POINTER(C.c_uint64)]
         _lib.emu_scan_batch_wire.restype = C.c_int
     return _lib
 
 
-def scan(wire, charwise, mode, text, offs, hot_n=0, pool_blocks=None, out_cap=None, kernel=2, seg_len=0):
+def scan(wire, charwise, mode, text, offs, hot_n=0, pool_blocks=None, out_cap=None, kernel=2, seg_len=0, seg_from=0):
     """Returns (rc, matches, out_offs, needed)."""
     wire_a = np.frombuffer(wire, dtype=np.uint8)
     text = np.ascontiguousarray(text, dtype=np.uint8)
@@ -40,7 +40,7 @@ def scan(wire, charwise, mode, text, offs, hot_n=0, pool_blocks=None, out_cap=No
         need = C.c_uint64()
         pad = text if text.size else np.zeros(16, dtype=np.uint8)
         rc = lib().emu_scan_batch_wire(wire_a.ctypes.data, wire_a.size, int(charwise), mode, pad.ctypes.data,
-                                       offs.ctypes.data, n, hot_n, kernel, seg_len, pb, out.ctypes.data, cap, oo.ctypes.data,
+                                       offs.ctypes.data, n, hot_n, kernel, seg_len, seg_from, pb, out.ctypes.data, cap, oo.ctypes.data,
                                        C.byref(need))
         if rc == 6 and out_cap is None and pool_blocks is None:
             cap = max(cap * 2, int(need.value))

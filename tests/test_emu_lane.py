@@ -137,10 +137,11 @@ def test_segments_reproduce_the_sequential_scan(seed):
         ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
         for seg_len in (1, 3, 16, 64, 100, 1000):
             for kernel in (1, 2):
-                rc, m, oo, need = E.scan(wire, False, mode, text, offs, seg_len=seg_len, kernel=kernel)
-                assert rc == 0 and need == ref["total"], (seg_len, mode)
-                assert m.tobytes() == ref["matches"].tobytes(), (seg_len, mode)
-                assert np.array_equal(np.diff(oo.astype(np.int64)), ref["counts"].astype(np.int64))
+                for seg_from in (0, 11, len(hays) - 3):  # > 0: only the tail of the batch is cut
+                    rc, m, oo, need = E.scan(wire, False, mode, text, offs, seg_len=seg_len, kernel=kernel, seg_from=seg_from)
+                    assert rc == 0 and need == ref["total"], (seg_len, mode)
+                    assert m.tobytes() == ref["matches"].tobytes(), (seg_len, mode)
+                    assert np.array_equal(np.diff(oo.astype(np.int64)), ref["counts"].astype(np.int64))
 
 
 @pytest.mark.parametrize("seed", range(45))

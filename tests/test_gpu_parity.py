@@ -395,6 +395,27 @@ def test_segmented_scan_equals_sequential():
     pma.set_option("seg_len", 0)
 
 
+def test_tail_segmentation_many_small_haystacks():
+    """More than 4 haystacks per lane: only the last 2 x lanes haystacks are cut into segments
+    (dev_scan.cu, scan_locked); ragged lengths, the longest haystacks sit in the tail."""
+    cfg = S.config("C2")
+    ps = S.make_patterns(cfg, n=3000)
+    pool, b = S.make_pool(cfg, ps, 8 << 20)
+    rng = np.random.default_rng(11)
+    n = 4 * 148 * 1024 + 5000
+    lens = rng.integers(0, 96, size=n)
+    lens[-3000:] = rng.integers(2000, 9000, size=3000)
+    lens[-1] = 0
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    reps = int(offs[-1]) // len(pool) + 1
+    text = np.ascontiguousarray(np.tile(pool, reps)[: int(offs[-1])])
+    pma = D.DoubleArrayAhoCorasick.new(ps.as_list())
+    opma = O.OraclePma.build_packed(ps.blob, ps.offs)
+    for mode in (D.FIND_OVERLAPPING, D.FIND_OVERLAPPING_NO_SUFFIX):
+        check_batch(pma, opma, mode, text, offs, nthreads=32)  # 46 MB: one host slice, i.e. one launch over all haystacks
+
+
 def test_config_c5_shape_long_records_reduced():
     """BASELINE.json configs[4] shape: a large automaton (here 200k patterns of the C5 generator) over
     a few long records; the scan cuts them into segments automatically.  Full tuple compare."""
