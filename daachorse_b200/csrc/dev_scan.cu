@@ -237,13 +237,20 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
     return before + inc - v;
 }
 
+// BLOCKS: scan ceil(count / BLK_MATCHES) (pool blocks per item) instead of the counts themselves
+template <bool BLOCKS>
+__device__ __forceinline__ uint32_t scan_term(uint32_t count) {
+    return BLOCKS ? (count + BLK_MATCHES - 1) / BLK_MATCHES : count;
+}
+
+template <bool BLOCKS>
 __global__ void __launch_bounds__(kScanThreads) k_offsets_tile_sums(const uint32_t* counts, uint64_t n,
                                                                       unsigned long long* tile_sums) {
     const uint64_t base = (uint64_t)blockIdx.x * kScanTile;
     unsigned long long s = 0;
     for (int k = 0; k < kScanPerThread; ++k) {
         const uint64_t i = base + (uint64_t)k * kScanThreads + threadIdx.x;
-        if (i < n) s += counts[i];
+        if (i < n) s += scan_term<BLOCKS>(counts[i]);
     }
     unsigned long long total;
     (void)block_exclusive_scan(s, &total);
@@ -267,6 +274,7 @@ __global__ void __launch_bounds__(kScanThreads) k_offsets_scan_tiles(unsigned lo
     }
 }
 
+template <bool BLOCKS>
 __global__ void __launch_bounds__(kScanThreads) k_offsets_apply(const uint32_t* counts, uint64_t n,
                                                                   const unsigned long long* tile_offs,
                                                                   unsigned long long* out_offs) {
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(kScanThreads) k_offsets_apply(const uint32_t* 
 #pragma unroll
     for (int k = 0; k < kScanPerThread; ++k) {
         const uint64_t i = first + k;
-        c[k] = i < n ? counts[i] : 0;
+        c[k] = i < n ? scan_term<BLOCKS>(counts[i]) : 0;
         s += c[k];
     }
     unsigned long long total;
@@ -292,11 +300,28 @@ __global__ void __launch_bounds__(kScanThreads) k_offsets_apply(const uint32_t* 
 }
 
 // ---- gather pooled blocks into the final, ordered match array ----------------------------
+// Pool blocks are handed out in the order lanes ask for them, i.e. scattered over the items in flight;
+// copying them in pool order makes every 240-byte write land somewhere else in the output (partial
+// sectors, no DRAM locality: 0.93 ms per GiB scanned).  k_blk_index lists the blocks in output order
+// (blkmap[first block of the item + seq] = pool block) and k_gather walks that list: scattered reads
+// of whole aligned 256-byte blocks, sequential writes.
+__global__ void __launch_bounds__(256) k_blk_index(const uint32_t* pool, const ScanCtrl* ctrl, uint32_t pool_blocks,
+                                                    const unsigned long long* blk_first, uint32_t* blkmap) {
+    if (ctrl->overflow) return;
+    const uint32_t used = min(ctrl->blk_cursor, pool_blocks);
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < used; b += (uint64_t)gridDim.x * blockDim.x) {
+        const uint2 h = *reinterpret_cast<const uint2*>(pool + b * BLK_WORDS);  // {item, seq}
+        const unsigned long long j = blk_first[h.x] + h.y;
+        if (j < used) blkmap[j] = (uint32_t)b;
+    }
+}
+
 // One warp per block.  Skipped entirely when the batch overflowed the pool or out_cap.
 template <int U>
 __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const ScanCtrl* ctrl, uint32_t pool_blocks,
                                                  const uint32_t* counts, const unsigned long long* out_offs,
-                                                 uint64_t n_items, unsigned long long out_cap, uint32_t* out_words, uint32_t dbg) {
+                                                 uint64_t n_items, unsigned long long out_cap, uint32_t* out_words, uint32_t dbg,
+                                                 const uint32_t* blkmap) {
     if (ctrl->overflow) return;
     if (out_offs[n_items] > out_cap) return;
     const uint32_t used = min(ctrl->blk_cursor, pool_blocks);
@@ -310,7 +335,8 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const Scan
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint64_t b = b0 + u;
-            blk[u] = pool + (b < used ? b : b0) * BLK_WORDS;
+            const uint64_t bb = b < used ? b : b0;
+            blk[u] = pool + (blkmap ? (uint64_t)blkmap[bb] : bb) * BLK_WORDS;
             item[u] = blk[u][0];
             seq[u] = blk[u][1];
             w0[u] = blk[u][2 + lane];
@@ -407,6 +433,7 @@ struct HostPinned {
 struct Workspace {
     DevBuf counts, tiles, ctrl, pool;
     DevBuf nseg, seg_first, item_hay, item_beg, item_offs, n_items_dev;  // segment table
+    DevBuf blk_first, blkmap, tiles2;  // pool blocks in output order (k_blk_index)
     HostPinned* pinned = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // host-batch slices only: device staging and the slice's stream
@@ -423,7 +450,7 @@ struct Workspace {
     }
     void release() {
         for (DevBuf* b : {&counts, &tiles, &ctrl, &pool, &text, &offs, &out, &out_offs, &nseg, &seg_first, &item_hay, &item_beg,
-                          &item_offs, &n_items_dev})
+                          &item_offs, &n_items_dev, &blk_first, &blkmap, &tiles2})
             if (b->p) {
                 cudaFree(b->p);
                 b->p = nullptr;
@@ -474,6 +501,8 @@ struct dach_dev {
     // (113 vs 116 GB/s, profiles/r1_cache_experiments.md); kept as an option (power of two).
     int64_t opt_hot_entries = 0;
     int64_t opt_profile_items = 2048;
+    int64_t opt_tail_seg = 0;        // cut only the last 2 x lanes haystacks of a large batch (measured: -2 %, off)
+    int64_t opt_gather_ordered = 1;  // copy pool blocks in output order (sequential writes)
     int64_t opt_gather_u = 4;     // pooled blocks in flight per warp of k_gather (2, 4 or 8)
     int64_t opt_reserve_sms = 0;  // SMs left free for concurrent kernels (e.g. the NCCL gather of the previous chunk)
     int64_t opt_dbg = 0;
@@ -693,7 +722,7 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
         uint64_t tail_bytes = text_bytes;
         if (d->opt_seg_len > 0) {
             want = (uint64_t)d->opt_seg_len;
-        } else if (n >= 4 * lanes && n < 0xffffffffull) {
+        } else if (d->opt_tail_seg && n >= 4 * lanes && n < 0xffffffffull) {
             // plenty of haystacks per lane: only the tail of the batch is cut, so that lanes that finish
             // early find short items instead of idling through the last wave
             const uint64_t n_tail = 2 * lanes;
@@ -784,9 +813,9 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
         uint32_t* nseg = static_cast<uint32_t*>(W.nseg.p);
         cudaMemsetAsync(W.counts.p, 0, n_items_max * 4, st);  // items past the real count stay empty
         k_seg_count<<<hb, 256, 0, st>>>(d_offs, n, seg_len, seg_from, nseg);
-        k_offsets_tile_sums<<<(unsigned)nt, kScanThreads, 0, st>>>(nseg, n, tiles);
+        k_offsets_tile_sums<false><<<(unsigned)nt, kScanThreads, 0, st>>>(nseg, n, tiles);
         k_offsets_scan_tiles<<<1, kScanThreads, 0, st>>>(tiles, nt);
-        k_offsets_apply<<<(unsigned)nt, kScanThreads, 0, st>>>(nseg, n, tiles, seg_first);
+        k_offsets_apply<false><<<(unsigned)nt, kScanThreads, 0, st>>>(nseg, n, tiles, seg_first);
         k_seg_fill<<<hb1, 256, 0, st>>>(seg_first, nseg, n, seg_len, static_cast<uint32_t*>(W.item_hay.p),
                                         static_cast<uint32_t*>(W.item_beg.p), static_cast<unsigned long long*>(W.n_items_dev.p));
         d->launches += 5;
@@ -844,19 +873,32 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
                  "k_scan launch"))
         return DACH_CUDA_ERROR;
     cudaEventRecord(W.ev[1], st);
-    k_offsets_tile_sums<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n_items_max, tiles);
+    k_offsets_tile_sums<false><<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n_items_max, tiles);
     k_offsets_scan_tiles<<<1, kScanThreads, 0, st>>>(tiles, n_tiles);
-    k_offsets_apply<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n_items_max, tiles, item_offs);
+    k_offsets_apply<false><<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n_items_max, tiles, item_offs);
     const int gather_grid = d->sm_count * 8;
+    const uint32_t* blkmap = nullptr;
+    if (d->opt_gather_ordered >= 2 || (d->opt_gather_ordered == 1 && pool_blocks >= 4096)) {  // tiny batches: not worth three more launches
+        if (!ensure(W.blk_first, (n_items_max + 1) * 8) || !ensure(W.blkmap, (size_t)pool_blocks * 4) || !ensure(W.tiles2, n_tiles * 8))
+            return DACH_CUDA_ERROR;
+        unsigned long long* tiles2 = static_cast<unsigned long long*>(W.tiles2.p);
+        unsigned long long* blk_first = static_cast<unsigned long long*>(W.blk_first.p);
+        k_offsets_tile_sums<true><<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n_items_max, tiles2);
+        k_offsets_scan_tiles<<<1, kScanThreads, 0, st>>>(tiles2, n_tiles);
+        k_offsets_apply<true><<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n_items_max, tiles2, blk_first);
+        k_blk_index<<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, blk_first, static_cast<uint32_t*>(W.blkmap.p));
+        d->launches += 4;
+        blkmap = static_cast<const uint32_t*>(W.blkmap.p);
+    }
     if (d->opt_gather_u >= 8)
         k_gather<8><<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, item_offs, n_items_max, out_cap,
-                                                reinterpret_cast<uint32_t*>(d_out), P.dbg);
+                                                reinterpret_cast<uint32_t*>(d_out), P.dbg, blkmap);
     else if (d->opt_gather_u <= 2)
         k_gather<2><<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, item_offs, n_items_max, out_cap,
-                                                reinterpret_cast<uint32_t*>(d_out), P.dbg);
+                                                reinterpret_cast<uint32_t*>(d_out), P.dbg, blkmap);
     else
         k_gather<4><<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, item_offs, n_items_max, out_cap,
-                                                reinterpret_cast<uint32_t*>(d_out), P.dbg);
+                                                reinterpret_cast<uint32_t*>(d_out), P.dbg, blkmap);
     d->launches += 5;
     if (seg) {
         k_hay_offsets<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(seg_first, item_offs, n, offs64);
@@ -1132,6 +1174,10 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
         d->opt_seg_len = value;
     else if (k == "dbg")
         d->opt_dbg = value;
+    else if (k == "tail_seg")
+        d->opt_tail_seg = value;
+    else if (k == "gather_ordered")
+        d->opt_gather_ordered = value;
     else if (k == "gather_u")
         d->opt_gather_u = value;
     else if (k == "reserve_sms")

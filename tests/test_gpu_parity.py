@@ -157,7 +157,7 @@ def test_kernel_options_do_not_change_results():
     base = pma.scan_batch_host(D.FIND_OVERLAPPING, text, offs)
     for opts in ({"hot_records": -1}, {"hot_records": 17}, {"threads": 128}, {"threads": 512, "ctas_per_sm": 2},
                  {"kernel": 0}, {"kernel": 2}, {"kernel": 2, "threads": 256}, {"kernel": 0, "hot_records": 100}, {"l2_persist": 0}, {"hot_entries": 0},
-                 {"hot_entries": 64}, {"hot_entries": 8192}, {"hot_entries": 4096, "profile_items": 3}, {"dbg": 4}, {"dbg": 2}):
+                 {"hot_entries": 64}, {"hot_entries": 8192}, {"hot_entries": 4096, "profile_items": 3}, {"dbg": 4}, {"dbg": 2}, {"gather_ordered": 0}, {"gather_ordered": 2}, {"tail_seg": 1}):
         for k, v in opts.items():
             pma.set_option(k, v)
         r = pma.scan_batch_host(D.FIND_OVERLAPPING, text, offs)
@@ -170,6 +170,8 @@ def test_kernel_options_do_not_change_results():
         pma.set_option("hot_entries", 0)
         pma.set_option("profile_items", 2048)
         pma.set_option("dbg", 0)
+        pma.set_option("gather_ordered", 1)
+        pma.set_option("tail_seg", 0)
 
 
 def test_overflow_protocol_through_the_c_abi():
@@ -412,6 +414,7 @@ def test_tail_segmentation_many_small_haystacks():
     text = np.ascontiguousarray(np.tile(pool, reps)[: int(offs[-1])])
     pma = D.DoubleArrayAhoCorasick.new(ps.as_list())
     opma = O.OraclePma.build_packed(ps.blob, ps.offs)
+    pma.set_option("tail_seg", 1)
     for mode in (D.FIND_OVERLAPPING, D.FIND_OVERLAPPING_NO_SUFFIX):
         check_batch(pma, opma, mode, text, offs, nthreads=32)  # 46 MB: one host slice, i.e. one launch over all haystacks
 
