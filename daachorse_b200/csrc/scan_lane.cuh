@@ -904,7 +904,7 @@ struct LaneLm : LaneStd {
 
 struct LmMachine {
     static constexpr int TOPUP = TEXT_TOPUP;
-    static constexpr bool LAZY = false;
+    static constexpr bool LAZY = true;
     using Std = StdMachine<M_LEFTMOST, false, false>;
 
     static DACH_HD void seek(LaneLm& L, const StdEnv& Ev, uint32_t pos, const uint8_t* emu_lo) {
@@ -956,6 +956,24 @@ struct LmMachine {
         restart(L, Ev, emu_lo);
     }
 
+    // failure link of the state in L: the next probe, or ROOT at once if the link is DEAD
+    // (src/bytewise.rs:1120-1123)
+    static DACH_HD void fall(LaneLm& L, const StdEnv& Ev, uint32_t& fl) {
+        const uint32_t f = L.nf >> 8;
+        if (f == D_DEAD) {
+            L.cb = 0;
+            L.sig = 0;
+            L.nf = 0;
+            L.nfb = 0;
+            L.addr = D_ROOT;
+            fl = (fl & ~(F_PROBE | F_LEARN | F_OWN | F_ROOTP)) | F_LAND;
+        } else {
+            const bool to_root = f == D_ROOT;
+            L.addr = (to_root ? Ev.root_base : (L.nfb >> 8)) ^ L.c;
+            fl = (fl & ~(F_LEARN | F_OWN | F_ROOTP)) | F_PROBE | (to_root ? F_ROOTP : 0u);
+        }
+    }
+
     static DACH_HD bool step(LaneLm& L, const StdEnv& Ev, const uint8_t* emu_lo) {
         uint32_t fl = L.fl;
         const bool run = (fl & (F_ACTIVE | F_DONE)) == F_ACTIVE && L.qn != (uint32_t)LANE_Q;
@@ -989,25 +1007,12 @@ struct LmMachine {
                 const uint32_t c = (((o & 4u) ? hi : lo) >> ((o & 3u) * 8u)) & 0xffu;
 #endif
                 L.c = c;
-                L.addr = L.cb ^ c;
-                fl |= ((L.sig >> (c & 31u)) & 1u) ? (F_PROBE | F_OWN) : F_FALL;
-            }
-        }
-        DACH_SYNCWARP();
-        // ---- phase 2: failure link; DEAD ends at ROOT without a probe (src/bytewise.rs:1120-1123) ----
-        if (fl & F_FALL) {
-            const uint32_t f = L.nf >> 8;
-            if (f == D_DEAD) {
-                L.cb = 0;
-                L.sig = 0;
-                L.nf = 0;
-                L.nfb = 0;
-                L.addr = D_ROOT;
-                fl = (fl & ~(F_FALL | F_OWN | F_ROOTP)) | F_LAND;
-            } else {
-                const bool to_root = f == D_ROOT;
-                L.addr = (to_root ? Ev.root_base : (L.nfb >> 8)) ^ L.c;
-                fl = (fl & ~(F_FALL | F_OWN | F_ROOTP)) | F_PROBE | (to_root ? F_ROOTP : 0u);
+                if ((L.sig >> (c & 31u)) & 1u) {
+                    L.addr = L.cb ^ c;
+                    fl |= F_PROBE | F_OWN;
+                } else {
+                    fall(L, Ev, fl);  // certainly no child for this byte
+                }
             }
         }
         DACH_SYNCWARP();
@@ -1030,10 +1035,10 @@ struct LmMachine {
                     L.addr = D_ROOT;
                     fl = (fl & ~(F_PROBE | F_ROOTP)) | F_LAND;
                 } else if (fl & F_OWN) {
-                    fl = (fl & ~(F_PROBE | F_OWN)) | F_FALL;
+                    fall(L, Ev, fl);
                 } else if (L.nf & CF_F2ROOT) {
                     L.nf = 0;
-                    fl = (fl & ~F_PROBE) | F_FALL;
+                    fall(L, Ev, fl);
                 } else {
                     fl = (fl & ~F_PROBE) | F_LEARN;
                     L.addr = L.nf >> 8;
@@ -1041,7 +1046,7 @@ struct LmMachine {
             } else {  // F_LEARN
                 L.nf = x.y;
                 L.nfb = x.z;
-                fl = (fl & ~F_LEARN) | F_FALL;
+                fall(L, Ev, fl);
             }
         }
         DACH_SYNCWARP();
@@ -1130,7 +1135,7 @@ struct LaneCw : LaneLm {
 template <int MODE>
 struct CwMachine {
     static constexpr int TOPUP = 4;
-    static constexpr bool LAZY = false;
+    static constexpr bool LAZY = true;
     static constexpr bool LM = MODE == M_LEFTMOST;
     using Std = StdMachine<M_OVERLAPPING, false, false>;
 
@@ -1227,6 +1232,19 @@ struct CwMachine {
         }
     }
 
+    // failure link of the state in L: the next probe, or ROOT at once if the link is DEAD
+    static DACH_HD void fall(LaneCw& L, const StdEnv& Ev, uint32_t& fl) {
+        const uint32_t f = L.nf >> 8;
+        if (f == D_DEAD) {
+            set_root(L, Ev);
+            fl = (fl & ~(F_PROBE | F_LEARN | F_OWN | F_ROOTP)) | F_LAND;
+        } else {
+            const bool to_root = f == D_ROOT;
+            L.addr = (to_root ? Ev.root_base : (L.nfb >> 8)) ^ L.c;
+            fl = (fl & ~(F_LEARN | F_OWN | F_ROOTP)) | F_PROBE | (to_root ? F_ROOTP : 0u);
+        }
+    }
+
     static DACH_HD bool step(LaneCw& L, const StdEnv& Ev, const uint8_t* emu_lo) {
         (void)emu_lo;
         uint32_t fl = L.fl;
@@ -1263,22 +1281,13 @@ struct CwMachine {
                     fl |= F_LAND;
                 } else {
                     L.c = mc;
-                    L.addr = L.cb ^ mc;
-                    fl |= ((L.sig >> (mc & 15u)) & 1u) ? (F_PROBE | F_OWN) : F_FALL;
+                    if ((L.sig >> (mc & 15u)) & 1u) {
+                        L.addr = L.cb ^ mc;
+                        fl |= F_PROBE | F_OWN;
+                    } else {
+                        fall(L, Ev, fl);  // certainly no child for this code
+                    }
                 }
-            }
-        }
-        DACH_SYNCWARP();
-        // ---- phase 2: failure link; DEAD ends at ROOT without a probe ------------------------------------
-        if (fl & F_FALL) {
-            const uint32_t f = L.nf >> 8;
-            if (f == D_DEAD) {
-                set_root(L, Ev);
-                fl = (fl & ~(F_FALL | F_OWN | F_ROOTP)) | F_LAND;
-            } else {
-                const bool to_root = f == D_ROOT;
-                L.addr = (to_root ? Ev.root_base : (L.nfb >> 8)) ^ L.c;
-                fl = (fl & ~(F_FALL | F_OWN | F_ROOTP)) | F_PROBE | (to_root ? F_ROOTP : 0u);
             }
         }
         DACH_SYNCWARP();
@@ -1297,10 +1306,10 @@ struct CwMachine {
                     set_root(L, Ev);
                     fl = (fl & ~(F_PROBE | F_ROOTP)) | F_LAND;
                 } else if (fl & F_OWN) {
-                    fl = (fl & ~(F_PROBE | F_OWN)) | F_FALL;
+                    fall(L, Ev, fl);
                 } else if (L.nf & CF_F2ROOT) {
                     L.nf = 0;
-                    fl = (fl & ~F_PROBE) | F_FALL;
+                    fall(L, Ev, fl);
                 } else {
                     fl = (fl & ~F_PROBE) | F_LEARN;
                     L.addr = L.nf >> 8;
@@ -1308,7 +1317,7 @@ struct CwMachine {
             } else {  // F_LEARN
                 L.nf = x.y;
                 L.nfb = x.z;
-                fl = (fl & ~F_LEARN) | F_FALL;
+                fall(L, Ev, fl);
             }
         }
         DACH_SYNCWARP();
@@ -1512,14 +1521,14 @@ struct StdMachine2 {
                 land(L, Ev, fl);
             } else {
                 const uint32_t c = L.w0 & 0xffu;
-                if (fl & S2_LEARN) {  // x is the failure state's record
+                if (fl & S2_OWN) {  // signature false positive (the common miss): probe the failure state's children
+                    L.addr = (L.r2 >> 8) ^ c;
+                    fl ^= S2_OWN | S2_FAIL;
+                } else if (fl & S2_LEARN) {  // x is the failure state's record
                     L.nf = x.y;
                     L.r2 = x.z;
                     L.addr = (x.z >> 8) ^ c;
                     fl ^= S2_LEARN | S2_FAIL;
-                } else if (fl & S2_OWN) {  // signature false positive: probe the failure state's children
-                    L.addr = (L.r2 >> 8) ^ c;
-                    fl ^= S2_OWN | S2_FAIL;
                 } else if ((fl & S2_ROOT) || (L.nf & CF_FROOT)) {  // ROOT has no such child: stay in ROOT
                     to_root(L, Ev);
                     L.addr = D_ROOT;
