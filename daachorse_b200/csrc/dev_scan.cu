@@ -878,7 +878,8 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     k_offsets_apply<false><<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n_items_max, tiles, item_offs);
     const int gather_grid = d->sm_count * 8;
     const uint32_t* blkmap = nullptr;
-    if (d->opt_gather_ordered >= 2 || (d->opt_gather_ordered == 1 && pool_blocks >= 4096)) {  // tiny batches: not worth three more launches
+    // batches whose match blocks stay in L2 anyway are copied in pool order (four launches fewer)
+    if (d->opt_gather_ordered >= 2 || (d->opt_gather_ordered == 1 && text_bytes >= (256ull << 20))) {
         if (!ensure(W.blk_first, (n_items_max + 1) * 8) || !ensure(W.blkmap, (size_t)pool_blocks * 4) || !ensure(W.tiles2, n_tiles * 8))
             return DACH_CUDA_ERROR;
         unsigned long long* tiles2 = static_cast<unsigned long long*>(W.tiles2.p);
