@@ -95,7 +95,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-// M: the lane machine (StdMachine<...> or LmMachine), LANE: its per-lane state
+// M: the lane machine (StdMachine2 / StdMachine / LmMachine / CwMachine), LANE: its per-lane state
 template <class M, class LANE, int MAXT, int MINB, bool PROFILE, bool HOT>
 __global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
     // dynamic shared memory: [state cache hot_entries x 16 B (HOT only)][event queues LANE_Q x blockDim x 8 B]
