@@ -1,13 +1,17 @@
 // CUDA kernels (sm_100a) and the device half of the C ABI of libdaachorse_b200.
 //
 // Pipeline of one dach_dev_scan_batch():
-//   1. k_scan<CHARWISE, MODE>   persistent grid (CTAs = SMs x ctas_per_sm); lanes pull items from
-//                               one atomic counter; each lane walks its haystack through the
-//                               automaton image (hot records + root row in shared memory, the
-//                               rest through L1/L2) and appends matches to pooled 256-byte blocks.
+//   1. k_scan_machine<M, LANE>  persistent grid (CTAs = SMs x ctas_per_sm); warps of 32 independent
+//                               walkers pull items (haystacks or segments) from one atomic counter
+//                               and step them in lock step through the automaton image -- one record
+//                               fetch per lane per iteration (scan_lane.cuh: StdMachine2, LmMachine,
+//                               CwMachine); matches go to pooled 256-byte blocks.
+//      k_scan<CHARWISE, MODE>   lane per haystack, reference-shaped loop: automata above 2^24 slots,
+//                               find_iter with an empty pattern, and option kernel=0.
 //   2. k_offsets_*              exclusive scan of the per-item match counts -> d_out_offs (u64).
-//   3. k_gather                 copies every pooled block to its final place, which makes the
-//                               output dense and ordered exactly like the crate's iterators.
+//   3. k_blk_index + k_gather   copy every pooled block to its final place (in output order for large
+//                               batches), which makes the output dense and ordered exactly like the
+//                               crate's iterators.
 // No CPU fallback exists: every entry point here fails with DACH_CUDA_ERROR without a device.
 #include <cuda_runtime.h>
 
