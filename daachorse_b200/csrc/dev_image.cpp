@@ -111,36 +111,6 @@ int build_image(const dach_pma* p, HostImage* img) {
                 r[3] = sig;
                 img->opos_tab[s] = opos;
             }
-            // Two-byte jump from ROOT (Standard automata with BASE(ROOT) != 0): entry (b0 | b1 << 8) is a
-            // copy of the record of d2 = child(child(ROOT, b0), b1), valid when both states exist and
-            // neither has an output list -- then landing on d2 directly reports exactly what two single
-            // steps would.  A lane whose failure target is ROOT consumes two bytes with ONE fetch (on
-            // UTF-8 text nearly every char boundary).  Invalid entries carry a CHECK byte that cannot
-            // match b1; the lane then takes the ordinary one-byte route.
-            if (!lm && img->root_base != 0) {
-                img->crec[kRoot * 4 + 3] = 0;  // ROOT's own signature: every byte takes the failure route (= ROOT)
-                img->jump_base = uint32_t(n);
-                img->crec.resize((n + 65536) * 4, 0);
-                auto child = [&](uint32_t st, uint32_t c) -> uint32_t {
-                    const uint32_t b = p->base[st];
-                    if (b == 0) return kRoot;
-                    const uint32_t ci = b ^ c;
-                    return (ci < n && (p->opos_ch[ci] & 0xff) == c) ? ci : kRoot;
-                };
-                for (uint32_t b0 = 0; b0 < 256; ++b0) {
-                    const uint32_t d1 = child(kRoot, b0);
-                    const bool d1_ok = d1 != kRoot && (p->opos_ch[d1] >> 8) == 0;
-                    for (uint32_t b1 = 0; b1 < 256; ++b1) {
-                        uint32_t* r = &img->crec[(size_t(n) + (b0 | (b1 << 8))) * 4];
-                        const uint32_t d2 = d1_ok ? child(d1, b1) : kRoot;
-                        if (d2 != kRoot && (p->opos_ch[d2] >> 8) == 0) {
-                            for (int k = 0; k < 4; ++k) r[k] = img->crec[size_t(d2) * 4 + k];
-                        } else {
-                            r[0] = (b1 ^ 0xffu) & 0xffu;  // CHECK != b1
-                        }
-                    }
-                }
-            }
         }
     } else {
         for (size_t s = 0; s < n; ++s) {

@@ -19,8 +19,6 @@ struct HostImage {
     std::vector<uint32_t> root_table;  // 256 words (bytewise)
     std::vector<uint32_t> crec;        // compact records, 4 words per slot (bytewise Standard, <= 2^24 slots)
     std::vector<uint32_t> opos_tab;    // output_pos per slot (with crec)
-    uint32_t jump_base = 0;            // bytewise Standard: crec[jump_base + (b0 | b1 << 8)] = record of the state two
-                                       // bytes below ROOT (0: no jump table); see dev_image.cpp
     uint32_t root_base = 0;
     std::vector<uint32_t> mapper;      // charwise code table
 };

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
     uint32_t hot_shift = 0;
     while ((1u << hot_shift) < P.hot_entries) ++hot_shift;
     const StdEnv Ev{P.crec,     s_hot,      HOT ? P.hot_entries - 1u : 0u, hot_shift, P.visits, P.opos_tab,
-                    P.text_end, P.root_base, P.root_opos ? CF_OUT : 0u, s_queue + threadIdx.x, blockDim.x, P.dbg, P.mapper, P.mapper_len, ld_u4(P.crec + D_ROOT), P.jump_base};
+                    P.text_end, P.root_base, P.root_opos ? CF_OUT : 0u, s_queue + threadIdx.x, blockDim.x, P.dbg, P.mapper, P.mapper_len, ld_u4(P.crec + D_ROOT)};
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     LANE L;
@@ -489,7 +489,6 @@ struct dach_dev {
     uint4* d_crec = nullptr;
     uint32_t* d_opos = nullptr;
     uint32_t root_base = 0;
-    uint32_t jump_base = 0;
     uint32_t* d_mapper = nullptr;
     void* image_base = nullptr;
     size_t image_alloc = 0, l2_window = 0, l2_persist = 0;
@@ -506,7 +505,6 @@ struct dach_dev {
     // (113 vs 116 GB/s, profiles/r1_cache_experiments.md); kept as an option (power of two).
     int64_t opt_hot_entries = 0;
     int64_t opt_profile_items = 2048;
-    int64_t opt_jump = 1;            // StdMachine2: two-byte jump table below ROOT
     int64_t opt_tail_seg = 0;        // cut only the last 2 x lanes haystacks of a large batch (measured: -2 %, off)
     int64_t opt_gather_ordered = 1;  // copy pool blocks in output order (sequential writes)
     int64_t opt_gather_u = 4;     // pooled blocks in flight per warp of k_gather (2, 4 or 8)
@@ -771,7 +769,6 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     P.crec = d->d_crec;
     P.opos_tab = d->d_opos;
     P.root_base = d->root_base;
-    P.jump_base = d->opt_jump ? d->jump_base : 0;
     P.mapper = d->d_mapper;
     P.mapper_len = d->mapper_len;
     P.n_slots = d->n_slots;
@@ -994,7 +991,6 @@ int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
             d->d_opos = reinterpret_cast<uint32_t*>(b + part_off[5]);
         }
         d->root_base = img.root_base;
-        d->jump_base = img.jump_base;
         // let the automaton persist in L2 while text and match streams pass through it
         d->l2_window = std::min<size_t>(total, (size_t)prop.accessPolicyMaxWindowSize);
         d->l2_persist = std::min<size_t>(d->l2_window, (size_t)prop.persistingL2CacheMaxSize);
@@ -1183,8 +1179,6 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
         d->opt_seg_len = value;
     else if (k == "dbg")
         d->opt_dbg = value;
-    else if (k == "jump")
-        d->opt_jump = value;
     else if (k == "tail_seg")
         d->opt_tail_seg = value;
     else if (k == "gather_ordered")

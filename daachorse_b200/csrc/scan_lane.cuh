@@ -106,7 +106,6 @@ struct ScanParams {
     const uint32_t* item_beg;
     const unsigned long long* n_items_dev;
     uint32_t seg_len, warm;
-    uint32_t jump_base;  // crec[jump_base + (b0 | b1 << 8)]: two-byte jump from ROOT (0: none)
     uint32_t seg_from;  // haystacks below this index stay whole (one item each): only the tail of a batch is cut
     uint32_t dbg;  // experiment switches (bench --option dbg=): 1 = count matches but do not store them,
                    // 2 = text via ld.global.cs, 4 = text via ld.global.nc.L1::no_allocate
@@ -611,7 +610,6 @@ struct StdEnv {
     const uint32_t* mapper;  // charwise: code point -> mapped code (D_INVALID_CODE = unmapped)
     uint32_t mapper_len;
     uint4 root_rec;          // StdMachine2: ROOT's compact record
-    uint32_t jump_base;      // StdMachine2: first record of the two-byte jump table, 0 = none
 };
 
 DACH_HD uint4 ld_text16(const uint8_t* q, const uint8_t* text_end, const uint8_t* emu_lo, uint32_t dbg = 0) {
@@ -1417,8 +1415,8 @@ struct CwMachine {
 // =============================================================================================
 
 constexpr uint32_t CF_FROOT = 8u;  // efail == ROOT (Standard records)
-constexpr uint32_t S2_OWN = 0x10u, S2_FAIL = 0x20u, S2_ROOT = 0x40u, S2_LEARN = 0x80u, S2_LAND = 0x100u, S2_FULL = 0x200u,
-                   S2_JUMP = 0x400u, S2_BUSY = 0x4f0u;
+constexpr uint32_t S2_OWN = 0x10u, S2_FAIL = 0x20u, S2_ROOT = 0x40u, S2_LEARN = 0x80u, S2_BUSY = 0xf0u, S2_LAND = 0x100u,
+                   S2_FULL = 0x200u;
 
 struct Lane2 {
     const uint8_t* hay;
@@ -1449,7 +1447,7 @@ DACH_HD uint2 ld_text8(const uint8_t* q, const uint8_t* text_end, const uint8_t*
 
 template <int MODE>
 struct StdMachine2 {
-    static constexpr int TOPUP = 4;  // a lane consumes at most 2 bytes per iteration: one window crossing per period
+    static constexpr int TOPUP = 8;
     static constexpr bool LAZY = true;
 
     static DACH_HD const uint8_t* block_of(const Lane2& L) {
@@ -1506,24 +1504,15 @@ struct StdMachine2 {
                 fl |= F_DONE;
             } else {
                 const uint32_t own = (L.sig >> (L.w0 & 31u)) & 1u;
-                // failure target ROOT and two bytes at hand (same 8-byte window, inside the item): one fetch
-                // from the jump table may consume both
-                const bool jump = !own && (L.nf & CF_FROOT) && Ev.jump_base != 0 &&
-                                  (((uint32_t)(uintptr_t)L.hay + L.pos) & 7u) != 7u && L.pos + 1u < L.len;
-                if (jump) {
-                    L.addr = Ev.jump_base + (L.w0 & 0xffffu);
-                    fl |= S2_JUMP;
-                } else {
-                    L.addr = ((own ? L.r0 : L.r2) >> 8) ^ (L.w0 & 0xffu);
-                    fl |= S2_FAIL >> own;  // S2_OWN == S2_FAIL >> 1
-                }
+                L.addr = ((own ? L.r0 : L.r2) >> 8) ^ (L.w0 & 0xffu);
+                fl |= S2_FAIL >> own;  // S2_OWN == S2_FAIL >> 1
             }
         }
         DACH_SYNCWARP();
         // ---- phase B: the one record fetch; a hit lands at once ----------------------------------------
         if (run && (fl & S2_BUSY) != 0) {
             const uint4 x = ld_u4(Ev.glob + L.addr);
-            if ((((x.x ^ L.w0) & 0xffu) | (fl & (S2_LEARN | S2_JUMP))) == 0) {  // CHECK == c: adopt the record
+            if ((((x.x ^ L.w0) & 0xffu) | (fl & S2_LEARN)) == 0) {  // CHECK == c: adopt the record
                 L.r0 = x.x;
                 L.nf = x.y;
                 L.r2 = x.z;
@@ -1532,26 +1521,7 @@ struct StdMachine2 {
                 land(L, Ev, fl);
             } else {
                 const uint32_t c = L.w0 & 0xffu;
-                if (fl & S2_JUMP) {
-                    if (((x.x ^ (L.w0 >> 8)) & 0xffu) == 0) {  // valid entry: two bytes consumed, no output on the way
-                        L.r0 = x.x;
-                        L.nf = x.y;
-                        L.r2 = x.z;
-                        L.sig = x.w;
-                        fl &= ~S2_BUSY;
-                        L.pos += 2;
-                        L.w0 = (L.w0 >> 16) | (L.w1 << 16);
-                        L.w1 >>= 16;
-                        if ((((uint32_t)(uintptr_t)L.hay + L.pos) & 7u) == 0) {
-                            L.w0 = L.n0;
-                            L.w1 = L.n1;
-                            fl |= F_NEED_NW;
-                        }
-                    } else {  // no such pair (or an output on the way): the ordinary probe of ROOT's children
-                        L.addr = Ev.root_base ^ c;
-                        fl ^= S2_JUMP | S2_FAIL;
-                    }
-                } else if (fl & S2_OWN) {  // signature false positive (the common miss): probe the failure state's children
+                if (fl & S2_OWN) {  // signature false positive (the common miss): probe the failure state's children
                     L.addr = (L.r2 >> 8) ^ c;
                     fl ^= S2_OWN | S2_FAIL;
                 } else if (fl & S2_LEARN) {  // x is the failure state's record

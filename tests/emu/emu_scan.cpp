@@ -211,7 +211,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
         std::vector<uint32_t> tab((size_t)(entries ? entries : 1) * 4, 0);
         StdEnv Ev{reinterpret_cast<const uint4*>(img.crec.data()), reinterpret_cast<const uint4*>(tab.data()), 0u, 0u, visits.data(),
                   img.opos_tab.data(), P.text_end, img.root_base, P.root_opos ? CF_OUT : 0u, nullptr, 0, 0, P.mapper, P.mapper_len,
-                  reinterpret_cast<const uint4*>(img.crec.data())[D_ROOT], getenv("DACH_EMU_NOJUMP") ? 0u : img.jump_base};
+                  reinterpret_cast<const uint4*>(img.crec.data())[D_ROOT]};
         const int n_warps = 3;
         if (entries) {
             ScanParams Q = P;

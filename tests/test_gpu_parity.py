@@ -157,7 +157,7 @@ def test_kernel_options_do_not_change_results():
     base = pma.scan_batch_host(D.FIND_OVERLAPPING, text, offs)
     for opts in ({"hot_records": -1}, {"hot_records": 17}, {"threads": 128}, {"threads": 512, "ctas_per_sm": 2},
                  {"kernel": 0}, {"kernel": 2}, {"kernel": 2, "threads": 256}, {"kernel": 0, "hot_records": 100}, {"l2_persist": 0}, {"hot_entries": 0},
-                 {"hot_entries": 64}, {"hot_entries": 8192}, {"hot_entries": 4096, "profile_items": 3}, {"dbg": 4}, {"dbg": 2}, {"gather_ordered": 0}, {"gather_ordered": 2}, {"tail_seg": 1}, {"jump": 0}):
+                 {"hot_entries": 64}, {"hot_entries": 8192}, {"hot_entries": 4096, "profile_items": 3}, {"dbg": 4}, {"dbg": 2}, {"gather_ordered": 0}, {"gather_ordered": 2}, {"tail_seg": 1}):
         for k, v in opts.items():
             pma.set_option(k, v)
         r = pma.scan_batch_host(D.FIND_OVERLAPPING, text, offs)
@@ -172,7 +172,6 @@ def test_kernel_options_do_not_change_results():
         pma.set_option("dbg", 0)
         pma.set_option("gather_ordered", 1)
         pma.set_option("tail_seg", 0)
-        pma.set_option("jump", 1)
 
 
 def test_overflow_protocol_through_the_c_abi():
