@@ -316,7 +316,7 @@ def main():
                "d2h_bytes_per_step": int(st["d2h_bytes"]), "ms_per_step": float(np.mean(e2e_ms)),
                "matches_per_step": int(len(r.matches)),
                "workload": "%d haystacks x %d B per step per GPU through dach_scan_batch_host: pinned host text -> "
-                           "device -> scan -> pinned host matches, 64 MiB slices, three in flight" % (ne, hay_len)}
+                           "device -> scan -> pinned host matches, 64 MiB slices, uploads two slices ahead" % (ne, hay_len)}
         del h_text, h_out_t, h_oo_t
 
     if rank != 0:
