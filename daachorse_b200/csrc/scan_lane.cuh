@@ -1479,15 +1479,12 @@ struct StdMachine2 {
             fl |= F_NEED_NW;
         }
         if ((L.nf & CF_OUT) && L.pos > L.from) {
-            QEntry* qe = Ev.q + L.qn * Ev.q_stride;
-            qe->end = L.pos;
-#if defined(__CUDA_ARCH__)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(&qe->opos)),
-                         "l"(Ev.opos + L.addr)
-                         : "memory");
-#else
-            qe->opos = Ev.opos[L.addr];
-#endif
+            // one 8-byte store: (end, slot).  output_pos is looked up when the queue is drained -- this block
+            // runs with ~1.5 of 32 lanes active in three of four iterations, so it has to be short
+            QEntry e;
+            e.end = L.pos;
+            e.opos = L.addr;
+            Ev.q[L.qn * Ev.q_stride] = e;
             ++L.qn;
             if (L.qn == (uint32_t)LANE_Q) fl |= S2_FULL;
             if (MODE == M_FIND) to_root(L, Ev);  // every next() restarts at ROOT (src/bytewise/iter.rs:87)
@@ -1548,16 +1545,14 @@ struct StdMachine2 {
     }
 
     static DACH_HD void drain(Lane2& L, const StdEnv& Ev, const ScanParams& P, Emitter& E) {
-#if defined(__CUDA_ARCH__)
-        asm volatile("cp.async.wait_all;" ::: "memory");
-#endif
         for (uint32_t j = 0; j < (uint32_t)LANE_Q; ++j) {
             if (j < L.qn) {
                 const QEntry e = Ev.q[j * Ev.q_stride];
+                const uint32_t opos = ld_u32(Ev.opos + e.opos);  // the entry holds the slot
                 if (MODE == M_OVERLAPPING)
-                    emit_chain(P, E, e.opos, e.end);
+                    emit_chain(P, E, opos, e.end);
                 else
-                    emit_head(P, E, e.opos, e.end);
+                    emit_head(P, E, opos, e.end);
             }
         }
         L.qn = 0;
@@ -1602,7 +1597,7 @@ struct StdMachine2 {
         if (MODE != M_FIND && (Ev.root_flags & CF_OUT) && beg == 0) {
             QEntry e;
             e.end = 0;
-            e.opos = ld_u32(Ev.opos + D_ROOT);
+            e.opos = D_ROOT;
             Ev.q[0] = e;
             L.qn = 1;
         }
