@@ -564,7 +564,8 @@ constexpr uint32_t F_ACTIVE = 1u, F_DONE = 2u, F_NEED_NW = 4u, F_OWN = 8u, F_ROO
                    F_FALL = 128u, F_LAND = 256u;
 
 struct QEntry {
-    uint32_t end, opos;  // opos is filled asynchronously (cp.async from the side table) when the event is queued
+    uint32_t end, opos;  // StdMachine: opos = output_pos, filled asynchronously by cp.async when the event is queued;
+                         // StdMachine2 / LmMachine / CwMachine: opos = the slot, output_pos is looked up at drain
 };
 
 // State cache entries are compact records whose spare bits carry a 14-bit tag: bits 2..7 of w1 and
@@ -927,14 +928,10 @@ struct LmMachine {
     }
 
     static DACH_HD void push(LaneLm& L, const StdEnv& Ev, uint32_t end, uint32_t slot) {
-        QEntry* qe = Ev.q + L.qn * Ev.q_stride;
-        qe->end = end;
-#if defined(__CUDA_ARCH__)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(&qe->opos)), "l"(Ev.opos + slot)
-                     : "memory");
-#else
-        qe->opos = Ev.opos[slot];
-#endif
+        QEntry e;  // (end, slot): output_pos is looked up when the queue is drained
+        e.end = end;
+        e.opos = slot;
+        Ev.q[L.qn * Ev.q_stride] = e;
         ++L.qn;
     }
 
@@ -1075,13 +1072,10 @@ struct LmMachine {
     }
 
     static DACH_HD void drain(LaneLm& L, const StdEnv& Ev, const ScanParams& P, Emitter& E) {
-#if defined(__CUDA_ARCH__)
-        asm volatile("cp.async.wait_all;" ::: "memory");
-#endif
         for (uint32_t j = 0; j < (uint32_t)LANE_Q; ++j) {
             if (j < L.qn) {
                 const QEntry e = Ev.q[j * Ev.q_stride];
-                emit_head(P, E, e.opos, e.end);
+                emit_head(P, E, ld_u32(Ev.opos + e.opos), e.end);
             }
         }
         L.qn = 0;
@@ -1191,14 +1185,10 @@ struct CwMachine {
     }
 
     static DACH_HD void push(LaneCw& L, const StdEnv& Ev, uint32_t end, uint32_t slot) {
-        QEntry* qe = Ev.q + L.qn * Ev.q_stride;
-        qe->end = end;
-#if defined(__CUDA_ARCH__)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(&qe->opos)), "l"(Ev.opos + slot)
-                     : "memory");
-#else
-        qe->opos = Ev.opos[slot];
-#endif
+        QEntry e;  // (end, slot): output_pos is looked up when the queue is drained
+        e.end = end;
+        e.opos = slot;
+        Ev.q[L.qn * Ev.q_stride] = e;
         ++L.qn;
     }
 
@@ -1359,16 +1349,14 @@ struct CwMachine {
     }
 
     static DACH_HD void drain(LaneCw& L, const StdEnv& Ev, const ScanParams& P, Emitter& E) {
-#if defined(__CUDA_ARCH__)
-        asm volatile("cp.async.wait_all;" ::: "memory");
-#endif
         for (uint32_t j = 0; j < (uint32_t)LANE_Q; ++j) {
             if (j < L.qn) {
                 const QEntry e = Ev.q[j * Ev.q_stride];
+                const uint32_t opos = ld_u32(Ev.opos + e.opos);
                 if (MODE == M_OVERLAPPING)
-                    emit_chain(P, E, e.opos, e.end);
+                    emit_chain(P, E, opos, e.end);
                 else
-                    emit_head(P, E, e.opos, e.end);
+                    emit_head(P, E, opos, e.end);
             }
         }
         L.qn = 0;
@@ -1393,7 +1381,7 @@ struct CwMachine {
         if (!LM && MODE != M_FIND && (Ev.root_flags & CF_OUT)) {  // ROOT's output list is pending at position 0
             QEntry e;
             e.end = 0;
-            e.opos = ld_u32(Ev.opos + D_ROOT);
+            e.opos = D_ROOT;
             Ev.q[0] = e;
             L.qn = 1;
         }
