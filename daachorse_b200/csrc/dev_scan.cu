@@ -160,24 +160,18 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
         if (!__any_sync(FULL, (L.fl & F_ACTIVE) != 0)) break;
         // ---- lock-step iterations until some lane needs service ----
         bool stop = false;
-        int idle_rounds = 0;
         while (!stop) {
             M::text_topup(L, Ev, nullptr);
-            if (M::LAZY) {
-                // Lanes that need service (item finished, queue full) are looked for once per top-up period,
-                // and a service phase is only worth its ~150 instructions for a full queue, for four waiting
-                // lanes, or after four periods of waiting -- short haystacks finish all the time.
+            if (M::LAZY) {  // look for lanes that need service once per top-up period, not per iteration
+                // (batching further -- wait for four lanes or four periods -- idles ~3 lanes of 32 on
+                // 1 KiB haystacks and lost 6-9 % on the leftmost configs: measured, dropped)
                 bool waiting = false;
 #pragma unroll 1
                 for (int k = 0; k < M::TOPUP; ++k) {
                     const bool ok = M::step(L, Ev, nullptr);
                     waiting |= !ok;
                 }
-                waiting = waiting && (L.fl & F_ACTIVE);
-                const unsigned wm = __ballot_sync(FULL, waiting);
-                const bool any_full = __any_sync(FULL, waiting && L.qn == (uint32_t)LANE_Q);
-                if (wm) ++idle_rounds;
-                stop = any_full || __popc(wm) >= 4 || idle_rounds >= 4;
+                stop = __any_sync(FULL, waiting && (L.fl & F_ACTIVE));
             } else {
 #pragma unroll 1
                 for (int k = 0; k < M::TOPUP; ++k) {

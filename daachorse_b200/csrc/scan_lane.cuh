@@ -892,6 +892,7 @@ struct StdMachine {
 
 constexpr uint32_t CF_F2DEAD = 4u;  // leftmost records: efail(efail) == DEAD
 // leftmost iterator flags (LaneLm::it)
+constexpr uint32_t F_REPORT = 0x200u, F_FLUSH = 0x400u;  // lane flags of the leftmost machines (phase 5)
 constexpr uint32_t IT_INIT = 1u;          // init_output_pos is Some (an empty pattern exists and is still reportable)
 constexpr uint32_t IT_HAVE_LAST = 2u;     // last_output_pos is Some
 constexpr uint32_t IT_LAST_IS_INIT = 4u;  // ... and it is the empty pattern's
@@ -908,23 +909,41 @@ struct LmMachine {
     static constexpr bool LAZY = true;
     using Std = StdMachine<M_LEFTMOST, false, false>;
 
-    static DACH_HD void seek(LaneLm& L, const StdEnv& Ev, uint32_t pos, const uint8_t* emu_lo) {
+    static DACH_HD void seek_full(LaneLm& L, const StdEnv& Ev, uint32_t pos, const uint8_t* emu_lo) {
         L.pos = pos;
         const uint8_t* b0 = Std::block_of(L);
         L.cw = ld_text16(b0, Ev.text_end, emu_lo, Ev.dbg);
         L.nw = ld_text16(b0 + 16, Ev.text_end, emu_lo, Ev.dbg);
         L.fl &= ~F_NEED_NW;
     }
+    // The cursor goes back to `pos` (the end of the reported match): usually a few bytes, so the windows
+    // are kept when `pos` is in the block they hold, and only one block is loaded when it is the one before.
+    static DACH_HD void seek(LaneLm& L, const StdEnv& Ev, uint32_t pos, const uint8_t* emu_lo) {
+        const uint8_t* cur = Std::block_of(L);
+        L.pos = pos;
+        const uint8_t* nb = Std::block_of(L);
+        if (nb == cur) return;
+        if (nb + 16 == cur) {
+            L.nw = L.cw;
+            L.cw = ld_text16(nb, Ev.text_end, emu_lo, Ev.dbg);
+            L.fl &= ~F_NEED_NW;
+            return;
+        }
+        seek_full(L, Ev, pos, emu_lo);
+    }
 
     // start of one next() call: ROOT, last = init, scan from self.pos
-    static DACH_HD void restart(LaneLm& L, const StdEnv& Ev, const uint8_t* emu_lo) {
+    static DACH_HD void restart(LaneLm& L, const StdEnv& Ev, const uint8_t* emu_lo, bool full = false) {
         L.cb = 0;
         L.sig = 0;
         L.nf = 0;
         L.nfb = 0;
         L.last = D_ROOT;
         L.it = (L.it & (IT_INIT | IT_SKIP_EMPTY)) | ((L.it & IT_INIT) ? (IT_HAVE_LAST | IT_LAST_IS_INIT) : 0u);
-        seek(L, Ev, L.self_pos, emu_lo);
+        if (full)
+            seek_full(L, Ev, L.self_pos, emu_lo);
+        else
+            seek(L, Ev, L.self_pos, emu_lo);
     }
 
     static DACH_HD void push(LaneLm& L, const StdEnv& Ev, uint32_t end, uint32_t slot) {
@@ -935,22 +954,27 @@ struct LmMachine {
         ++L.qn;
     }
 
-    // The automaton is back in ROOT (or the input ended) with a match pending: the report rules of
-    // iter.rs:283-306.  `unit` = bytes consumed by the unit that led here (1 for bytes).
-    static DACH_HD void report(LaneLm& L, const StdEnv& Ev, const uint8_t* emu_lo) {
+    // End of one next() call, the only place a match is queued.  F_REPORT: the automaton fell back to ROOT
+    // (or the input ended inside a partial match) with a match pending -- the rules of
+    // iter.rs:283-306.  F_FLUSH: the input ended (iter.rs:320-339).  Then the next call starts at self.pos.
+    static DACH_HD void finish_next(LaneLm& L, const StdEnv& Ev, uint32_t& fl, const uint8_t* emu_lo) {
         const uint32_t end = L.self_pos;
         bool emit = true;
-        if (L.it & IT_LAST_IS_INIT) {
-            L.self_pos += 1;
-            if (L.it & IT_SKIP_EMPTY) {
-                L.it &= ~IT_SKIP_EMPTY;
-                emit = false;  // continue 'a: re-scan from the new self.pos without yielding
+        if (fl & F_REPORT) {
+            if (L.it & IT_LAST_IS_INIT) {
+                L.self_pos += 1;
+                if (L.it & IT_SKIP_EMPTY) {
+                    L.it &= ~IT_SKIP_EMPTY;
+                    emit = false;  // continue 'a: re-scan from the new self.pos without yielding
+                }
+            } else {
+                L.it |= IT_SKIP_EMPTY;
             }
-        } else {
-            L.it |= IT_SKIP_EMPTY;
         }
         if (emit) push(L, Ev, end, L.last);
+        L.fl = fl & ~(F_REPORT | F_FLUSH);
         restart(L, Ev, emu_lo);
+        fl = L.fl;
     }
 
     // failure link of the state in L: the next probe, or ROOT at once if the link is DEAD
@@ -979,18 +1003,9 @@ struct LmMachine {
             if (L.pos >= L.len) {
                 if (L.self_pos == L.len) L.it &= ~IT_INIT;
                 if (L.it & IT_HAVE_LAST) {
-                    if (L.self_pos < L.len && (L.it & IT_LAST_IS_INIT)) {
-                        // input ended inside a partial match with only the empty pattern pending: the
-                        // reference never terminates here; treated like the fall-back-to-ROOT branch
-                        L.fl = fl;
-                        report(L, Ev, emu_lo);
-                        fl = L.fl;
-                    } else {
-                        push(L, Ev, L.self_pos, L.last);
-                        L.fl = fl;
-                        restart(L, Ev, emu_lo);
-                        fl = L.fl;
-                    }
+                    // input ended inside a partial match with only the empty pattern pending: the reference
+                    // never terminates here; treated like the fall-back-to-ROOT branch (F_REPORT)
+                    fl |= (L.self_pos < L.len && (L.it & IT_LAST_IS_INIT)) ? F_REPORT : F_FLUSH;
                 } else {
                     fl |= F_DONE;
                 }
@@ -1056,17 +1071,15 @@ struct LmMachine {
                 fl |= F_NEED_NW;
             }
             if (L.addr == D_ROOT) {
-                if (L.it & IT_HAVE_LAST) {
-                    L.fl = fl;
-                    report(L, Ev, emu_lo);
-                    fl = L.fl;
-                }
+                if (L.it & IT_HAVE_LAST) fl |= F_REPORT;
             } else if (L.nf & CF_OUT) {
                 L.last = L.addr;
                 L.it = (L.it | IT_HAVE_LAST) & ~IT_LAST_IS_INIT;
                 L.self_pos = L.pos;
             }
         }
+        // ---- phase 5: a next() call ends ---------------------------------------------------------------
+        if (fl & (F_REPORT | F_FLUSH)) finish_next(L, Ev, fl, emu_lo);
         L.fl = fl;
         return run;
     }
@@ -1095,7 +1108,7 @@ struct LmMachine {
         L.self_pos = 0;
         L.it = (Ev.root_flags & CF_OUT) ? IT_INIT : 0u;
         E.begin((uint32_t)item);
-        restart(L, Ev, emu_lo);
+        restart(L, Ev, emu_lo, true);
     }
 };
 
@@ -1165,15 +1178,30 @@ struct CwMachine {
         L.addr = D_ROOT;
     }
 
-    static DACH_HD void seek(LaneCw& L, const StdEnv& Ev, uint32_t pos, const uint8_t* emu_lo) {
+    static DACH_HD void seek_full(LaneCw& L, const StdEnv& Ev, uint32_t pos, const uint8_t* emu_lo) {
         L.pos = pos;
         const uint8_t* b0 = Std::block_of(L);
         L.cw = ld_text16(b0, Ev.text_end, emu_lo, Ev.dbg);
         L.nw = ld_text16(b0 + 16, Ev.text_end, emu_lo, Ev.dbg);
         L.fl &= ~F_NEED_NW;
     }
+    // the cursor goes back a few bytes: keep the windows when they still hold `pos` (see LmMachine::seek)
+    static DACH_HD void seek(LaneCw& L, const StdEnv& Ev, uint32_t pos, const uint8_t* emu_lo) {
+        const uint8_t* cur = Std::block_of(L);
+        const bool nw_stale = (L.fl & F_NEED_NW) != 0;
+        L.pos = pos;
+        const uint8_t* nb = Std::block_of(L);
+        if (nb == cur && !nw_stale) return;
+        if (nb + 16 == cur) {
+            L.nw = L.cw;
+            L.cw = ld_text16(nb, Ev.text_end, emu_lo, Ev.dbg);
+            L.fl &= ~F_NEED_NW;
+            return;
+        }
+        seek_full(L, Ev, pos, emu_lo);
+    }
 
-    static DACH_HD void restart(LaneCw& L, const StdEnv& Ev, const uint8_t* emu_lo) {
+    static DACH_HD void restart(LaneCw& L, const StdEnv& Ev, const uint8_t* emu_lo, bool full = false) {
         L.cb = 0;
         L.sig = 0;
         L.nf = 0;
@@ -1181,7 +1209,10 @@ struct CwMachine {
         L.cur = D_ROOT;
         L.last = D_ROOT;
         L.it = (L.it & (IT_INIT | IT_SKIP_EMPTY)) | ((L.it & IT_INIT) ? (IT_HAVE_LAST | IT_LAST_IS_INIT) : 0u);
-        seek(L, Ev, L.self_pos, emu_lo);
+        if (full)
+            seek_full(L, Ev, L.self_pos, emu_lo);
+        else
+            seek(L, Ev, L.self_pos, emu_lo);
     }
 
     static DACH_HD void push(LaneCw& L, const StdEnv& Ev, uint32_t end, uint32_t slot) {
@@ -1192,25 +1223,29 @@ struct CwMachine {
         ++L.qn;
     }
 
-    // src/charwise/iter.rs:345-366; `adv` = bytes of the char that led back to ROOT
-    static DACH_HD void report(LaneCw& L, const StdEnv& Ev, uint32_t adv, const uint8_t* emu_lo) {
+    // End of one next() call, the only place a leftmost match is queued (see LmMachine::finish_next).
+    // F_REPORT: src/charwise/iter.rs:345-366 with adv = L.ulen, the bytes of the char that led back to ROOT.
+    static DACH_HD void finish_next(LaneCw& L, const StdEnv& Ev, uint32_t& fl, const uint8_t* emu_lo) {
         const uint32_t end = L.self_pos;
         bool emit = true;
         bool snap = false;
-        if (L.it & IT_LAST_IS_INIT) {
-            L.self_pos += adv;
-            snap = true;
-            if (L.it & IT_SKIP_EMPTY) {
-                L.it &= ~IT_SKIP_EMPTY;
-                emit = false;
+        if (fl & F_REPORT) {
+            if (L.it & IT_LAST_IS_INIT) {
+                L.self_pos += L.ulen;
+                snap = true;
+                if (L.it & IT_SKIP_EMPTY) {
+                    L.it &= ~IT_SKIP_EMPTY;
+                    emit = false;
+                }
+            } else {
+                L.it |= IT_SKIP_EMPTY;
             }
-        } else {
-            L.it |= IT_SKIP_EMPTY;
         }
         if (emit) push(L, Ev, end, L.last);
+        L.fl = fl & ~(F_REPORT | F_FLUSH);
         restart(L, Ev, emu_lo);
         if (snap && L.self_pos < L.len) {
-            // `adv` belongs to the char that fell back to ROOT, not to the one at self_pos: never stop
+            // the advance belongs to the char that fell back to ROOT, not to the one at self_pos: never stop
             // inside a char ("Reference divergences") -- skip at most 3 continuation bytes
             const uint32_t u = peek4(L);
             uint32_t k = 0;
@@ -1220,6 +1255,7 @@ struct CwMachine {
                 seek(L, Ev, L.self_pos, emu_lo);
             }
         }
+        fl = L.fl;
     }
 
     // failure link of the state in L: the next probe, or ROOT at once if the link is DEAD
@@ -1247,15 +1283,15 @@ struct CwMachine {
                 } else {  // end-of-input rules (src/charwise/iter.rs:381-398), as in LmMachine
                     if (L.self_pos >= L.len) L.it &= ~IT_INIT;
                     if (L.it & IT_HAVE_LAST) {
-                        L.fl = fl;
                         if (L.self_pos < L.len && (L.it & IT_LAST_IS_INIT)) {
+                            L.fl = fl;  // the unit consumed is the char at self_pos
                             seek(L, Ev, L.self_pos, emu_lo);
-                            report(L, Ev, utf8_len(peek4(L) & 0xffu), emu_lo);
+                            fl = L.fl;
+                            L.ulen = utf8_len(peek4(L) & 0xffu);
+                            fl |= F_REPORT;
                         } else {
-                            push(L, Ev, L.self_pos, L.last);
-                            restart(L, Ev, emu_lo);
+                            fl |= F_FLUSH;
                         }
-                        fl = L.fl;
                     } else {
                         fl |= F_DONE;
                     }
@@ -1323,11 +1359,7 @@ struct CwMachine {
             L.cur = L.addr;
             if (LM) {
                 if (L.addr == D_ROOT) {
-                    if (L.it & IT_HAVE_LAST) {
-                        L.fl = fl;
-                        report(L, Ev, L.ulen, emu_lo);
-                        fl = L.fl;
-                    }
+                    if (L.it & IT_HAVE_LAST) fl |= F_REPORT;
                 } else if (L.nf & CF_OUT) {
                     L.last = L.addr;
                     L.it = (L.it | IT_HAVE_LAST) & ~IT_LAST_IS_INIT;
@@ -1344,6 +1376,8 @@ struct CwMachine {
                 }
             }
         }
+        // ---- phase 5 (leftmost): a next() call ends --------------------------------------------------------
+        if (LM && (fl & (F_REPORT | F_FLUSH))) finish_next(L, Ev, fl, emu_lo);
         L.fl = fl;
         return run;
     }
@@ -1377,7 +1411,7 @@ struct CwMachine {
         L.self_pos = 0;
         L.it = (LM && (Ev.root_flags & CF_OUT)) ? IT_INIT : 0u;
         E.begin((uint32_t)item);
-        restart(L, Ev, emu_lo);
+        restart(L, Ev, emu_lo, true);
         if (!LM && MODE != M_FIND && (Ev.root_flags & CF_OUT)) {  // ROOT's output list is pending at position 0
             QEntry e;
             e.end = 0;

@@ -104,7 +104,6 @@ static void run_machine(const ScanParams& P, const StdEnv& Ev0, const uint8_t* l
             }
             any_left = true;
             bool stop = false;
-            int idle_rounds = 0;
             while (!stop) {
                 for (int l = 0; l < 32; ++l) M::text_topup(w.L[l], w.Ev[l], lo);
                 bool waiting[32] = {false};
@@ -118,15 +117,8 @@ static void run_machine(const ScanParams& P, const StdEnv& Ev0, const uint8_t* l
                     if (!M::LAZY && need_service) stop = true;
                 }
                 if (M::LAZY) {  // mirrors the vote in k_scan_machine
-                    int n_wait = 0;
-                    bool any_full = false;
                     for (int l = 0; l < 32; ++l)
-                        if (waiting[l] && (w.L[l].fl & F_ACTIVE)) {
-                            ++n_wait;
-                            if (w.L[l].qn == (uint32_t)LANE_Q) any_full = true;
-                        }
-                    if (n_wait) ++idle_rounds;
-                    stop = any_full || n_wait >= 4 || idle_rounds >= 4;
+                        if (waiting[l] && (w.L[l].fl & F_ACTIVE)) stop = true;
                 }
             }
         }
