@@ -508,6 +508,7 @@ struct dach_dev {
     // (113 vs 116 GB/s, profiles/r1_cache_experiments.md); kept as an option (power of two).
     int64_t opt_hot_entries = 0;
     int64_t opt_profile_items = 2048;
+    int64_t opt_slice_ramp = 1;      // host path: small slices at the head and the tail of a batch
     int64_t opt_tail_seg = 0;        // cut only the last 2 x lanes haystacks of a large batch (measured: -2 %, off)
     int64_t opt_gather_ordered = 1;  // copy pool blocks in output order (sequential writes)
     int64_t opt_gather_u = 4;     // pooled blocks in flight per warp of k_gather (2, 4 or 8)
@@ -1069,9 +1070,20 @@ int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint6
         uint64_t total;
     };
     std::vector<Slice> slices;
+    // Slice sizes ramp up at the head of the batch and down at its tail (1/8, 1/4, 1/2, 1, ..., 1/2, 1/4,
+    // 1/8 of slice_bytes): nothing can be scanned before the first upload lands and nothing overlaps the
+    // last scan + download, so those two are kept short.
+    const uint64_t batch_end = offs[n];
     for (uint64_t i = 0; i < n;) {
         uint64_t j = i + 1;
-        const uint64_t lim = offs[i] + slice_bytes;
+        const uint64_t done = offs[i] - offs[0], left = batch_end - offs[i];
+        uint64_t want = slice_bytes;
+        const size_t k = slices.size();
+        if (d->opt_slice_ramp && k < 3) want = std::min(want, slice_bytes >> (3 - k));  // head: 1/8, 1/4, 1/2
+        if (d->opt_slice_ramp && left < 2 * slice_bytes) want = std::min(want, std::max<uint64_t>(left / 3, slice_bytes >> 3));  // tail: shrinking
+        (void)done;
+        want = std::max<uint64_t>(want, 1u << 20);
+        const uint64_t lim = offs[i] + want;
         if (j < n && offs[j + 1] <= lim) {  // largest j with offs[j] <= lim
             uint64_t lo = j, hi = n;
             while (lo < hi) {
@@ -1186,6 +1198,8 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
         d->opt_seg_len = value;
     else if (k == "dbg")
         d->opt_dbg = value;
+    else if (k == "slice_ramp")
+        d->opt_slice_ramp = value;
     else if (k == "tail_seg")
         d->opt_tail_seg = value;
     else if (k == "gather_ordered")
