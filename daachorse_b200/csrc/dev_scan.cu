@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1103,11 +1104,17 @@ int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint6
     // every slot's previous work must be finished before its buffers are reused
     bool overflow = false;
     uint64_t base = 0;
+    const bool trace = getenv("DACH_DEBUG") != nullptr;
+    double t_reuse = 0, t_scan = 0, t_final = 0, gpu_ms = 0;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
     auto issue_h2d = [&](size_t k) -> bool {
         Workspace& W = d->slot[k % dach_dev::kSlots];
         const Slice& s = slices[k];
         const uint64_t tb = offs[s.last] - offs[s.first], ns = s.last - s.first;
+        const double t0 = now();
         if (!cuda_ok(cudaStreamSynchronize(W.stream), "slot reuse")) return false;
+        t_reuse += now() - t0;
         if (!ensure(W.text, tb + 32) || !ensure(W.offs, (ns + 1) * 8) || !ensure(W.out_offs, (ns + 1) * 8)) return false;
         if (tb && !cuda_ok(cudaMemcpyAsync(W.text.p, text + offs[s.first], tb, cudaMemcpyHostToDevice, W.stream), "H2D text"))
             return false;
@@ -1130,6 +1137,7 @@ int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint6
         // device-side capacity of this slice: what is left of the caller's buffer, bounded by a
         // generous per-slice estimate that grows if a slice overflows it
         uint64_t cap = std::max<uint64_t>(std::max<uint64_t>(tb / 4, 4096), W.out.bytes > 16 ? (W.out.bytes - 16) / 12 : 0);
+        const double t_s0 = now();
         for (;;) {
             if (!ensure(W.out, cap * 12 + 16)) return DACH_CUDA_ERROR;
             uint64_t total = 0;
@@ -1143,6 +1151,8 @@ int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint6
             }
             break;
         }
+        t_scan += now() - t_s0;
+        gpu_ms += d->last_total_ms;
         if (rc != DACH_OK && rc != DACH_OUTPUT_OVERFLOW) return rc;
         if (base + s.total > out_cap) overflow = true;
         if (!overflow) {
@@ -1156,8 +1166,13 @@ int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint6
         }
         base += s.total;
     }
+    const double t_f0 = now();
     for (Workspace& w : d->slot)
         if (!cuda_ok(cudaStreamSynchronize(w.stream), "D2H")) return DACH_CUDA_ERROR;
+    t_final = now() - t_f0;
+    if (trace)
+        fprintf(stderr, "dach_scan_batch_host: %zu slices, %.2f ms total: waiting for slot reuse %.2f, in scan_locked %.2f, final D2H wait %.2f; kernels %.2f ms\n",
+                slices.size(), now() - t_begin, t_reuse, t_scan, t_final, gpu_ms);
     if (needed) *needed = base;
     if (overflow) {
         set_error("output capacity too small");
