@@ -17,7 +17,7 @@ SYMBOLS = [
     "dach_bytewise_build", "dach_charwise_build", "dach_pma_deserialize", "dach_pma_serialized_bytes",
     "dach_pma_serialize", "dach_pma_match_kind", "dach_pma_num_states", "dach_pma_heap_bytes",
     "dach_pma_num_elements", "dach_pma_is_charwise", "dach_pma_max_pattern_len", "dach_pma_free",
-    "dach_dev_upload", "dach_dev_free", "dach_dev_image_bytes", "dach_dev_scan_batch",
+    "dach_dev_upload", "dach_dev_free", "dach_dev_image_bytes", "dach_dev_scan_batch", "dach_dev_scan_stream",
     "dach_scan_batch_host", "dach_dev_kernel_launches", "dach_dev_last_scan_kernel_ms",
     "dach_dev_last_total_ms", "dach_dev_last_h2d_bytes", "dach_dev_last_d2h_bytes",
     "dach_dev_set_option", "dach_last_error", "dach_abi_version",
@@ -64,6 +64,9 @@ def load():
     L.dach_dev_scan_batch.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp,
                                       C.POINTER(C.c_uint64), vp]
     L.dach_dev_scan_batch.restype = C.c_int
+    L.dach_dev_scan_stream.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp, C.c_uint64, vp,
+                                       C.POINTER(C.c_uint64), vp]
+    L.dach_dev_scan_stream.restype = C.c_int
     L.dach_scan_batch_host.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, vp, C.c_uint64, vp,
                                        C.POINTER(C.c_uint64)]
     L.dach_scan_batch_host.restype = C.c_int

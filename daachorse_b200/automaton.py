@@ -309,6 +309,43 @@ class _Automaton:
             _check(rc)
             return BatchResult(out[: need.value], out_offs)
 
+    def scan_stream_device(self, mode, text, offs, state, pos=None, out=None, out_offs=None, stream=None):
+        """Chunks of streams -- the batch form of ``find_stepper()`` / ``find_overlapping_stepper()``
+        (src/bytewise.rs:627-729): haystack i is the next chunk of stream i.  ``state`` (CUDA int32/uint32,
+        n entries) holds each stream's state id and is updated in place; ``pos`` (optional, n entries) is
+        the stream position of each chunk's first byte and is added to the reported positions.  For every
+        byte: consume(byte), then matches().  Returns a BatchResult of device tensors."""
+        import torch
+
+        self._assert_mode(mode)
+        L = _lib.load()
+        dev = text.device.index if text.device.index is not None else torch.cuda.current_device()
+        d = self.device_handle(dev)
+        n = offs.numel() - 1
+        assert state.numel() == n and (pos is None or pos.numel() == n)
+        if out_offs is None:
+            out_offs = torch.empty(n + 1, dtype=torch.int64, device=text.device)
+        cap = out.shape[0] if out is not None else max(1024, int(text.numel() // 8))
+        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(text.device).cuda_stream)
+        state_in = state.clone()  # the call advances `state` even when the output overflows
+        while True:
+            if out is None or out.shape[0] < cap:
+                out = torch.empty((cap, 3), dtype=torch.int32, device=text.device)
+            need = C.c_uint64()
+            rc = L.dach_dev_scan_stream(d, mode, C.c_void_p(text.data_ptr()), C.c_void_p(offs.data_ptr()), n, text.numel(),
+                                        C.c_void_p(state.data_ptr()), C.c_void_p(pos.data_ptr()) if pos is not None else None,
+                                        C.c_void_p(out.data_ptr()), out.shape[0], C.c_void_p(out_offs.data_ptr()),
+                                        C.byref(need), st)
+            if rc == _lib.OUTPUT_OVERFLOW:
+                if int(need.value) <= cap:
+                    raise DaachorseError(rc, "overflow reported although capacity %d >= needed %d" % (cap, need.value))
+                cap = int(need.value)
+                out = None
+                state.copy_(state_in)
+                continue
+            _check(rc)
+            return BatchResult(out[: need.value], out_offs)
+
     def _batch(self, mode, haystacks):
         blob, offs = _pack(list(haystacks), self._charwise)
         return self.scan_batch_host(mode, blob, offs)

@@ -140,7 +140,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
         // ---- service phase (the warp is converged here) ----
         if (L.fl & F_ACTIVE) M::drain(L, Ev, P, E);
         if ((L.fl & (F_ACTIVE | F_DONE)) == (F_ACTIVE | F_DONE)) {
-            if (!PROFILE) E.finish(P);
+            if (!PROFILE) {
+                E.finish(P);
+                M::finish_item(L, P);
+            }
             L.fl = 0;
         }
         const bool need = !(L.fl & F_ACTIVE) && !exhausted;
@@ -366,6 +369,28 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const Scan
 }
 
 __global__ void k_zero_offsets(unsigned long long* out_offs) { out_offs[0] = 0; }
+
+// Stream chunks: positions are reported in stream coordinates -- add the position of the chunk's first
+// byte to start and end of every match of that chunk (haystack found by binary search in out_offs).
+__global__ void __launch_bounds__(256) k_add_base(const ScanCtrl* ctrl, const unsigned long long* out_offs, uint64_t n,
+                                                   unsigned long long out_cap, const uint32_t* pos_in, uint32_t* out_words) {
+    const unsigned long long total = out_offs[n];
+    if (ctrl->overflow || total > out_cap) return;
+    for (unsigned long long m = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; m < total;
+         m += (unsigned long long)gridDim.x * blockDim.x) {
+        uint64_t lo = 0, hi = n;  // largest h with out_offs[h] <= m
+        while (lo + 1 < hi) {
+            const uint64_t mid = (lo + hi) / 2;
+            if (out_offs[mid] <= m)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const uint32_t b = pos_in[lo];
+        out_words[m * 3 + 0] += b;
+        out_words[m * 3 + 1] += b;
+    }
+}
 
 // ---- segment table (intra-haystack chunking for find_overlapping / no_suffix) --------------------
 __global__ void __launch_bounds__(256) k_seg_count(const uint64_t* offs, uint64_t n, uint32_t seg_len, uint32_t seg_from,
@@ -692,7 +717,8 @@ int check_mode(const dach_dev* d, int mode) {
 // d_text + d_offs[i] addresses haystack i; text_end is one past the last text byte on the device;
 // text_bytes is the number of text bytes this call covers (sizing only).
 int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, const uint8_t* text_end, uint64_t text_bytes,
-                const uint64_t* d_offs, uint64_t n, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs, uint64_t* needed, cudaStream_t st) {
+                const uint64_t* d_offs, uint64_t n, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs, uint64_t* needed, cudaStream_t st,
+                uint32_t* d_state_io = nullptr, const uint32_t* d_pos_in = nullptr) {
     if (n > 0xfffffff0ull) {
         set_error("too many haystacks in one batch (max 2^32-16)");
         return DACH_INVALID_ARGUMENT;
@@ -717,10 +743,17 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     // StdMachine2 keeps ROOT's record in registers and probes it like any state: needs BASE(ROOT) != 0
     const bool std2 = v1 && !d->charwise && mode != M_LEFTMOST && d->opt_kernel >= 2 && d->root_base != 0 && d->opt_hot_entries <= 0;
 
+    if (d_state_io && !std2) {
+        set_error("stream chunks need the bytewise Standard lane machine (find / find_overlapping, at most 2^24 states, "
+                  "BASE(ROOT) != 0, no empty pattern for find)");
+        return DACH_INVALID_ARGUMENT;
+    }
+
     // Work items.  find_overlapping / no_suffix may cut haystacks into segments (exact with an
     // (L-1)-byte warm-up) so that small batches and long haystacks still
     // fill the machine; everything else works on whole haystacks.
-    bool seg = v1 && !d->charwise && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX) && d->opt_seg_len >= 0;
+    // (a chunk of a stream resumes in a given state: it stays one item)
+    bool seg = v1 && !d->charwise && !d_state_io && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX) && d->opt_seg_len >= 0;
     uint32_t seg_len = 0, seg_from = 0;
     uint64_t n_items_max = n;
     if (seg) {
@@ -787,6 +820,7 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     P.pool_blocks = pool_blocks;
     P.ctrl = static_cast<ScanCtrl*>(W.ctrl.p);
     P.dbg = (uint32_t)d->opt_dbg;
+    P.state_io = d_state_io;
 
     const size_t smem_budget = std::min<size_t>(d->smem_optin, 226 * 1024) / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
     size_t smem;
@@ -914,6 +948,10 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
         k_hay_offsets<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(seg_first, item_offs, n, offs64);
         d->launches += 1;
     }
+    if (d_pos_in) {
+        k_add_base<<<gather_grid, 256, 0, st>>>(P.ctrl, offs64, n, out_cap, d_pos_in, reinterpret_cast<uint32_t*>(d_out));
+        d->launches += 1;
+    }
     if (!cuda_ok(cudaGetLastError(), "kernel launch")) return DACH_CUDA_ERROR;
     cudaEventRecord(W.ev[2], st);
     cudaMemcpyAsync(&W.pinned->total, offs64 + n, 8, cudaMemcpyDeviceToHost, st);
@@ -1038,6 +1076,26 @@ int dach_dev_scan_batch(dach_dev* d, int mode, const uint8_t* d_text, const uint
     if (!g.ok) return DACH_CUDA_ERROR;
     return scan_locked(d, d->ws, mode, d_text, d_text + text_bytes, text_bytes, d_offs, n, d_out, out_cap, d_out_offs, needed,
                        static_cast<cudaStream_t>(stream));
+}
+
+int dach_dev_scan_stream(dach_dev* d, int mode, const uint8_t* d_text, const uint64_t* d_offs, uint64_t n, uint64_t text_bytes,
+                         uint32_t* d_state, const uint32_t* d_pos, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs,
+                         uint64_t* needed, void* stream) {
+    if (!d || !d_offs || !d_out_offs || !d_state || (out_cap && !d_out)) {
+        set_error("null argument");
+        return DACH_INVALID_ARGUMENT;
+    }
+    if (mode != DACH_FIND && mode != DACH_FIND_OVERLAPPING) {
+        set_error("stream chunks: mode must be DACH_FIND or DACH_FIND_OVERLAPPING (the crate's two steppers)");
+        return DACH_INVALID_ARGUMENT;
+    }
+    const int rc = check_mode(d, mode);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(d->mu);
+    DeviceGuard g(d->device);
+    if (!g.ok) return DACH_CUDA_ERROR;
+    return scan_locked(d, d->ws, mode, d_text, d_text + text_bytes, text_bytes, d_offs, n, d_out, out_cap, d_out_offs, needed,
+                       static_cast<cudaStream_t>(stream), d_state, d_pos);
 }
 
 int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint64_t* offs, uint64_t n,

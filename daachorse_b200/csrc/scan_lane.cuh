@@ -106,6 +106,8 @@ struct ScanParams {
     const uint32_t* item_beg;
     const unsigned long long* n_items_dev;
     uint32_t seg_len, warm;
+    uint32_t* state_io;  // stream chunks (dach_dev_scan_stream): state id per haystack, read at its start and
+                         // written at its end; nullptr for ordinary scans (every haystack starts in ROOT)
     uint32_t seg_from;  // haystacks below this index stay whole (one item each): only the tail of a batch is cut
     uint32_t dbg;  // experiment switches (bench --option dbg=): 1 = count matches but do not store them,
                    // 2 = text via ld.global.cs, 4 = text via ld.global.nc.L1::no_allocate
@@ -658,6 +660,7 @@ template <int MODE, bool PROFILE = false, bool HOT = false>
 struct StdMachine {
     static constexpr int TOPUP = TEXT_TOPUP;
     static constexpr bool LAZY = false;
+    static DACH_HD void finish_item(const LaneStd&, const ScanParams&) {}
     static DACH_HD const uint8_t* block_of(const LaneStd& L) {
         return reinterpret_cast<const uint8_t*>(((uintptr_t)L.hay + L.pos) & ~(uintptr_t)15);
     }
@@ -907,6 +910,7 @@ struct LaneLm : LaneStd {
 struct LmMachine {
     static constexpr int TOPUP = TEXT_TOPUP;
     static constexpr bool LAZY = true;
+    static DACH_HD void finish_item(const LaneLm&, const ScanParams&) {}
     using Std = StdMachine<M_LEFTMOST, false, false>;
 
     static DACH_HD void seek_full(LaneLm& L, const StdEnv& Ev, uint32_t pos, const uint8_t* emu_lo) {
@@ -1143,6 +1147,7 @@ template <int MODE>
 struct CwMachine {
     static constexpr int TOPUP = 4;
     static constexpr bool LAZY = true;
+    static DACH_HD void finish_item(const LaneCw&, const ScanParams&) {}
     static constexpr bool LM = MODE == M_LEFTMOST;
     using Std = StdMachine<M_OVERLAPPING, false, false>;
 
@@ -1509,7 +1514,10 @@ struct StdMachine2 {
             Ev.q[L.qn * Ev.q_stride] = e;
             ++L.qn;
             if (L.qn == (uint32_t)LANE_Q) fl |= S2_FULL;
-            if (MODE == M_FIND) to_root(L, Ev);  // every next() restarts at ROOT (src/bytewise/iter.rs:87)
+            if (MODE == M_FIND) {  // every next() restarts at ROOT (src/bytewise/iter.rs:87)
+                to_root(L, Ev);
+                L.addr = D_ROOT;
+            }
         }
     }
 
@@ -1581,6 +1589,11 @@ struct StdMachine2 {
         L.fl &= ~S2_FULL;
     }
 
+    // the item is complete (its last byte landed): hand the state on to the next chunk of the stream
+    static DACH_HD void finish_item(const Lane2& L, const ScanParams& P) {
+        if (P.state_io) P.state_io[L.item] = L.addr;
+    }
+
     static DACH_HD void begin_item(Lane2& L, const ScanParams& P, const StdEnv& Ev, Emitter& E, uint64_t item,
                                    const uint8_t* emu_lo) {
         uint64_t hay = item;
@@ -1616,6 +1629,20 @@ struct StdMachine2 {
         to_root(L, Ev);
         L.addr = D_ROOT;
         L.fl = F_ACTIVE;
+        if (P.state_io) {
+            // a chunk of a stream: resume in the state the previous chunk ended in (the stepper contract,
+            // src/bytewise/iter.rs:344-475); the outputs of that state were reported with the previous chunk
+            const uint32_t st = P.state_io[item];
+            if (st != D_ROOT && st < P.n_slots) {
+                const uint4 x = ld_u4(Ev.glob + st);
+                L.r0 = x.x;
+                L.nf = x.y;
+                L.r2 = x.z;
+                L.sig = x.w;
+                L.addr = st;
+            }
+            return;
+        }
         if (MODE != M_FIND && (Ev.root_flags & CF_OUT) && beg == 0) {
             QEntry e;
             e.end = 0;

@@ -78,7 +78,10 @@ static void run_machine(const ScanParams& P, const StdEnv& Ev0, const uint8_t* l
                 if (w.L[l].fl & F_ACTIVE) M::drain(w.L[l], w.Ev[l], P, w.E[l]);
             for (int l = 0; l < 32; ++l)
                 if ((w.L[l].fl & (F_ACTIVE | F_DONE)) == (F_ACTIVE | F_DONE)) {
-                    if (!PROFILE) w.E[l].finish(P);
+                    if (!PROFILE) {
+                        w.E[l].finish(P);
+                        M::finish_item(w.L[l], P);
+                    }
                     w.L[l].fl = 0;
                 }
             unsigned m = 0;
@@ -130,6 +133,9 @@ static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* 
     run_machine<StdMachine<MODE, PROFILE, HOT>, LaneStd, PROFILE>(P, Ev0, lo, n_warps);
 }
 
+static uint32_t* g_state_io = nullptr;
+static const uint32_t* g_pos_in = nullptr;
+
 extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int charwise, int mode,
                                    const uint8_t* text, const uint64_t* offs, uint64_t n, uint32_t hot_n,
                                    int kernel_version, uint32_t seg_len, uint32_t seg_from, uint32_t pool_blocks, dach_match* out, uint64_t out_cap, uint64_t* out_offs,
@@ -147,7 +153,9 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
 
     // segment table (mirrors k_seg_count / k_seg_fill in dev_scan.cu)
     const bool v1 = kernel_version >= 1 && !img.crec.empty() && !(mode == M_FIND && img.root_opos != 0);
-    const bool seg = v1 && !charwise && seg_len > 0 && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX);
+    if (g_state_io && !(v1 && !charwise && mode != M_LEFTMOST && kernel_version >= 2 && img.root_base != 0 && hot_n == 0))
+        return DACH_INVALID_ARGUMENT;  // as scan_locked() in dev_scan.cu
+    const bool seg = v1 && !charwise && !g_state_io && seg_len > 0 && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX);
     std::vector<uint32_t> item_hay, item_beg;
     std::vector<uint64_t> seg_first(n + 1, 0);
     uint64_t n_items = n;
@@ -195,6 +203,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     P.pool = pool.data();
     P.pool_blocks = pool_blocks;
     P.ctrl = &ctrl;
+    P.state_io = g_state_io;
     // "shared memory" copy of the hot records
     std::vector<uint32_t> hot(img.rec.begin(), img.rec.begin() + (size_t)hot_n * 4);
     hot.resize(hot.size() + 4);
@@ -296,5 +305,24 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
         uint32_t* dst = out_words + (item_offs[item] + first) * 3ull;
         for (uint32_t w = 0; w < nm * 3; ++w) dst[w] = blk[2 + w];
     }
+    if (g_pos_in)  // k_add_base
+        for (uint64_t h = 0; h < n; ++h)
+            for (uint64_t m = out_offs[h]; m < out_offs[h + 1]; ++m) {
+                out_words[m * 3 + 0] += g_pos_in[h];
+                out_words[m * 3 + 1] += g_pos_in[h];
+            }
     return DACH_OK;
+}
+
+// dach_dev_scan_stream: chunks of streams (state in/out per haystack, optional base position)
+extern "C" int emu_scan_stream_wire(const uint8_t* wire, size_t wire_len, int mode, const uint8_t* text, const uint64_t* offs,
+                                    uint64_t n, uint32_t* state_io, const uint32_t* pos_in, uint32_t pool_blocks, dach_match* out,
+                                    uint64_t out_cap, uint64_t* out_offs, uint64_t* needed) {
+    if (mode != M_FIND && mode != M_OVERLAPPING) return DACH_INVALID_ARGUMENT;
+    g_state_io = state_io;
+    g_pos_in = pos_in;
+    const int rc = emu_scan_batch_wire(wire, wire_len, 0, mode, text, offs, n, 0, 2, 0, 0, pool_blocks, out, out_cap, out_offs, needed);
+    g_state_io = nullptr;
+    g_pos_in = nullptr;
+    return rc;
 }

@@ -22,6 +22,9 @@ def lib():
                                              C.c_uint64, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
                                              C.c_void_p, C.POINTER(C.c_uint64)]
         _lib.emu_scan_batch_wire.restype = C.c_int
+        _lib.emu_scan_stream_wire.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                              C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+        _lib.emu_scan_stream_wire.restype = C.c_int
     return _lib
 
 
@@ -43,6 +46,31 @@ def scan(wire, charwise, mode, text, offs, hot_n=0, pool_blocks=None, out_cap=No
                                        offs.ctypes.data, n, hot_n, kernel, seg_len, seg_from, pb, out.ctypes.data, cap, oo.ctypes.data,
                                        C.byref(need))
         if rc == 6 and out_cap is None and pool_blocks is None:
+            cap = max(cap * 2, int(need.value))
+            continue
+        return rc, out[: need.value] if rc == 0 else None, oo, need.value
+
+
+def scan_stream(wire, mode, text, offs, state, pos=None, out_cap=1 << 16):
+    """dach_dev_scan_stream through the emulation: ``state`` (uint32, n) is updated in place.
+    Returns (rc, matches, out_offs, needed)."""
+    wire_a = np.frombuffer(wire, dtype=np.uint8)
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    n = len(offs) - 1
+    assert state.dtype == np.uint32 and len(state) == n
+    cap = int(out_cap)
+    while True:
+        saved = state.copy()
+        out = np.zeros(max(cap, 1), dtype=MATCH_DTYPE)
+        oo = np.zeros(n + 1, dtype=np.uint64)
+        need = C.c_uint64()
+        pad = text if text.size else np.zeros(16, dtype=np.uint8)
+        rc = lib().emu_scan_stream_wire(wire_a.ctypes.data, wire_a.size, mode, pad.ctypes.data, offs.ctypes.data, n,
+                                        state.ctypes.data, pos.ctypes.data if pos is not None else None, cap // 20 + n + 16,
+                                        out.ctypes.data, cap, oo.ctypes.data, C.byref(need))
+        if rc == 6:
+            state[:] = saved
             cap = max(cap * 2, int(need.value))
             continue
         return rc, out[: need.value] if rc == 0 else None, oo, need.value

@@ -194,6 +194,35 @@ class OraclePma:
             raise IndexError(idx)
         return tuple(v.value for v in vals)  # base, check, fail, output_pos
 
+    def state_after(self, data, find_mode=False, state=0):
+        """State id of the bytewise Standard automaton after consuming ``data`` from ``state`` with the
+        transition function of src/bytewise.rs:1063-1088 (pure Python over peek(); small inputs only).
+        ``find_mode``: FindStepper::consume, which returns to ROOT after a state with an output."""
+        n = self.num_elements()
+        cache = {}
+
+        def st(i):
+            if i not in cache:
+                cache[i] = self.peek(i)
+            return cache[i]
+
+        for c in bytes(data):
+            s = state
+            while True:
+                base = st(s)[0]
+                if base != 0:
+                    ci = base ^ c
+                    if ci < n and st(ci)[1] == c:
+                        s = ci
+                        break
+                if s == 0:
+                    break
+                s = st(s)[2]
+            state = s
+            if find_mode and st(state)[3] != 0:
+                state = 0
+        return state
+
     def scan(self, mode, haystack):
         """Returns a structured array of (start, end, value)."""
         L = lib()

@@ -172,3 +172,54 @@ def test_charwise_leftmost_empty_pattern_never_stops_inside_a_char():
     for kernel in (1, 0):
         rc, m, oo, need = E.scan(pma.serialize(), True, 3, text, offs, kernel=kernel)
         assert rc == 0 and triples(m) == triples(ref["matches"])
+
+
+def _stream_case(seed):
+    rng = np.random.default_rng(31000 + seed)
+    alpha = int(rng.integers(1, 5))
+    pats = rand_patterns(rng, int(rng.integers(1, 60)), alpha, int(rng.integers(1, 10)), allow_empty=(seed % 6 == 0))
+    n_streams = 9
+    streams = [bytes(rng.integers(97, 97 + alpha + (seed % 2), size=int(rng.integers(0, 500))).tolist()) for _ in range(n_streams)]
+    return pats, streams, rng
+
+
+@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("mode", [0, 1])
+def test_stream_chunks_equal_the_stepper_over_the_whole_stream(seed, mode):
+    """dach_dev_scan_stream (lane machine, emulated): streams cut into ragged chunks and scanned round
+    by round with the state carried over report exactly what the crate's stepper reports over the
+    whole stream (consume + matches(), tests/aho_corasick_crate_test.rs:422-520) -- minus the
+    matches() of the initial state at position 0, which no consume() produced."""
+    pats, streams, rng = _stream_case(seed)
+    pma = O.OraclePma.build(pats)
+    wire = pma.serialize()
+    orc_mode = O.FIND_STEPPER if mode == 0 else O.FIND_OVERLAPPING_STEPPER
+    want = []
+    for sbytes in streams:
+        t = np.frombuffer(sbytes, dtype=np.uint8)
+        ref = pma.scan_batch(orc_mode, t, np.array([0, len(sbytes)], dtype=np.uint64), want_matches=True)
+        want.append([x for x in triples(ref["matches"]) if x[1] != 0])
+    state = np.zeros(len(streams), dtype=np.uint32)
+    pos = np.zeros(len(streams), dtype=np.uint32)
+    got = [[] for _ in streams]
+    while any(int(pos[i]) < len(s) for i, s in enumerate(streams)):
+        chunks = []
+        for i, s in enumerate(streams):
+            k = int(rng.integers(0, 70))  # empty chunks included
+            chunks.append(s[int(pos[i]): int(pos[i]) + k])
+        offs = np.zeros(len(streams) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(c) for c in chunks])
+        text = np.frombuffer(b"".join(chunks), dtype=np.uint8)
+        rc, m, oo, need = E.scan_stream(wire, mode, text, offs, state, pos)
+        if mode == 0 and any(len(p) == 0 for p in pats):
+            assert rc == 1  # DACH_INVALID_ARGUMENT: find stepper with an empty pattern keeps the simple kernel
+            return
+        assert rc == 0
+        tr = triples(m)
+        for i in range(len(streams)):
+            got[i] += tr[int(oo[i]): int(oo[i + 1])]
+            pos[i] += len(chunks[i])
+    assert got == want
+    # the carried state is the reference's state id: one more round from a CPU-side walk agrees
+    for i, s in enumerate(streams):
+        assert int(state[i]) == pma.state_after(s, find_mode=(mode == 0))

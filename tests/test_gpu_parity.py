@@ -433,3 +433,54 @@ def test_config_c5_shape_long_records_reduced():
     assert pma.serialize() == opma.serialize()
     check_batch(pma, opma, D.FIND_OVERLAPPING, text, offs)
     check_batch(pma, opma, D.FIND_OVERLAPPING_NO_SUFFIX, text, offs)
+
+
+@pytest.mark.parametrize("mode", [D.FIND, D.FIND_OVERLAPPING])
+def test_stream_chunks_equal_the_stepper_over_the_whole_stream(mode):
+    """dach_dev_scan_stream: 3000 streams cut into ragged chunks, state and position carried from round
+    to round, against the crate's stepper driven over each whole stream (oracle), and the carried state
+    ids against a CPU walk of the reference transition function."""
+    import torch
+
+    cfg = S.config("C2")
+    ps = S.make_patterns(cfg, n=4000)
+    pool, b = S.make_pool(cfg, ps, 4 << 20)
+    rng = np.random.default_rng(21)
+    n = 3000
+    lens = rng.integers(0, 1200, size=n)
+    starts = rng.integers(0, len(pool) - 1300, size=n)
+    streams = [pool[int(s): int(s) + int(l)] for s, l in zip(starts, lens)]
+    pma = D.DoubleArrayAhoCorasick.new(ps.as_list())
+    opma = O.OraclePma.build_packed(ps.blob, ps.offs)
+    offs_all = np.zeros(n + 1, dtype=np.uint64)
+    offs_all[1:] = np.cumsum(lens)
+    whole = np.concatenate(streams) if n else np.zeros(0, np.uint8)
+    ref = opma.scan_batch(O.FIND_STEPPER if mode == D.FIND else O.FIND_OVERLAPPING_STEPPER, whole, offs_all, nthreads=16,
+                          want_matches=True)
+    state = torch.zeros(n, dtype=torch.int32, device="cuda")
+    pos = np.zeros(n, dtype=np.int64)
+    got = [[] for _ in range(n)]
+    while (pos < lens).any():
+        k = rng.integers(0, 400, size=n)
+        chunks = [st[int(p): int(p) + int(kk)] for st, p, kk in zip(streams, pos, k)]
+        offs = np.zeros(n + 1, dtype=np.int64)
+        offs[1:] = np.cumsum([len(c) for c in chunks])
+        text = np.concatenate(chunks) if offs[-1] else np.zeros(0, np.uint8)
+        t = torch.from_numpy(np.ascontiguousarray(text)).cuda() if len(text) else torch.zeros(16, dtype=torch.uint8, device="cuda")[:0]
+        r = pma.scan_stream_device(mode, t, torch.from_numpy(offs).cuda(), state, torch.from_numpy(pos.astype(np.int32)).cuda())
+        m = r.matches.cpu().numpy().view(np.uint32).reshape(-1, 3)
+        oo = r.offsets.cpu().numpy()
+        for i in range(n):
+            if oo[i + 1] > oo[i]:
+                got[i].append(m[oo[i]: oo[i + 1]])
+        pos += np.array([len(c) for c in chunks])
+    rm = ref["matches"]
+    ro = np.concatenate([[0], np.cumsum(ref["counts"])]).astype(np.int64)
+    for i in range(n):
+        want = np.stack([rm["start"][ro[i]: ro[i + 1]], rm["end"][ro[i]: ro[i + 1]], rm["value"][ro[i]: ro[i + 1]]], axis=1)
+        want = want[want[:, 1] != 0]  # matches() of the initial state, which no consume() produced
+        have = np.concatenate(got[i]) if got[i] else np.zeros((0, 3), np.uint32)
+        assert np.array_equal(have, want), i
+    st = state.cpu().numpy().view(np.uint32)
+    for i in range(0, n, 97):
+        assert int(st[i]) == opma.state_after(bytes(streams[i]), find_mode=(mode == D.FIND))
