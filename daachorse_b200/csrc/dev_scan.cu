@@ -36,6 +36,7 @@ namespace dach {
 // ------------------------------------------------------------------------------------------
 
 constexpr int kMaxThreads = 1024;
+constexpr int kMaxDevices = 64;
 constexpr uint32_t kRootBytes = 1024;  // 256 x u32 at the front of dynamic shared memory
 
 template <bool CHARWISE, int MODE>
@@ -573,11 +574,13 @@ struct DeviceGuard {
 
 template <bool CW, int MODE>
 cudaError_t launch_scan_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
-    static bool attr_done = false;  // per instantiation
-    if (!attr_done) {
+    static bool attr_done[kMaxDevices] = {};  // per instantiation and per device (the attribute is per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices || !attr_done[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_scan<CW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        if (dev >= 0 && dev < kMaxDevices) attr_done[dev] = true;
     }
     k_scan<CW, MODE><<<grid, threads, smem, st>>>(P);
     return cudaGetLastError();
@@ -591,11 +594,13 @@ struct L2Window {
 
 template <class M, class LANE, int MAXT, int MINB, bool PROFILE, bool HOT>
 cudaError_t launch_machine_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[kMaxDevices] = {};  // per instantiation and per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices || !attr_done[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_scan_machine<M, LANE, MAXT, MINB, PROFILE, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        if (dev >= 0 && dev < kMaxDevices) attr_done[dev] = true;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

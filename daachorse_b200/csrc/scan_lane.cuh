@@ -119,7 +119,18 @@ struct ScanParams {
 };
 
 DACH_HD uint4 ld_u4(const uint4* p) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(DACH_L2HINT)
+    // Experiment build (-DDACH_L2HINT, not the default library): automaton records carry an L2 evict_last
+    // policy so that the text and match-block streams do not push them out of L2 (the scan kernel reads
+    // 2.4 B of DRAM per scanned byte; 1.0 of it is the text).  To be measured: DESIGN.md section 8.
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+#elif defined(__CUDA_ARCH__)
     return __ldg(p);
 #else
     return *p;
