@@ -170,9 +170,13 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly one JSON line: while the job runs, file descriptor 1 points at stderr, so that
+    # anything a library writes to stdout (NCCL prints its version banner there under NCCL_DEBUG=VERSION)
+    # lands in the log; the descriptor is restored just before rank 0 prints the line.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     t_setup = time.time()
@@ -391,9 +395,11 @@ def main():
         "gpu_launches": int(launches2 - launches1), "launches_per_step": (launches2 - launches1) / args.steps,
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
