@@ -5,8 +5,17 @@
 // That harness is test infrastructure; the product only ever runs this code inside the
 // CUDA kernels of dev_scan.cu.
 //
+// Contents, in file order:
+//   - wide records + the lane-per-haystack loops (scan_standard / scan_leftmost): the reference's control
+//     flow as written; used by k_scan for automata above 2^24 slots, find_iter with an empty pattern, kernel=0
+//   - StdMachine   bytewise Standard lane machine, first cut (kernel=1; optional shared-memory state cache)
+//   - LmMachine    bytewise leftmost_find_iter on the lane machine
+//   - CwMachine    the four charwise iterators on the lane machine
+//   - StdMachine2  bytewise Standard lane machine, the default (three phases, ROOT in registers, text shift
+//                  register); also serves stream chunks (state carried in and out)
+//
 // Device image (built by dev_image.cpp from the validated host automaton):
-//   bytewise record  uint4 {base, efail, fbase, opos<<8 | check}           16 B / slot
+//   wide bytewise record  uint4 {base, efail, fbase, opos<<8 | check}      16 B / slot
 //       base    BASE of the slot (0 = no children)            src/bytewise.rs:1131-1137
 //       efail   failure target with child-less states skipped (a state without children can
 //               never satisfy a probe, src/bytewise.rs:1075-1083); kRoot ends the chase in the
@@ -15,7 +24,8 @@
 //       fbase   BASE of efail, so a missed probe is followed by the next probe without first
 //               loading the failure state's record; bit 31 (F2ROOT_BIT) says efail(efail) == ROOT,
 //               so a second miss goes straight to the dense root row (slots are < 2^31)
-//   charwise record  uint4 {base, check(parent), fail, output_pos}         src/charwise.rs:1096-1101
+//   wide charwise record  uint4 {base, check(parent), fail, output_pos}    src/charwise.rs:1096-1101
+//   compact records (lane machines, at most 2^24 slots): described above each machine
 //   output           uint4 {value, length, parent, 0}                      src/lib.rs:213-218
 //   root table       256 x u32                                             src/bytewise.rs:1040-1056
 #pragma once
