@@ -471,6 +471,8 @@ struct Workspace {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // host-batch slices only: device staging and the slice's stream
     DevBuf text, offs, out, out_offs;
+    void* offs_stage = nullptr;  // pinned staging of the slice's offsets (the caller's array may be pageable)
+    size_t offs_stage_bytes = 0;
     cudaStream_t stream = nullptr;
     bool init(bool with_stream) {
         if (!pinned && !cuda_ok(cudaMallocHost(reinterpret_cast<void**>(&pinned), sizeof(HostPinned)), "cudaMallocHost"))
@@ -491,6 +493,9 @@ struct Workspace {
             }
         if (pinned) cudaFreeHost(pinned);
         pinned = nullptr;
+        if (offs_stage) cudaFreeHost(offs_stage);
+        offs_stage = nullptr;
+        offs_stage_bytes = 0;
         for (int i = 0; i < 4; ++i)
             if (ev[i]) {
                 cudaEventDestroy(ev[i]);
@@ -1181,7 +1186,28 @@ int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint6
         if (!ensure(W.text, tb + 32) || !ensure(W.offs, (ns + 1) * 8) || !ensure(W.out_offs, (ns + 1) * 8)) return false;
         if (tb && !cuda_ok(cudaMemcpyAsync(W.text.p, text + offs[s.first], tb, cudaMemcpyHostToDevice, W.stream), "H2D text"))
             return false;
-        if (!cuda_ok(cudaMemcpyAsync(W.offs.p, offs + s.first, (ns + 1) * 8, cudaMemcpyHostToDevice, W.stream), "H2D offsets"))
+        // The offsets go through a pinned staging buffer: an async copy from pageable memory first waits
+        // for everything queued in the stream (here: the 64 MiB text upload) and blocks the host meanwhile,
+        // which starves the whole pipeline.  (The slot's stream was synchronised above, so the buffer is free.)
+        const void* offs_src = offs + s.first;
+        const size_t ob = (ns + 1) * 8;
+        if (W.offs_stage_bytes < ob) {
+            if (W.offs_stage) cudaFreeHost(W.offs_stage);
+            W.offs_stage = nullptr;
+            W.offs_stage_bytes = 0;
+            void* q = nullptr;
+            if (cudaMallocHost(&q, ob + ob / 2) == cudaSuccess) {
+                W.offs_stage = q;
+                W.offs_stage_bytes = ob + ob / 2;
+            } else {
+                cudaGetLastError();  // no staging: copy from the caller's memory directly
+            }
+        }
+        if (W.offs_stage) {
+            memcpy(W.offs_stage, offs_src, ob);
+            offs_src = W.offs_stage;
+        }
+        if (!cuda_ok(cudaMemcpyAsync(W.offs.p, offs_src, ob, cudaMemcpyHostToDevice, W.stream), "H2D offsets"))
             return false;
         d->last_h2d += tb + (ns + 1) * 8;
         return true;
