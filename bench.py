@@ -173,9 +173,13 @@ def main():
     # stdout carries exactly one JSON line: while the job runs, file descriptor 1 points at stderr, so that
     # anything a library writes to stdout (NCCL prints its version banner there under NCCL_DEBUG=VERSION)
     # lands in the log; the descriptor is restored just before rank 0 prints the line.
-    sys.stdout.flush()
-    saved_stdout = os.dup(1)
-    os.dup2(2, 1)
+    saved_stdout = None
+    try:
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+    except OSError:  # no usable stderr: leave stdout alone
+        saved_stdout = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -398,7 +402,8 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     sys.stdout.flush()
-    os.dup2(saved_stdout, 1)
+    if saved_stdout is not None:
+        os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
 
 
