@@ -19,7 +19,14 @@ struct HostImage {
     std::vector<uint32_t> root_table;  // 256 words (bytewise)
     std::vector<uint32_t> crec;        // compact records, 4 words per slot (bytewise Standard, <= 2^24 slots)
     std::vector<uint32_t> opos_tab;    // output_pos per slot (with crec)
-    uint32_t root_base = 0;
+    uint32_t root_base = 0;            // BASE of ROOT in the compact image
+    // hot-first relayout of the compact bytewise image (dev_image.cpp): the children of the hottest states
+    // occupy slots [0, hot_slots), every other slot s of the crate's numbering sits at s + hot_slots
+    uint32_t want_hot_slots = 65536;   // in: size of the hot region to build (rounded to 256; 0 = keep the crate's numbering)
+    uint32_t hot_slots = 0;            // out
+    uint32_t n_cslots = 0;             // slots of the compact image (n_slots + hot_slots)
+    std::vector<uint32_t> new_of_old;  // crate slot -> compact slot (stream chunks take and return crate state ids)
+    std::vector<uint32_t> old_of_new;  // compact slot -> crate slot
     std::vector<uint32_t> mapper;      // charwise code table
 };
 

@@ -101,36 +101,36 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-// M: the lane machine (StdMachine2 / StdMachine / LmMachine / CwMachine), LANE: its per-lane state
-template <class M, class LANE, int MAXT, int MINB, bool PROFILE, bool HOT>
+// M: the lane machine (StdMachine3 / StdMachine2 / StdMachine / LmMachine / CwMachine), LANE: its per-lane state.
+// HOT: the leading P.hot_entries compact records (the front of the hot region, dev_image.cpp) are staged in
+// shared memory by TMA bulk copies and served from there (StdMachine3).
+template <class M, class LANE, int MAXT, int MINB, bool HOT>
 __global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
-    // dynamic shared memory: [state cache hot_entries x 16 B (HOT only)][event queues LANE_Q x blockDim x 8 B]
+    // dynamic shared memory: [hot records hot_entries x 16 B (HOT only)][event queues LANE_Q x blockDim x 8 B]
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* s_hot = reinterpret_cast<uint4*>(smem_raw);
     QEntry* s_queue = reinterpret_cast<QEntry*>(smem_raw + (HOT ? (size_t)P.hot_entries * 16 : 0));
     __shared__ __align__(8) uint64_t s_bar;
     if (HOT) {
-        // one elected thread arms the mbarrier and lets the TMA engine stage the state cache
-        // (up to 128 KiB) while the other threads set up
+        // one elected thread arms the mbarrier and lets the TMA engine stage the hot records
+        // (up to 144 KiB) while the other threads set up
         if (threadIdx.x == 0) mbar_init(&s_bar, 1);
         __syncthreads();
         if (threadIdx.x == 0) {
             const uint32_t hot_bytes = P.hot_entries * 16u;
             mbar_expect_tx(&s_bar, hot_bytes);
             for (uint32_t off = 0; off < hot_bytes; off += 32768u)
-                tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_hot) + off, reinterpret_cast<const unsigned char*>(P.hot_tab) + off,
+                tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_hot) + off, reinterpret_cast<const unsigned char*>(P.crec) + off,
                              min(32768u, hot_bytes - off), &s_bar);
         }
     }
 
-    uint32_t hot_shift = 0;
-    while ((1u << hot_shift) < P.hot_entries) ++hot_shift;
-    const StdEnv Ev{P.crec,     s_hot,      HOT ? P.hot_entries - 1u : 0u, hot_shift, P.visits, P.opos_tab,
-                    P.text_end, P.root_base, P.root_opos ? CF_OUT : 0u, s_queue + threadIdx.x, blockDim.x, P.dbg, P.mapper, P.mapper_len, ld_u4(P.crec + D_ROOT)};
+    const StdEnv Ev{P.crec,      s_hot,       smem_u32(s_hot), HOT ? P.hot_entries : 0u, P.opos_tab, P.text_end, P.text_lo, P.root_base, P.root_opos ? CF_OUT : 0u,
+                    s_queue + threadIdx.x, blockDim.x, P.dbg, P.mapper, P.mapper_len, ld_u4(P.crec + D_ROOT)};
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     LANE L;
-    L.fl = 0;
+    L.fl = M::IDLE;
     L.qn = 0;
     Emitter E;
     E.begin(0);
@@ -141,11 +141,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
         // ---- service phase (the warp is converged here) ----
         if (L.fl & F_ACTIVE) M::drain(L, Ev, P, E);
         if ((L.fl & (F_ACTIVE | F_DONE)) == (F_ACTIVE | F_DONE)) {
-            if (!PROFILE) {
-                E.finish(P);
-                M::finish_item(L, P);
-            }
-            L.fl = 0;
+            E.finish(P);
+            M::finish_item(L, P);
+            L.fl = M::IDLE;
         }
         const bool need = !(L.fl & F_ACTIVE) && !exhausted;
         const unsigned m = __ballot_sync(FULL, need);
@@ -167,7 +165,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
         bool stop = false;
         while (!stop) {
             M::text_topup(L, Ev, nullptr);
-            if (M::LAZY) {  // look for lanes that need service once per top-up period, not per iteration
+            if (M::LEAN) {  // the lane's stop bit says it all; read once per top-up period
+#pragma unroll 1
+                for (int k = 0; k < M::TOPUP; ++k) (void)M::step(L, Ev, nullptr);
+                stop = __any_sync(FULL, (L.fl & (F_ACTIVE | M::IDLE)) == (F_ACTIVE | M::IDLE));
+            } else if (M::LAZY) {  // look for lanes that need service once per top-up period, not per iteration
                 // (batching further -- wait for four lanes or four periods -- idles ~3 lanes of 32 on
                 // 1 KiB haystacks and lost 6-9 % on the leftmost configs: measured, dropped)
                 bool waiting = false;
@@ -189,31 +191,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
             }
         }
     }
-}
-
-// ---- state cache construction from the profiling counters -------------------------------------
-// best[bin] = max over slots of that bin of (visits << 32 | slot)
-__global__ void __launch_bounds__(256) k_hot_pick(const uint32_t* visits, uint32_t n_slots, uint32_t mask,
-                                                   unsigned long long* best) {
-    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
-        const uint32_t v = visits[s];
-        if (v) atomicMax(best + (s & mask), ((unsigned long long)v << 32) | s);
-    }
-}
-__global__ void __launch_bounds__(256) k_hot_fill(const unsigned long long* best, const uint4* crec, uint32_t entries,
-                                                   uint32_t shift, uint4* tab) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= entries) return;
-    const unsigned long long v = best[b];
-    uint4 e;
-    if (v) {
-        const uint32_t slot = (uint32_t)v;
-        e = hot_entry(crec[slot], slot >> shift);
-    } else {
-        e.x = e.y = e.z = e.w = 0;
-        e = hot_entry(e, HOT_TAG_INVALID);
-    }
-    tab[b] = e;
 }
 
 // ---- exclusive scan of counts (u32) into offsets (u64) -----------------------------------
@@ -522,6 +499,9 @@ struct dach_dev {
     uint32_t* d_root = nullptr;
     uint4* d_crec = nullptr;
     uint32_t* d_opos = nullptr;
+    uint32_t* d_id_in = nullptr;   // crate slot -> compact slot (stream chunks)
+    uint32_t* d_id_out = nullptr;  // compact slot -> crate slot
+    uint32_t hot_slots = 0;        // size of the hot region of the compact image
     uint32_t root_base = 0;
     uint32_t* d_mapper = nullptr;
     void* image_base = nullptr;
@@ -532,14 +512,9 @@ struct dach_dev {
     static constexpr int kSlots = 4;
     Workspace slot[kSlots];  // dach_scan_batch_host: slices in flight (H2D of k+1 and k+2 | scan of k | D2H of k-1)
     int64_t opt_slice_mib = 64;
-    // profile-guided shared-memory state cache (lane-machine kernels)
-    DevBuf hot_tab, visits, best;
-    bool hot_ready = false;
-    uint32_t hot_tab_entries = 0;
-    // Off by default: on the C3 workload L1 alone serves the hot states as well as this cache does
-    // (113 vs 116 GB/s, profiles/r1_cache_experiments.md); kept as an option (power of two).
-    int64_t opt_hot_entries = 0;
-    int64_t opt_profile_items = 2048;
+    // Records of the hot region staged in shared memory by StdMachine3: -1 = as many as fit next to the
+    // event queues (the region is laid out hottest first, so any prefix is the best set of its size), 0 = none
+    int64_t opt_hot_entries = -1;
     int64_t opt_slice_ramp = 1;      // host path: small slices at the head and the tail of a batch
     int64_t opt_tail_seg = 0;        // cut only the last 2 x lanes haystacks of a large batch (measured: -2 %, off)
     int64_t opt_gather_ordered = 1;  // copy pool blocks in output order (sequential writes)
@@ -555,8 +530,8 @@ struct dach_dev {
     int64_t opt_threads = 1024;
     int64_t opt_ctas_per_sm = 1;
     int64_t opt_l2_persist = 1;  // 1: access-policy window over the image during the scan kernel
-    int64_t opt_kernel = 2;  // 2: lane machines, StdMachine2 for the bytewise Standard iterators; 1: StdMachine instead;
-                             // 0: always the lane-per-haystack kernels
+    int64_t opt_kernel = 3;  // 3: lane machines, StdMachine3 for the bytewise Standard iterators; 2: StdMachine2 instead;
+                             // 1: StdMachine instead; 0: always the lane-per-haystack kernels
     // stats
     uint64_t launches = 0;
     double last_scan_ms = 0, last_total_ms = 0;
@@ -597,13 +572,13 @@ struct L2Window {
     float hit_ratio = 1.0f;
 };
 
-template <class M, class LANE, int MAXT, int MINB, bool PROFILE, bool HOT>
+template <class M, class LANE, int MAXT, int MINB, bool HOT>
 cudaError_t launch_machine_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
     static bool attr_done[kMaxDevices] = {};  // per instantiation and per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= kMaxDevices || !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_scan_machine<M, LANE, MAXT, MINB, PROFILE, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_scan_machine<M, LANE, MAXT, MINB, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < kMaxDevices) attr_done[dev] = true;
     }
@@ -625,75 +600,48 @@ cudaError_t launch_machine_t(const ScanParams& P, int grid, int threads, size_t 
         cfg.attrs = at;
         cfg.numAttrs = 1;
     }
-    return cudaLaunchKernelEx(&cfg, k_scan_machine<M, LANE, MAXT, MINB, PROFILE, HOT>, P);
+    return cudaLaunchKernelEx(&cfg, k_scan_machine<M, LANE, MAXT, MINB, HOT>, P);
 }
 
-template <int MODE, int MAXT, int MINB, bool PROFILE, bool HOT>
-cudaError_t launch_std_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
-    return launch_machine_t<StdMachine<MODE, PROFILE, HOT>, LaneStd, MAXT, MINB, PROFILE, HOT>(P, grid, threads, smem, st, w);
-}
-
-cudaError_t launch_std2(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w,
-                        bool dense) {
-    if (dense) {  // two CTAs of up to 768 threads per SM (40 registers)
-        switch (mode) {
-            case M_FIND: return launch_machine_t<StdMachine2<M_FIND>, Lane2, 768, 2, false, false>(P, grid, threads, smem, st, w);
-            case M_NO_SUFFIX: return launch_machine_t<StdMachine2<M_NO_SUFFIX>, Lane2, 768, 2, false, false>(P, grid, threads, smem, st, w);
-            default: return launch_machine_t<StdMachine2<M_OVERLAPPING>, Lane2, 768, 2, false, false>(P, grid, threads, smem, st, w);
-        }
-    }
+template <template <int> class M, class LANE, int MAXT, int MINB, bool HOT>
+cudaError_t launch_std_modes(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
     switch (mode) {
-        case M_FIND: return launch_machine_t<StdMachine2<M_FIND>, Lane2, 1024, 1, false, false>(P, grid, threads, smem, st, w);
-        case M_NO_SUFFIX: return launch_machine_t<StdMachine2<M_NO_SUFFIX>, Lane2, 1024, 1, false, false>(P, grid, threads, smem, st, w);
-        default: return launch_machine_t<StdMachine2<M_OVERLAPPING>, Lane2, 1024, 1, false, false>(P, grid, threads, smem, st, w);
+        case M_FIND: return launch_machine_t<M<M_FIND>, LANE, MAXT, MINB, HOT>(P, grid, threads, smem, st, w);
+        case M_NO_SUFFIX: return launch_machine_t<M<M_NO_SUFFIX>, LANE, MAXT, MINB, HOT>(P, grid, threads, smem, st, w);
+        case M_OVERLAPPING: return launch_machine_t<M<M_OVERLAPPING>, LANE, MAXT, MINB, HOT>(P, grid, threads, smem, st, w);
     }
+    return cudaErrorInvalidValue;
+}
+
+// bytewise Standard iterators: which = 3 StdMachine3 (hot records in shared memory if P.hot_entries), 2 StdMachine2,
+// 1 StdMachine; dense = two CTAs of up to 768 threads per SM (40 registers) instead of one of 1024
+cudaError_t launch_std(int which, int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w,
+                       bool dense) {
+    if (which >= 3) {
+        if (P.hot_entries)
+            return dense ? launch_std_modes<StdMachine3, Lane3, 768, 2, true>(mode, P, grid, threads, smem, st, w)
+                         : launch_std_modes<StdMachine3, Lane3, 1024, 1, true>(mode, P, grid, threads, smem, st, w);
+        return dense ? launch_std_modes<StdMachine3, Lane3, 768, 2, false>(mode, P, grid, threads, smem, st, w)
+                     : launch_std_modes<StdMachine3, Lane3, 1024, 1, false>(mode, P, grid, threads, smem, st, w);
+    }
+    if (which == 2)
+        return dense ? launch_std_modes<StdMachine2, Lane2, 768, 2, false>(mode, P, grid, threads, smem, st, w)
+                     : launch_std_modes<StdMachine2, Lane2, 1024, 1, false>(mode, P, grid, threads, smem, st, w);
+    return dense ? launch_std_modes<StdMachine, LaneStd, 768, 2, false>(mode, P, grid, threads, smem, st, w)
+                 : launch_std_modes<StdMachine, LaneStd, 1024, 1, false>(mode, P, grid, threads, smem, st, w);
 }
 
 cudaError_t launch_cw(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
     switch (mode) {
-        case M_FIND: return launch_machine_t<CwMachine<M_FIND>, LaneCw, 1024, 1, false, false>(P, grid, threads, smem, st, w);
-        case M_OVERLAPPING: return launch_machine_t<CwMachine<M_OVERLAPPING>, LaneCw, 1024, 1, false, false>(P, grid, threads, smem, st, w);
-        case M_NO_SUFFIX: return launch_machine_t<CwMachine<M_NO_SUFFIX>, LaneCw, 1024, 1, false, false>(P, grid, threads, smem, st, w);
-        default: return launch_machine_t<CwMachine<M_LEFTMOST>, LaneCw, 1024, 1, false, false>(P, grid, threads, smem, st, w);
+        case M_FIND: return launch_machine_t<CwMachine<M_FIND>, LaneCw, 1024, 1, false>(P, grid, threads, smem, st, w);
+        case M_OVERLAPPING: return launch_machine_t<CwMachine<M_OVERLAPPING>, LaneCw, 1024, 1, false>(P, grid, threads, smem, st, w);
+        case M_NO_SUFFIX: return launch_machine_t<CwMachine<M_NO_SUFFIX>, LaneCw, 1024, 1, false>(P, grid, threads, smem, st, w);
+        default: return launch_machine_t<CwMachine<M_LEFTMOST>, LaneCw, 1024, 1, false>(P, grid, threads, smem, st, w);
     }
 }
 
 cudaError_t launch_lm(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
-    return launch_machine_t<LmMachine, LaneLm, 1024, 1, false, false>(P, grid, threads, smem, st, w);
-}
-
-cudaError_t launch_std(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w,
-                       bool dense_hint, bool profile) {
-    // two register budgets: 1024 threads x 1 CTA/SM (64 regs) or up to 768 threads x 2 CTAs/SM (42 regs)
-    const bool dense = threads <= 768 && (grid % 2 == 0) && dense_hint;
-    const bool hot = P.hot_entries != 0;
-    if (profile) {
-        switch (mode) {
-            case M_FIND: return launch_std_t<M_FIND, 1024, 1, true, false>(P, grid, threads, smem, st, w);
-            case M_OVERLAPPING: return launch_std_t<M_OVERLAPPING, 1024, 1, true, false>(P, grid, threads, smem, st, w);
-            case M_NO_SUFFIX: return launch_std_t<M_NO_SUFFIX, 1024, 1, true, false>(P, grid, threads, smem, st, w);
-        }
-        return cudaErrorInvalidValue;
-    }
-#define DACH_CASE(M, D, H)                                                                  \
-    case ((M)*4 + (D)*2 + (H)):                                                               \
-        return launch_std_t<M, (D) ? 768 : 1024, (D) ? 2 : 1, false, (H) != 0>(P, grid, threads, smem, st, w);
-    switch (mode * 4 + (dense ? 2 : 0) + (hot ? 1 : 0)) {
-        DACH_CASE(M_FIND, 0, 0)
-        DACH_CASE(M_FIND, 0, 1)
-        DACH_CASE(M_FIND, 1, 0)
-        DACH_CASE(M_FIND, 1, 1)
-        DACH_CASE(M_OVERLAPPING, 0, 0)
-        DACH_CASE(M_OVERLAPPING, 0, 1)
-        DACH_CASE(M_OVERLAPPING, 1, 0)
-        DACH_CASE(M_OVERLAPPING, 1, 1)
-        DACH_CASE(M_NO_SUFFIX, 0, 0)
-        DACH_CASE(M_NO_SUFFIX, 0, 1)
-        DACH_CASE(M_NO_SUFFIX, 1, 0)
-        DACH_CASE(M_NO_SUFFIX, 1, 1)
-    }
-#undef DACH_CASE
-    return cudaErrorInvalidValue;
+    return launch_machine_t<LmMachine, LaneLm, 1024, 1, false>(P, grid, threads, smem, st, w);
 }
 
 cudaError_t launch_scan(bool cw, int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
@@ -726,7 +674,7 @@ int check_mode(const dach_dev* d, int mode) {
 // the device-side pipeline; caller holds d->mu and has set the device
 // d_text + d_offs[i] addresses haystack i; text_end is one past the last text byte on the device;
 // text_bytes is the number of text bytes this call covers (sizing only).
-int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, const uint8_t* text_end, uint64_t text_bytes,
+int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, const uint8_t* text_lo, const uint8_t* text_end, uint64_t text_bytes,
                 const uint64_t* d_offs, uint64_t n, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs, uint64_t* needed, cudaStream_t st,
                 uint32_t* d_state_io = nullptr, const uint32_t* d_pos_in = nullptr) {
     if (n > 0xfffffff0ull) {
@@ -750,8 +698,9 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     const bool v1 = d->opt_kernel >= 1 && d->d_crec && !(mode == M_FIND && d->root_opos != 0);
     const bool cw_machine = v1 && d->charwise;
     const bool lm_machine = v1 && !d->charwise && mode == M_LEFTMOST;
-    // StdMachine2 keeps ROOT's record in registers and probes it like any state: needs BASE(ROOT) != 0
-    const bool std2 = v1 && !d->charwise && mode != M_LEFTMOST && d->opt_kernel >= 2 && d->root_base != 0 && d->opt_hot_entries <= 0;
+    // StdMachine2 / StdMachine3 keep ROOT's record in registers and probe it like any state: needs BASE(ROOT) != 0
+    const bool std2 = v1 && !d->charwise && mode != M_LEFTMOST && d->opt_kernel >= 2 && d->root_base != 0;
+    const bool std3 = std2 && d->opt_kernel >= 3;
 
     if (d_state_io && !std2) {
         set_error("stream chunks need the bytewise Standard lane machine (find / find_overlapping, at most 2^24 states, "
@@ -820,8 +769,11 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     P.mapper = d->d_mapper;
     P.mapper_len = d->mapper_len;
     P.n_slots = d->n_slots;
+    P.id_in = d->d_id_in;
+    P.id_out = d->d_id_out;
     P.root_opos = d->root_opos;
     P.text = d_text;
+    P.text_lo = text_lo;
     P.text_end = text_end;
     P.offs = d_offs;
     P.n_items = n;
@@ -836,15 +788,18 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     size_t smem;
     uint32_t hot_entries = 0;
     if (v1) {
-        const size_t fixed = (size_t)LANE_Q * threads * sizeof(QEntry) + 256;
-        // largest power of two that fits next to the root row and the queues
-        uint64_t want = (d->opt_hot_entries > 0 && !lm_machine && !cw_machine) ? (uint64_t)d->opt_hot_entries : 0;
-        while (want && fixed + want * 16 > smem_budget) want >>= 1;
-        while (want & (want - 1)) want &= want - 1;
-        if (want && (uint64_t)d->n_slots > want * (uint64_t)HOT_TAG_INVALID) want = 0;  // tag would not fit
+        const size_t queues = (size_t)LANE_Q * threads * sizeof(QEntry);
+        // StdMachine3: as much of the hot region as fits next to the queues (whole 256-slot blocks)
+        uint64_t want = 0;
+        if (std3 && d->opt_hot_entries != 0 && smem_budget > queues + 512) {
+            want = std::min<uint64_t>(d->hot_slots, (smem_budget - queues - 512) / 16);
+            if (d->opt_hot_entries > 0) want = std::min<uint64_t>(want, (uint64_t)d->opt_hot_entries);
+            want &= ~uint64_t(255);
+        }
         hot_entries = (uint32_t)want;
-        smem = (size_t)hot_entries * 16 + (size_t)LANE_Q * threads * sizeof(QEntry);
+        smem = (size_t)hot_entries * 16 + queues;
         P.hot_n = 0;
+        P.hot_entries = hot_entries;
     } else {
         uint64_t hot = smem_budget > kRootBytes ? (smem_budget - kRootBytes) / 16 : 0;
         if (d->opt_hot_records >= 0) hot = std::min<uint64_t>(hot, (uint64_t)d->opt_hot_records);
@@ -879,37 +834,6 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
         P.seg_from = seg_from;
         P.warm = d->max_pattern_len ? d->max_pattern_len - 1 : 0;
     }
-    if (v1 && hot_entries) {
-        if (!ensure(d->hot_tab, (size_t)hot_entries * 16)) return DACH_CUDA_ERROR;
-        if (!d->hot_ready || d->hot_tab_entries != hot_entries) {
-            // Profiling pass: walk a sample of the batch counting landings per slot, then keep, for
-            // every cache bin, the record of its most visited slot.
-            if (!ensure(d->visits, (size_t)d->n_slots * 4) || !ensure(d->best, (size_t)hot_entries * 8)) return DACH_CUDA_ERROR;
-            cudaMemsetAsync(d->visits.p, 0, (size_t)d->n_slots * 4, st);
-            cudaMemsetAsync(d->best.p, 0, (size_t)hot_entries * 8, st);
-            ScanParams Q = P;
-            Q.item_hay = nullptr;
-            Q.item_beg = nullptr;
-            Q.n_items_dev = nullptr;
-            Q.n_items = std::min<uint64_t>(n, (uint64_t)std::max<int64_t>(d->opt_profile_items, 1));
-            Q.hot_entries = 0;
-            Q.hot_tab = nullptr;
-            Q.visits = static_cast<uint32_t*>(d->visits.p);
-            const size_t psmem = (size_t)LANE_Q * threads * sizeof(QEntry);
-            if (!cuda_ok(launch_std(mode, Q, grid, threads, psmem, st, L2Window(), false, true), "profile launch")) return DACH_CUDA_ERROR;
-            uint32_t shift = 0;
-            while ((1u << shift) < hot_entries) ++shift;
-            k_hot_pick<<<d->sm_count * 4, 256, 0, st>>>(Q.visits, d->n_slots, hot_entries - 1, static_cast<unsigned long long*>(d->best.p));
-            k_hot_fill<<<(hot_entries + 255) / 256, 256, 0, st>>>(static_cast<const unsigned long long*>(d->best.p), d->d_crec, hot_entries,
-                                                               shift, static_cast<uint4*>(d->hot_tab.p));
-            cudaMemsetAsync(W.ctrl.p, 0, sizeof(ScanCtrl), st);  // the pass consumed the item counter
-            d->launches += 3;
-            d->hot_ready = true;
-            d->hot_tab_entries = hot_entries;
-        }
-        P.hot_tab = static_cast<const uint4*>(d->hot_tab.p);
-        P.hot_entries = hot_entries;
-    }
     L2Window win;
     if (d->opt_l2_persist && d->l2_persist > 0 && v1) {
         // the lane-machine kernels touch the compact records, the opos table and the outputs
@@ -920,8 +844,8 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     cudaEventRecord(W.ev[3], st);
     if (!cuda_ok(cw_machine   ? launch_cw(mode, P, grid, std::min(threads, 1024), smem, st, win)
                  : lm_machine ? launch_lm(P, grid, std::min(threads, 1024), smem, st, win)
-                 : std2       ? launch_std2(mode, P, grid, threads, smem, st, win, ctas_per_sm >= 2 && threads <= 768)
-                 : v1       ? launch_std(mode, P, grid, threads, smem, st, win, ctas_per_sm >= 2, false)
+                 : v1         ? launch_std(std3 ? 3 : std2 ? 2 : 1, mode, P, grid, threads, smem, st, win,
+                                           ctas_per_sm >= 2 && threads <= 768 && grid % 2 == 0)
                             : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
                  "k_scan launch"))
         return DACH_CUDA_ERROR;
@@ -1019,16 +943,18 @@ int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
     d->smem_optin = prop.sharedMemPerBlockOptin;
     // one allocation for the whole image (records | outputs | root rows | mapper), 256-byte aligned
     // parts, so that a single L2 access-policy window can cover it
-    const std::vector<uint32_t>* parts[6] = {&img.rec, &img.outputs, &img.root_table, &img.mapper, &img.crec, &img.opos_tab};
-    size_t part_off[6], total = 0;
-    for (int i = 0; i < 6; ++i) {
+    constexpr int kParts = 8;
+    const std::vector<uint32_t>* parts[kParts] = {&img.rec, &img.outputs, &img.root_table, &img.mapper, &img.crec, &img.opos_tab,
+                                                   &img.new_of_old, &img.old_of_new};
+    size_t part_off[kParts], total = 0;
+    for (int i = 0; i < kParts; ++i) {
         part_off[i] = total;
         total += (std::max<size_t>(parts[i]->size() * 4, 16) + 511) & ~size_t(511);
         d->image_bytes += parts[i]->size() * 4;
     }
     bool ok = cuda_ok(cudaMalloc(&d->image_base, total), "cudaMalloc image");
     d->image_alloc = total;
-    for (int i = 0; ok && i < 6; ++i)
+    for (int i = 0; ok && i < kParts; ++i)
         if (!parts[i]->empty())
             ok = cuda_ok(cudaMemcpy(static_cast<char*>(d->image_base) + part_off[i], parts[i]->data(), parts[i]->size() * 4,
                                     cudaMemcpyHostToDevice),
@@ -1042,6 +968,11 @@ int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
         if (!img.crec.empty()) {
             d->d_crec = reinterpret_cast<uint4*>(b + part_off[4]);
             d->d_opos = reinterpret_cast<uint32_t*>(b + part_off[5]);
+            if (img.hot_slots) {  // the compact image is renumbered: stream chunks translate state ids
+                d->d_id_in = reinterpret_cast<uint32_t*>(b + part_off[6]);
+                d->d_id_out = reinterpret_cast<uint32_t*>(b + part_off[7]);
+            }
+            d->hot_slots = img.hot_slots;
         }
         d->root_base = img.root_base;
         // let the automaton persist in L2 while text and match streams pass through it
@@ -1065,8 +996,6 @@ void dach_dev_free(dach_dev* d) {
     cudaFree(d->image_base);
     d->ws.release();
     for (Workspace& w : d->slot) w.release();
-    for (DevBuf* b : {&d->hot_tab, &d->visits, &d->best})
-        if (b->p) cudaFree(b->p);
     delete d;
 }
 
@@ -1084,7 +1013,7 @@ int dach_dev_scan_batch(dach_dev* d, int mode, const uint8_t* d_text, const uint
     std::lock_guard<std::mutex> lk(d->mu);
     DeviceGuard g(d->device);
     if (!g.ok) return DACH_CUDA_ERROR;
-    return scan_locked(d, d->ws, mode, d_text, d_text + text_bytes, text_bytes, d_offs, n, d_out, out_cap, d_out_offs, needed,
+    return scan_locked(d, d->ws, mode, d_text, d_text, d_text + text_bytes, text_bytes, d_offs, n, d_out, out_cap, d_out_offs, needed,
                        static_cast<cudaStream_t>(stream));
 }
 
@@ -1104,7 +1033,7 @@ int dach_dev_scan_stream(dach_dev* d, int mode, const uint8_t* d_text, const uin
     std::lock_guard<std::mutex> lk(d->mu);
     DeviceGuard g(d->device);
     if (!g.ok) return DACH_CUDA_ERROR;
-    return scan_locked(d, d->ws, mode, d_text, d_text + text_bytes, text_bytes, d_offs, n, d_out, out_cap, d_out_offs, needed,
+    return scan_locked(d, d->ws, mode, d_text, d_text, d_text + text_bytes, text_bytes, d_offs, n, d_out, out_cap, d_out_offs, needed,
                        static_cast<cudaStream_t>(stream), d_state, d_pos);
 }
 
@@ -1231,7 +1160,7 @@ int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint6
             if (!ensure(W.out, cap * 12 + 16)) return DACH_CUDA_ERROR;
             uint64_t total = 0;
             const uint8_t* d_text = static_cast<const uint8_t*>(W.text.p) - offs[s.first];
-            rc = scan_locked(d, W, mode, d_text, static_cast<const uint8_t*>(W.text.p) + tb, tb, static_cast<const uint64_t*>(W.offs.p), ns,
+            rc = scan_locked(d, W, mode, d_text, static_cast<const uint8_t*>(W.text.p), static_cast<const uint8_t*>(W.text.p) + tb, tb, static_cast<const uint64_t*>(W.offs.p), ns,
                              static_cast<dach_match*>(W.out.p), cap, static_cast<uint64_t*>(W.out_offs.p), &total, W.stream);
             s.total = total;
             if (rc == DACH_OUTPUT_OVERFLOW && total > cap) {
@@ -1312,14 +1241,8 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
         d->opt_gather_u = value;
     else if (k == "reserve_sms")
         d->opt_reserve_sms = value;
-    else if (k == "hot_entries") {
+    else if (k == "hot_entries")
         d->opt_hot_entries = value;
-        d->hot_ready = false;
-    } else if (k == "profile_items") {
-        d->opt_profile_items = value;
-        d->hot_ready = false;
-    } else if (k == "reprofile")
-        d->hot_ready = false;
     else {
         set_error("unknown option " + k);
         return DACH_INVALID_ARGUMENT;

@@ -95,17 +95,18 @@ struct ScanParams {
     const uint4* crec;           // compact records (lane-machine kernels), nullptr if > 2^24 slots
     const uint32_t* opos_tab;    // output_pos per slot (lane-machine kernels)
     uint32_t root_base;          // BASE of ROOT
-    const uint4* hot_tab;        // state cache image (global), hot_entries records; staged into shared memory
-    uint32_t hot_entries;        // power of two, 0 = none
-    uint32_t* visits;            // per-slot landing counters (profiling pass)
+    uint32_t hot_entries;        // leading compact records staged in shared memory (StdMachine3), 0 = none
+    const uint32_t* id_in;       // stream chunks: crate state id -> compact slot (nullptr: identity)
+    const uint32_t* id_out;      // stream chunks: compact slot -> crate state id
     const uint32_t* mapper;
     uint32_t mapper_len;
-    uint32_t n_slots;
+    uint32_t n_slots;    // slots in the crate's numbering
     uint32_t root_opos;  // output_pos of ROOT (empty pattern), 0 = none
     uint32_t hot_n;      // leading records staged in shared memory
     // batch
     const uint8_t* text;
-    const uint8_t* text_end;  // text + total bytes: no 16-byte block starting at or past it is read
+    const uint8_t* text_lo;   // first text byte of the batch: nothing below it is read
+    const uint8_t* text_end;  // one past the last text byte: nothing at or past it is read
     const uint64_t* offs;
     uint64_t n_items;  // number of work items (== haystacks unless a segment table is given)
     // Optional segment table (find_overlapping / no_suffix only): item i covers bytes
@@ -591,16 +592,6 @@ struct QEntry {
                          // StdMachine2 / LmMachine / CwMachine: opos = the slot, output_pos is looked up at drain
 };
 
-// State cache entries are compact records whose spare bits carry a 14-bit tag: bits 2..7 of w1 and
-// bits 0..7 of w2.  The record's consumers ignore those bits (flags are bits 0..1 of w1).
-constexpr uint32_t HOT_TAG_INVALID = 0x3fffu;
-DACH_HD uint32_t hot_tag(const uint4& e) { return (((e.y >> 2) & 0x3fu) << 8) | (e.z & 0xffu); }
-DACH_HD uint4 hot_entry(uint4 rec, uint32_t tag) {
-    rec.y = (rec.y & ~0xfcu) | ((tag >> 8) << 2);
-    rec.z = (rec.z & ~0xffu) | (tag & 0xffu);
-    return rec;
-}
-
 struct LaneStd {
     const uint8_t* hay;
     uint32_t len, pos, item;
@@ -618,14 +609,13 @@ struct LaneStd {
 };
 
 struct StdEnv {
-    const uint4* glob;     // compact records in global memory
-    const uint4* hot;      // shared-memory state cache: direct-mapped, entry (slot & hot_mask) holds the
-                           // record of one hot slot with (slot >> hot_shift) stored in its spare bits
-    uint32_t hot_mask;     // entries - 1 (entries is a power of two), 0 = no cache
-    uint32_t hot_shift;    // log2(entries)
-    uint32_t* visits;      // profiling pass only: landings per slot
+    const uint4* glob;     // compact records in global memory (hot-first layout, dev_image.cpp)
+    const uint4* hot;      // shared-memory copy of glob[0 .. hot_n): the hot region's leading records
+    uint32_t hot_s;        // ... its shared-window address (device code addresses it directly)
+    uint32_t hot_n;        // records staged in shared memory (StdMachine3), 0 = none
     const uint32_t* opos;  // output_pos per slot (global)
     const uint8_t* text_end;
+    const uint8_t* text_lo;
     uint32_t root_base;    // BASE of ROOT: the child for byte c sits in slot root_base ^ c
     uint32_t root_flags;   // CF_OUT if ROOT has an output list (an empty pattern)
     QEntry* q;             // this lane's queue: entry j at q[j * q_stride]
@@ -677,10 +667,12 @@ extern EmuStats g_emu_stats;
 #define DACH_STAT(f)
 #endif
 
-template <int MODE, bool PROFILE = false, bool HOT = false>
+template <int MODE>
 struct StdMachine {
     static constexpr int TOPUP = TEXT_TOPUP;
     static constexpr bool LAZY = false;
+    static constexpr bool LEAN = false;
+    static constexpr uint32_t IDLE = 0;
     static DACH_HD void finish_item(const LaneStd&, const ScanParams&) {}
     static DACH_HD const uint8_t* block_of(const LaneStd& L) {
         return reinterpret_cast<const uint8_t*>(((uintptr_t)L.hay + L.pos) & ~(uintptr_t)15);
@@ -747,14 +739,7 @@ struct StdMachine {
         // ---- phase 3: the one record fetch ---------------------------------------------------------
         if (run && (fl & (F_PROBE | F_LEARN)) != 0) {
             const uint32_t a = L.addr;
-            uint4 x;
-            bool cached = false;
-            if (HOT) {
-                x = Ev.hot[a & Ev.hot_mask];
-                cached = hot_tag(x) == (a >> Ev.hot_shift);
-                if (cached) DACH_STAT(cache_hits);
-            }
-            if (!cached) x = ld_u4(Ev.glob + a);
+            const uint4 x = ld_u4(Ev.glob + a);
             if (fl & F_PROBE) {
                 DACH_STAT(probes);
                 // BASE 0 means "no children" (src/bytewise.rs:1075): a ROOT without children is never entered
@@ -796,13 +781,6 @@ struct StdMachine {
         if (fl & F_LAND) {
             fl &= ~F_LAND;
             ++L.pos;
-            if (PROFILE) {
-#if defined(__CUDA_ARCH__)
-                atomicAdd(Ev.visits + L.addr, 1u);
-#else
-                ++Ev.visits[L.addr];
-#endif
-            }
             if ((((uint32_t)(uintptr_t)L.hay + L.pos) & 15u) == 0) {  // crossed into the next window
                 L.cw = L.nw;
                 fl |= F_NEED_NW;
@@ -838,10 +816,6 @@ struct StdMachine {
 #if defined(__CUDA_ARCH__)
         asm volatile("cp.async.wait_all;" ::: "memory");
 #endif
-        if (PROFILE) {  // the profiling pass only counts landings
-            L.qn = 0;
-            return;
-        }
         for (uint32_t j = 0; j < (uint32_t)LANE_Q; ++j) {
             if (j < L.qn) {
                 const QEntry e = Ev.q[j * Ev.q_stride];
@@ -872,7 +846,6 @@ struct StdMachine {
             L.len = end < hay_len ? end : hay_len;
             start = beg > P.warm ? beg - P.warm : 0;  // warm-up: the state at `beg` only depends on these bytes
         }
-        if (PROFILE && L.len > 16384u) L.len = 16384u;  // a sample is enough
         L.pos = start;
         L.from = beg;
         L.item = (uint32_t)item;
@@ -931,8 +904,10 @@ struct LaneLm : LaneStd {
 struct LmMachine {
     static constexpr int TOPUP = TEXT_TOPUP;
     static constexpr bool LAZY = true;
+    static constexpr bool LEAN = false;
+    static constexpr uint32_t IDLE = 0;
     static DACH_HD void finish_item(const LaneLm&, const ScanParams&) {}
-    using Std = StdMachine<M_LEFTMOST, false, false>;
+    using Std = StdMachine<M_LEFTMOST>;
 
     static DACH_HD void seek_full(LaneLm& L, const StdEnv& Ev, uint32_t pos, const uint8_t* emu_lo) {
         L.pos = pos;
@@ -1168,9 +1143,11 @@ template <int MODE>
 struct CwMachine {
     static constexpr int TOPUP = 4;
     static constexpr bool LAZY = true;
+    static constexpr bool LEAN = false;
+    static constexpr uint32_t IDLE = 0;
     static DACH_HD void finish_item(const LaneCw&, const ScanParams&) {}
     static constexpr bool LM = MODE == M_LEFTMOST;
-    using Std = StdMachine<M_OVERLAPPING, false, false>;
+    using Std = StdMachine<M_OVERLAPPING>;
 
     // the four bytes at L.pos, little endian (bytes past the windows' 32 are never needed)
     static DACH_HD uint32_t peek4(const LaneCw& L) {
@@ -1497,6 +1474,8 @@ template <int MODE>
 struct StdMachine2 {
     static constexpr int TOPUP = 8;
     static constexpr bool LAZY = true;
+    static constexpr bool LEAN = false;
+    static constexpr uint32_t IDLE = 0;
 
     static DACH_HD const uint8_t* block_of(const Lane2& L) {
         return reinterpret_cast<const uint8_t*>(((uintptr_t)L.hay + L.pos) & ~(uintptr_t)7);
@@ -1612,7 +1591,7 @@ struct StdMachine2 {
 
     // the item is complete (its last byte landed): hand the state on to the next chunk of the stream
     static DACH_HD void finish_item(const Lane2& L, const ScanParams& P) {
-        if (P.state_io) P.state_io[L.item] = L.addr;
+        if (P.state_io) P.state_io[L.item] = P.id_out ? P.id_out[L.addr] : L.addr;
     }
 
     static DACH_HD void begin_item(Lane2& L, const ScanParams& P, const StdEnv& Ev, Emitter& E, uint64_t item,
@@ -1653,8 +1632,9 @@ struct StdMachine2 {
         if (P.state_io) {
             // a chunk of a stream: resume in the state the previous chunk ended in (the stepper contract,
             // src/bytewise/iter.rs:344-475); the outputs of that state were reported with the previous chunk
-            const uint32_t st = P.state_io[item];
+            uint32_t st = P.state_io[item];
             if (st != D_ROOT && st < P.n_slots) {
+                if (P.id_in) st = P.id_in[st];
                 const uint4 x = ld_u4(Ev.glob + st);
                 L.r0 = x.x;
                 L.nf = x.y;
@@ -1666,6 +1646,256 @@ struct StdMachine2 {
         }
         if (MODE != M_FIND && (Ev.root_flags & CF_OUT) && beg == 0) {
             QEntry e;
+            e.end = 0;
+            e.opos = D_ROOT;
+            Ev.q[0] = e;
+            L.qn = 1;
+        }
+    }
+};
+
+// =============================================================================================
+// StdMachine3: the bytewise Standard machine, third cut -- the default.
+//
+// StdMachine2 sits on two ceilings at once (profiles/r1d_*): the L1 data pipe (every lane's record
+// fetch is its own wavefront) and the issue slots (98 warp instructions per lock-step iteration).
+// This cut attacks both:
+//   * records come from the hot-first image (dev_image.cpp): the leading Ev.hot_n slots are staged
+//     in shared memory and served from there by a plain prefix compare -- no tag, no dependent
+//     lookup; a warp's 32 random 16-byte reads cost ~10 shared-memory wavefronts instead of 32 L1 ones;
+//   * no probe-state flags: a missed own-child probe (signature false positive) clears the
+//     signature bit of that byte, a missed failure probe rewrites (nf, r2) in place, so every
+//     iteration is the same "probe, compare, adopt" and the rare paths leave no trace in the loop;
+//   * one stop bit (haystack finished or queue full) replaces the per-iteration bookkeeping; the
+//     service vote reads it once per period;
+//   * the cursor is the low address word of the byte being matched: the same register answers
+//     "window boundary?", "end of haystack?" and, minus the haystack's low address word, the match end;
+//   * the segment filter (only matches ending inside the segment) moved out of the loop to the drain.
+// Semantics are StdMachine2's (src/bytewise.rs:1063-1088, src/bytewise/iter.rs:58-243, 344-475).
+// =============================================================================================
+
+constexpr uint32_t F3_STOP = 0x10u;  // the lane does not step: idle, finished, or its queue is full
+
+struct Lane3 {
+    uint32_t hay_lo, hay_hi;  // address of the haystack's first byte
+    uint32_t ap, ap_end;      // low address word of the byte being matched / of one past the item's last byte
+    uint32_t w0, w1, n0, n1;  // text: current 8 bytes (shifted: the low byte is the one being matched), next 8 bytes
+    uint32_t r0, nf, r2, sig; // the state the lane sits in: raw words of its compact record
+    uint32_t addr;            // the slot landed on
+    uint32_t qn, fl, item;
+    uint32_t from;            // drain: only events with end >= from are reported (segment start + 1, or 0)
+};
+
+// 8 text bytes at the 8-aligned address q; bytes outside [text_lo, text_end) read as 0 and are never touched
+DACH_HD uint2 ld_text8_safe(const uint8_t* q, const uint8_t* text_lo, const uint8_t* text_end) {
+    uint2 w;
+    w.x = w.y = 0;
+    if (q >= text_end || q + 8 <= text_lo) return w;
+    if (q >= text_lo && q + 8 <= text_end) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(q));
+#else
+        for (int i = 0; i < 8; ++i) (i < 4 ? w.x : w.y) |= (uint32_t)q[i] << ((i & 3) * 8);
+#endif
+        return w;
+    }
+    for (int i = 0; i < 8; ++i) {  // first or last block of the batch: byte by byte
+        const uint8_t* qi = q + i;
+        if (qi >= text_lo && qi < text_end) {
+#if defined(__CUDA_ARCH__)
+            const uint32_t b = __ldg(qi);
+#else
+            const uint32_t b = *qi;
+#endif
+            (i < 4 ? w.x : w.y) |= b << ((i & 3) * 8);
+        }
+    }
+    return w;
+}
+
+template <int MODE>
+struct StdMachine3 {
+    static constexpr int TOPUP = 8;
+    static constexpr bool LAZY = true;
+    static constexpr bool LEAN = true;
+    static constexpr uint32_t IDLE = F3_STOP;
+
+    // one record: the hot region's leading slots from shared memory, everything else through L1 / L2
+    static DACH_HD uint4 fetch(const StdEnv& Ev, uint32_t a) {
+#if defined(__CUDA_ARCH__) && defined(DACH_FETCH_GENERIC)
+        // experiment build: one generic load, the address space is resolved per lane by the hardware
+        const uint4* q = a < Ev.hot_n ? Ev.hot + a : Ev.glob + a;
+        return *q;
+#else
+        if (a < Ev.hot_n) {
+            DACH_STAT(cache_hits);
+#if defined(__CUDA_ARCH__)
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(Ev.hot_s + a * 16u));
+            return v;
+#else
+            return Ev.hot[a];
+#endif
+        }
+        return ld_u4(Ev.glob + a);
+#endif
+    }
+    static DACH_HD const uint8_t* block_of(const Lane3& L) {  // the 8-byte block the cursor is in
+        const uint64_t hi = (uint64_t)(L.hay_hi + (L.ap < L.hay_lo ? 1u : 0u));  // the cursor wrapped past 2^32
+        return reinterpret_cast<const uint8_t*>((uintptr_t)((hi << 32) | (L.ap & ~7u)));
+    }
+    static DACH_HD void text_topup(Lane3& L, const StdEnv& Ev, const uint8_t* emu_lo) {
+        (void)emu_lo;
+        if (L.fl & F_NEED_NW) {
+            const uint2 n = ld_text8_safe(block_of(L) + 8, Ev.text_lo, Ev.text_end);
+            L.n0 = n.x;
+            L.n1 = n.y;
+            L.fl &= ~F_NEED_NW;
+        }
+    }
+    static DACH_HD void to_root(Lane3& L, const StdEnv& Ev) {
+        L.r0 = Ev.root_rec.x;
+        L.nf = Ev.root_rec.y;
+        L.r2 = Ev.root_rec.z;
+        L.sig = Ev.root_rec.w;
+        L.addr = D_ROOT;
+    }
+
+    // the byte is consumed; the lane sits in the state whose record it just adopted
+    static DACH_HD void land(Lane3& L, const StdEnv& Ev) {
+        ++L.ap;
+        L.w0 = (L.w0 >> 8) | (L.w1 << 24);
+        L.w1 >>= 8;
+        if ((L.ap & 7u) == 0) {  // the next 8 bytes become current
+            L.w0 = L.n0;
+            L.w1 = L.n1;
+            L.fl |= F_NEED_NW;
+        }
+        if (L.ap == L.ap_end) L.fl |= F_DONE | F3_STOP;
+        if (L.nf & CF_OUT) {
+            DACH_STAT(pushes);
+            QEntry e;  // one 8-byte store: (end, slot); output_pos is looked up when the queue is drained
+            e.end = L.ap - L.hay_lo;
+            e.opos = L.addr;
+            Ev.q[L.qn * Ev.q_stride] = e;
+            if (++L.qn == (uint32_t)LANE_Q) L.fl |= F3_STOP;
+            if (MODE == M_FIND) to_root(L, Ev);  // every next() restarts at ROOT (src/bytewise/iter.rs:87)
+        }
+    }
+
+    static DACH_HD bool step(Lane3& L, const StdEnv& Ev, const uint8_t* emu_lo = nullptr) {
+        (void)emu_lo;
+        if (L.fl & F3_STOP) return false;
+        DACH_STAT(steps);
+        const uint32_t c = L.w0 & 0xffu;
+        const uint32_t own = (L.sig >> (L.w0 & 31u)) & 1u;  // may this state have a child labelled c?
+        const uint32_t a = ((own ? L.r0 : L.r2) >> 8) ^ c;  // its child, or the failure state's
+        DACH_STAT(probes);
+        const uint4 x = fetch(Ev, a);
+        if (((x.x ^ L.w0) & 0xffu) == 0) {  // CHECK == c: adopt the record
+            DACH_STAT(hits);
+            L.r0 = x.x;
+            L.nf = x.y;
+            L.r2 = x.z;
+            L.sig = x.w;
+            L.addr = a;
+            land(L, Ev);
+        } else if (own) {  // signature false positive: this state has no child for c after all
+            DACH_STAT(miss_known);
+            L.sig &= ~(1u << (L.w0 & 31u));
+        } else if (L.nf & CF_FROOT) {  // that was ROOT's row: stay in ROOT
+            DACH_STAT(root_stay);
+            to_root(L, Ev);
+            land(L, Ev);
+        } else if (L.nf & CF_F2ROOT) {  // the failure state's own failure target is ROOT: probe ROOT's row next
+            DACH_STAT(miss_f2root);
+            L.r2 = Ev.root_base << 8;
+            L.nf |= CF_FROOT;
+        } else {  // go on from the failure state's record (rare: 0.003 per byte on the bench text)
+            DACH_STAT(learns);
+            const uint4 y = fetch(Ev, L.nf >> 8);
+            L.nf = y.y;
+            L.r2 = y.z;
+        }
+        return true;
+    }
+
+    static DACH_HD void drain(Lane3& L, const StdEnv& Ev, const ScanParams& P, Emitter& E) {
+        for (uint32_t j = 0; j < (uint32_t)LANE_Q; ++j) {
+            if (j < L.qn) {
+                const QEntry e = Ev.q[j * Ev.q_stride];
+                if (e.end >= L.from) {  // a segment reports only what ends inside it
+                    const uint32_t opos = ld_u32(Ev.opos + e.opos);  // the entry holds the slot
+                    if (MODE == M_OVERLAPPING)
+                        emit_chain(P, E, opos, e.end);
+                    else
+                        emit_head(P, E, opos, e.end);
+                }
+            }
+        }
+        L.qn = 0;
+        if (!(L.fl & F_DONE)) L.fl &= ~F3_STOP;
+    }
+
+    // the item is complete (its last byte landed): hand the state on to the next chunk of the stream
+    static DACH_HD void finish_item(const Lane3& L, const ScanParams& P) {
+        if (P.state_io) P.state_io[L.item] = P.id_out ? P.id_out[L.addr] : L.addr;
+    }
+
+    static DACH_HD void begin_item(Lane3& L, const ScanParams& P, const StdEnv& Ev, Emitter& E, uint64_t item,
+                                   const uint8_t* emu_lo) {
+        (void)emu_lo;
+        uint64_t hay = item;
+        uint32_t beg = 0;
+        if (P.item_hay) {
+            hay = P.item_hay[item];
+            beg = P.item_beg[item];
+        }
+        const uint64_t o0 = P.offs[hay], o1 = P.offs[hay + 1];
+        const uint32_t hay_len = (uint32_t)(o1 - o0);
+        const uintptr_t h = (uintptr_t)(P.text + o0);
+        L.hay_lo = (uint32_t)h;
+        L.hay_hi = (uint32_t)((uint64_t)h >> 32);
+        uint32_t start = 0, end = hay_len;
+        if (P.item_hay && hay >= P.seg_from) {
+            const uint64_t e64 = (uint64_t)beg + P.seg_len;
+            if (e64 < hay_len) end = (uint32_t)e64;
+            start = beg > P.warm ? beg - P.warm : 0;  // warm-up: the state at `beg` only depends on these bytes
+        }
+        L.ap = L.hay_lo + start;
+        L.ap_end = L.hay_lo + end;
+        L.from = beg ? beg + 1 : 0;
+        L.item = (uint32_t)item;
+        L.qn = 0;
+        E.begin((uint32_t)item);
+        const uint8_t* b0 = block_of(L);
+        const uint2 a = ld_text8_safe(b0, Ev.text_lo, Ev.text_end);
+        const uint2 n = ld_text8_safe(b0 + 8, Ev.text_lo, Ev.text_end);
+        const uint32_t sh = (L.ap & 7u) * 8u;  // the byte at the cursor goes to bit 0
+        const uint64_t cur = (((uint64_t)a.y << 32) | a.x) >> sh;
+        L.w0 = (uint32_t)cur;
+        L.w1 = (uint32_t)(cur >> 32);
+        L.n0 = n.x;
+        L.n1 = n.y;
+        to_root(L, Ev);
+        L.fl = F_ACTIVE | (start >= end ? (F_DONE | F3_STOP) : 0u);
+        if (P.state_io) {
+            // a chunk of a stream: resume in the state the previous chunk ended in (the stepper contract,
+            // src/bytewise/iter.rs:344-475); the outputs of that state were reported with the previous chunk
+            uint32_t st = P.state_io[item];
+            if (st != D_ROOT && st < P.n_slots) {
+                if (P.id_in) st = P.id_in[st];
+                const uint4 x = fetch(Ev, st);
+                L.r0 = x.x;
+                L.nf = x.y;
+                L.r2 = x.z;
+                L.sig = x.w;
+                L.addr = st;
+            }
+            return;
+        }
+        if (MODE != M_FIND && (Ev.root_flags & CF_OUT) && beg == 0) {
+            QEntry e;  // the iterator starts in ROOT with ROOT's output list pending at position 0
             e.end = 0;
             e.opos = D_ROOT;
             Ev.q[0] = e;

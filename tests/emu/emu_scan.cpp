@@ -44,7 +44,7 @@ static void run_items(const ScanParams& P, const RecView& V, const uint8_t* lo, 
 
 // Warp-level driver of the v1 lane machine, mirroring k_scan_std in dev_scan.cu with the warp
 // collectives (ballot / any / shuffle) written out as loops over 32 lane states.
-template <class M, class LANE, bool PROFILE>
+template <class M, class LANE>
 static void run_machine(const ScanParams& P, const StdEnv& Ev0, const uint8_t* lo, int n_warps) {
     struct Warp {
         LANE L[32];
@@ -58,7 +58,7 @@ static void run_machine(const ScanParams& P, const StdEnv& Ev0, const uint8_t* l
     for (auto& w : warps) {
         w.queue.assign((size_t)LANE_Q * 32, QEntry{0, 0});
         for (int l = 0; l < 32; ++l) {
-            w.L[l].fl = 0;
+            w.L[l].fl = M::IDLE;
             w.L[l].qn = 0;
             w.E[l].begin(0);
             w.exhausted[l] = false;
@@ -78,11 +78,9 @@ static void run_machine(const ScanParams& P, const StdEnv& Ev0, const uint8_t* l
                 if (w.L[l].fl & F_ACTIVE) M::drain(w.L[l], w.Ev[l], P, w.E[l]);
             for (int l = 0; l < 32; ++l)
                 if ((w.L[l].fl & (F_ACTIVE | F_DONE)) == (F_ACTIVE | F_DONE)) {
-                    if (!PROFILE) {
-                        w.E[l].finish(P);
-                        M::finish_item(w.L[l], P);
-                    }
-                    w.L[l].fl = 0;
+                    w.E[l].finish(P);
+                    M::finish_item(w.L[l], P);
+                    w.L[l].fl = M::IDLE;
                 }
             unsigned m = 0;
             for (int l = 0; l < 32; ++l)
@@ -119,7 +117,10 @@ static void run_machine(const ScanParams& P, const StdEnv& Ev0, const uint8_t* l
                     }
                     if (!M::LAZY && need_service) stop = true;
                 }
-                if (M::LAZY) {  // mirrors the vote in k_scan_machine
+                if (M::LEAN) {  // mirrors the votes in k_scan_machine
+                    for (int l = 0; l < 32; ++l)
+                        if ((w.L[l].fl & (F_ACTIVE | M::IDLE)) == (F_ACTIVE | M::IDLE)) stop = true;
+                } else if (M::LAZY) {
                     for (int l = 0; l < 32; ++l)
                         if (waiting[l] && (w.L[l].fl & F_ACTIVE)) stop = true;
                 }
@@ -128,12 +129,20 @@ static void run_machine(const ScanParams& P, const StdEnv& Ev0, const uint8_t* l
     }
 }
 
-template <int MODE, bool PROFILE, bool HOT>
+template <int MODE>
 static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* lo, int n_warps) {
-    run_machine<StdMachine<MODE, PROFILE, HOT>, LaneStd, PROFILE>(P, Ev0, lo, n_warps);
+    run_machine<StdMachine<MODE>, LaneStd>(P, Ev0, lo, n_warps);
 }
 
 static uint32_t* g_state_io = nullptr;
+static int g_stream_kernel = 3;       // which bytewise Standard machine serves emu_scan_stream_wire
+static uint32_t g_stream_hot = 4096;  // ... and its shared-memory records
+static uint32_t g_want_hot_slots = 65536;  // size of the hot region build_image() lays out
+extern "C" void emu_set_hot_slots(uint32_t n) { g_want_hot_slots = n; }
+extern "C" void emu_stream_config(int kernel, uint32_t hot_n) {
+    g_stream_kernel = kernel;
+    g_stream_hot = hot_n;
+}
 static const uint32_t* g_pos_in = nullptr;
 
 extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int charwise, int mode,
@@ -145,6 +154,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     int rc = wire_read(wire, wire_len, charwise != 0, &pma, &used);
     if (rc) return rc;
     HostImage img;
+    img.want_hot_slots = g_want_hot_slots;
     rc = build_image(pma, &img);
     const bool lm = is_leftmost(pma->match_kind);
     delete pma;
@@ -153,7 +163,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
 
     // segment table (mirrors k_seg_count / k_seg_fill in dev_scan.cu)
     const bool v1 = kernel_version >= 1 && !img.crec.empty() && !(mode == M_FIND && img.root_opos != 0);
-    if (g_state_io && !(v1 && !charwise && mode != M_LEFTMOST && kernel_version >= 2 && img.root_base != 0 && hot_n == 0))
+    if (g_state_io && !(v1 && !charwise && mode != M_LEFTMOST && kernel_version >= 2 && img.root_base != 0))
         return DACH_INVALID_ARGUMENT;  // as scan_locked() in dev_scan.cu
     const bool seg = v1 && !charwise && !g_state_io && seg_len > 0 && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX);
     std::vector<uint32_t> item_hay, item_beg;
@@ -188,7 +198,12 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     if (hot_n > img.n_slots) hot_n = img.n_slots;
     P.hot_n = hot_n;
     P.text = text;
+    P.text_lo = text + (n ? offs[0] : 0);
     P.text_end = text + (n ? offs[n] : 0);
+    if (img.hot_slots) {
+        P.id_in = img.new_of_old.data();
+        P.id_out = img.old_of_new.data();
+    }
     P.offs = offs;
 
     P.n_items = n_items;
@@ -211,69 +226,39 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
     const uint8_t* lo = text + (n ? offs[0] : 0);
     const uint8_t* hi = text + (n ? offs[n] : 0);
     if (v1) {
-        // state cache: profiling pass over the first items, then k_hot_pick / k_hot_fill
-        uint32_t entries = (mode == M_LEFTMOST || charwise) ? 0 : hot_n;
-        while (entries & (entries - 1)) entries &= entries - 1;  // power of two
-        if (entries && (uint64_t)img.n_slots > (uint64_t)entries * HOT_TAG_INVALID) entries = 0;
-        uint32_t shift = 0;
-        while ((1u << shift) < entries) ++shift;
-        std::vector<uint32_t> visits(img.n_slots ? img.n_slots : 1, 0);
-        std::vector<uint32_t> tab((size_t)(entries ? entries : 1) * 4, 0);
-        StdEnv Ev{reinterpret_cast<const uint4*>(img.crec.data()), reinterpret_cast<const uint4*>(tab.data()), 0u, 0u, visits.data(),
-                  img.opos_tab.data(), P.text_end, img.root_base, P.root_opos ? CF_OUT : 0u, nullptr, 0, 0, P.mapper, P.mapper_len,
+        // StdMachine3: the leading hot_n compact records are served from a "shared memory" copy; everything past
+        // them in that copy is poison, so a wrong prefix compare cannot go unnoticed
+        uint32_t entries = (mode == M_LEFTMOST || charwise || kernel_version < 3) ? 0 : hot_n;
+        if (entries > img.hot_slots) entries = img.hot_slots;
+        std::vector<uint32_t> tab(img.crec.size() ? img.crec.size() : 4, 0xdeadbeefu);
+        memcpy(tab.data(), img.crec.data(), (size_t)entries * 16);
+        StdEnv Ev{reinterpret_cast<const uint4*>(img.crec.data()), reinterpret_cast<const uint4*>(tab.data()), 0u, entries,
+                  img.opos_tab.data(), P.text_end, P.text_lo, img.root_base, P.root_opos ? CF_OUT : 0u, nullptr, 0, 0, P.mapper, P.mapper_len,
                   reinterpret_cast<const uint4*>(img.crec.data())[D_ROOT]};
         const int n_warps = 3;
-        if (entries) {
-            ScanParams Q = P;
-            Q.item_hay = nullptr;
-            Q.item_beg = nullptr;
-            Q.n_items = n < 7 ? n : 7;  // a small sample, like the device pass
-            if (mode == M_FIND) run_items_v1<M_FIND, true, false>(Q, Ev, lo, n_warps);
-            if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING, true, false>(Q, Ev, lo, n_warps);
-            if (mode == M_NO_SUFFIX) run_items_v1<M_NO_SUFFIX, true, false>(Q, Ev, lo, n_warps);
-            ctrl.next_item = 0;
-            std::vector<uint64_t> best(entries, 0);
-            for (uint32_t sidx = 0; sidx < img.n_slots; ++sidx)
-                if (visits[sidx]) {
-                    const uint64_t v = ((uint64_t)visits[sidx] << 32) | sidx;
-                    if (v > best[sidx & (entries - 1)]) best[sidx & (entries - 1)] = v;
-                }
-            for (uint32_t b = 0; b < entries; ++b) {
-                uint4 e;
-                if (best[b]) {
-                    const uint32_t slot = (uint32_t)best[b];
-                    e = hot_entry(reinterpret_cast<const uint4*>(img.crec.data())[slot], slot >> shift);
-                } else {
-                    e.x = e.y = e.z = e.w = 0;
-                    e = hot_entry(e, HOT_TAG_INVALID);
-                }
-                memcpy(&tab[(size_t)b * 4], &e, 16);
-            }
-            Ev.hot_mask = entries - 1;
-            Ev.hot_shift = shift;
-        }
         if (charwise) {
             if (getenv("DACH_EMU_TRACE")) fprintf(stderr, "emu: charwise lane machine\n");
-            if (mode == M_FIND) run_machine<CwMachine<M_FIND>, LaneCw, false>(P, Ev, lo, n_warps);
-            if (mode == M_OVERLAPPING) run_machine<CwMachine<M_OVERLAPPING>, LaneCw, false>(P, Ev, lo, n_warps);
-            if (mode == M_NO_SUFFIX) run_machine<CwMachine<M_NO_SUFFIX>, LaneCw, false>(P, Ev, lo, n_warps);
-            if (mode == M_LEFTMOST) run_machine<CwMachine<M_LEFTMOST>, LaneCw, false>(P, Ev, lo, n_warps);
-        } else if (mode != M_LEFTMOST && kernel_version >= 2 && img.root_base != 0 && entries == 0) {
+            if (mode == M_FIND) run_machine<CwMachine<M_FIND>, LaneCw>(P, Ev, lo, n_warps);
+            if (mode == M_OVERLAPPING) run_machine<CwMachine<M_OVERLAPPING>, LaneCw>(P, Ev, lo, n_warps);
+            if (mode == M_NO_SUFFIX) run_machine<CwMachine<M_NO_SUFFIX>, LaneCw>(P, Ev, lo, n_warps);
+            if (mode == M_LEFTMOST) run_machine<CwMachine<M_LEFTMOST>, LaneCw>(P, Ev, lo, n_warps);
+        } else if (mode != M_LEFTMOST && kernel_version >= 3 && img.root_base != 0) {
+            if (getenv("DACH_EMU_TRACE")) fprintf(stderr, "emu: StdMachine3, %u hot records\n", entries);
+            if (mode == M_FIND) run_machine<StdMachine3<M_FIND>, Lane3>(P, Ev, lo, n_warps);
+            if (mode == M_OVERLAPPING) run_machine<StdMachine3<M_OVERLAPPING>, Lane3>(P, Ev, lo, n_warps);
+            if (mode == M_NO_SUFFIX) run_machine<StdMachine3<M_NO_SUFFIX>, Lane3>(P, Ev, lo, n_warps);
+        } else if (mode != M_LEFTMOST && kernel_version >= 2 && img.root_base != 0) {
             if (getenv("DACH_EMU_TRACE")) fprintf(stderr, "emu: StdMachine2\n");
-            if (mode == M_FIND) run_machine<StdMachine2<M_FIND>, Lane2, false>(P, Ev, lo, n_warps);
-            if (mode == M_OVERLAPPING) run_machine<StdMachine2<M_OVERLAPPING>, Lane2, false>(P, Ev, lo, n_warps);
-            if (mode == M_NO_SUFFIX) run_machine<StdMachine2<M_NO_SUFFIX>, Lane2, false>(P, Ev, lo, n_warps);
+            if (mode == M_FIND) run_machine<StdMachine2<M_FIND>, Lane2>(P, Ev, lo, n_warps);
+            if (mode == M_OVERLAPPING) run_machine<StdMachine2<M_OVERLAPPING>, Lane2>(P, Ev, lo, n_warps);
+            if (mode == M_NO_SUFFIX) run_machine<StdMachine2<M_NO_SUFFIX>, Lane2>(P, Ev, lo, n_warps);
         } else if (mode == M_LEFTMOST) {
             if (getenv("DACH_EMU_TRACE")) fprintf(stderr, "emu: leftmost lane machine\n");
-            run_machine<LmMachine, LaneLm, false>(P, Ev, lo, n_warps);
-        } else if (entries) {
-            if (mode == M_FIND) run_items_v1<M_FIND, false, true>(P, Ev, lo, n_warps);
-            if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING, false, true>(P, Ev, lo, n_warps);
-            if (mode == M_NO_SUFFIX) run_items_v1<M_NO_SUFFIX, false, true>(P, Ev, lo, n_warps);
+            run_machine<LmMachine, LaneLm>(P, Ev, lo, n_warps);
         } else {
-            if (mode == M_FIND) run_items_v1<M_FIND, false, false>(P, Ev, lo, n_warps);
-            if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING, false, false>(P, Ev, lo, n_warps);
-            if (mode == M_NO_SUFFIX) run_items_v1<M_NO_SUFFIX, false, false>(P, Ev, lo, n_warps);
+            if (mode == M_FIND) run_items_v1<M_FIND>(P, Ev, lo, n_warps);
+            if (mode == M_OVERLAPPING) run_items_v1<M_OVERLAPPING>(P, Ev, lo, n_warps);
+            if (mode == M_NO_SUFFIX) run_items_v1<M_NO_SUFFIX>(P, Ev, lo, n_warps);
         }
     } else
     switch ((charwise ? 4 : 0) + mode) {
@@ -321,7 +306,7 @@ extern "C" int emu_scan_stream_wire(const uint8_t* wire, size_t wire_len, int mo
     if (mode != M_FIND && mode != M_OVERLAPPING) return DACH_INVALID_ARGUMENT;
     g_state_io = state_io;
     g_pos_in = pos_in;
-    const int rc = emu_scan_batch_wire(wire, wire_len, 0, mode, text, offs, n, 0, 2, 0, 0, pool_blocks, out, out_cap, out_offs, needed);
+    const int rc = emu_scan_batch_wire(wire, wire_len, 0, mode, text, offs, n, g_stream_hot, g_stream_kernel, 0, 0, pool_blocks, out, out_cap, out_offs, needed);
     g_state_io = nullptr;
     g_pos_in = nullptr;
     return rc;

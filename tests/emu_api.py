@@ -28,7 +28,7 @@ def lib():
     return _lib
 
 
-def scan(wire, charwise, mode, text, offs, hot_n=0, pool_blocks=None, out_cap=None, kernel=2, seg_len=0, seg_from=0):
+def scan(wire, charwise, mode, text, offs, hot_n=0, pool_blocks=None, out_cap=None, kernel=3, seg_len=0, seg_from=0):
     """Returns (rc, matches, out_offs, needed)."""
     wire_a = np.frombuffer(wire, dtype=np.uint8)
     text = np.ascontiguousarray(text, dtype=np.uint8)

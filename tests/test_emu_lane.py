@@ -36,7 +36,7 @@ def test_golden_vectors(variant, iterator, kind, t):
     wire = O.OraclePma.build(t["patterns"], charwise=cw, match_kind=O.KIND[kind]).serialize()
     hay = t["haystack"].encode()
     text = np.frombuffer(hay, dtype=np.uint8)
-    for hot, kernel in ((0, 1), (64, 1), (3, 0), (0, 2)):
+    for hot, kernel in ((0, 1), (3, 0), (0, 2), (0, 3), (256, 3), (1 << 16, 3)):
         rc, m, oo, need = E.scan(wire, cw, MODE[iterator], text, np.array([0, len(hay)], dtype=np.uint64), hot_n=hot,
                                  kernel=kernel)
         assert rc == 0
@@ -75,7 +75,7 @@ def test_random_batches(seed, kind, cw):
     modes = [3] if kind else [0, 1, 2]
     for mode in modes:
         ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
-        for hot, kernel in ((0, 1), (2, 1), (16, 1), (1 << 12, 1), (5, 0), (0, 2)):
+        for hot, kernel in ((0, 1), (5, 0), (0, 2), (0, 3), (256, 3), (512, 3), (1 << 16, 3)):
             rc, m, oo, need = E.scan(wire, cw, mode, text, offs, hot_n=hot, kernel=kernel)
             assert rc == 0
             assert need == ref["total"]
@@ -93,8 +93,8 @@ def test_unaligned_offsets_and_long_chains():
         text = np.frombuffer(b"x" * shift + b"a" * 70 + b"b" + b"a" * 40, dtype=np.uint8)
         offs = np.array([shift, shift + 50, shift + 50, shift + 111], dtype=np.uint64)
         ref = pma.scan_batch(O.FIND_OVERLAPPING, text, offs, want_matches=True)
-        for kernel in (0, 1, 2):
-            rc, m, oo, need = E.scan(wire, False, 1, text, offs, kernel=kernel)
+        for kernel in (0, 1, 2, 3):
+            rc, m, oo, need = E.scan(wire, False, 1, text, offs, kernel=kernel, hot_n=256 if kernel == 3 else 0)
             assert rc == 0 and m.tobytes() == ref["matches"].tobytes()
             assert list(oo) == [0] + list(np.cumsum(ref["counts"]))
 
@@ -136,9 +136,10 @@ def test_segments_reproduce_the_sequential_scan(seed):
     for mode in (1, 2):
         ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
         for seg_len in (1, 3, 16, 64, 100, 1000):
-            for kernel in (1, 2):
+            for kernel in (1, 2, 3):
                 for seg_from in (0, 11, len(hays) - 3):  # > 0: only the tail of the batch is cut
-                    rc, m, oo, need = E.scan(wire, False, mode, text, offs, seg_len=seg_len, kernel=kernel, seg_from=seg_from)
+                    rc, m, oo, need = E.scan(wire, False, mode, text, offs, seg_len=seg_len, kernel=kernel, seg_from=seg_from,
+                                             hot_n=256 if kernel == 3 else 0)
                     assert rc == 0 and need == ref["total"], (seg_len, mode)
                     assert m.tobytes() == ref["matches"].tobytes(), (seg_len, mode)
                     assert np.array_equal(np.diff(oo.astype(np.int64)), ref["counts"].astype(np.int64))
@@ -185,12 +186,14 @@ def _stream_case(seed):
 
 @pytest.mark.parametrize("seed", range(24))
 @pytest.mark.parametrize("mode", [0, 1])
-def test_stream_chunks_equal_the_stepper_over_the_whole_stream(seed, mode):
+@pytest.mark.parametrize("kernel", [3, 2])
+def test_stream_chunks_equal_the_stepper_over_the_whole_stream(seed, mode, kernel):
     """dach_dev_scan_stream (lane machine, emulated): streams cut into ragged chunks and scanned round
     by round with the state carried over report exactly what the crate's stepper reports over the
     whole stream (consume + matches(), tests/aho_corasick_crate_test.rs:422-520) -- minus the
     matches() of the initial state at position 0, which no consume() produced."""
     pats, streams, rng = _stream_case(seed)
+    E.lib().emu_stream_config(kernel, 256 if seed % 2 else 0)
     pma = O.OraclePma.build(pats)
     wire = pma.serialize()
     orc_mode = O.FIND_STEPPER if mode == 0 else O.FIND_OVERLAPPING_STEPPER
@@ -223,3 +226,39 @@ def test_stream_chunks_equal_the_stepper_over_the_whole_stream(seed, mode):
     # the carried state is the reference's state id: one more round from a CPU-side walk agrees
     for i, s in enumerate(streams):
         assert int(state[i]) == pma.state_after(s, find_mode=(mode == 0))
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("hot_slots", [0, 256, 1024, 65536])
+def test_hot_first_relayout_at_dictionary_shape(seed, hot_slots):
+    """The compact image moves the children of the hottest states into a region at the front and shifts
+    every other slot up (dev_image.cpp); results must not depend on the region's size -- none at all,
+    one or a few 256-slot blocks (most states stay in the shifted part), everything -- nor on how much
+    of it a kernel serves from shared memory.  Standard and leftmost automata, stream state ids included."""
+    rng = np.random.default_rng(7000 + seed)
+    pats = sorted(set(rand_patterns(rng, 1500, 6, 9)))
+    E.lib().emu_set_hot_slots(hot_slots)
+    try:
+        for kind in (0, 1):
+            pma = O.OraclePma.build(pats, match_kind=kind)
+            wire = pma.serialize()
+            n = 12
+            hays = [bytes(rng.integers(97, 104, size=int(rng.integers(0, 700))).tolist()) for _ in range(n)]
+            offs = np.zeros(n + 1, dtype=np.uint64)
+            offs[1:] = np.cumsum([len(h) for h in hays])
+            text = np.frombuffer(b"".join(hays), dtype=np.uint8)
+            for mode in ([3] if kind else [0, 1, 2]):
+                ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
+                for hot, kernel in ((0, 1), (0, 2), (0, 3), (256, 3), (768, 3), (1 << 16, 3)):
+                    rc, m, oo, need = E.scan(wire, False, mode, text, offs, hot_n=hot, kernel=kernel)
+                    assert rc == 0 and need == ref["total"]
+                    assert m.tobytes() == ref["matches"].tobytes(), (mode, hot, kernel)
+            if kind == 0:  # state ids crossing the boundary are the crate's
+                E.lib().emu_stream_config(3, 256)
+                state = np.zeros(n, dtype=np.uint32)
+                rc, m, oo, need = E.scan_stream(wire, 1, text, offs, state)
+                assert rc == 0
+                for i, h in enumerate(hays):
+                    assert int(state[i]) == pma.state_after(h, find_mode=False)
+    finally:
+        E.lib().emu_set_hot_slots(65536)

@@ -13,7 +13,7 @@ from cases import mixed_width_case
 from daachorse_b200 import synth as S
 
 pytestmark = pytest.mark.gpu
-DEFAULT_KERNEL = 2
+DEFAULT_KERNEL = 3
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "search_tests.json"), encoding="utf-8"))
@@ -156,8 +156,9 @@ def test_kernel_options_do_not_change_results():
     pma = D.DoubleArrayAhoCorasick.new(pats)
     base = pma.scan_batch_host(D.FIND_OVERLAPPING, text, offs)
     for opts in ({"hot_records": -1}, {"hot_records": 17}, {"threads": 128}, {"threads": 512, "ctas_per_sm": 2},
-                 {"kernel": 0}, {"kernel": 2}, {"kernel": 2, "threads": 256}, {"kernel": 0, "hot_records": 100}, {"l2_persist": 0}, {"hot_entries": 0},
-                 {"hot_entries": 64}, {"hot_entries": 8192}, {"hot_entries": 4096, "profile_items": 3}, {"dbg": 4}, {"dbg": 2}, {"gather_ordered": 0}, {"gather_ordered": 2}, {"tail_seg": 1}):
+                 {"kernel": 0}, {"kernel": 1}, {"kernel": 2}, {"kernel": 2, "threads": 256}, {"kernel": 3, "threads": 256},
+                 {"kernel": 3, "threads": 768, "ctas_per_sm": 2}, {"kernel": 0, "hot_records": 100}, {"l2_persist": 0}, {"hot_entries": 0},
+                 {"hot_entries": 256}, {"hot_entries": 8192}, {"hot_entries": 1 << 20}, {"gather_ordered": 0}, {"gather_ordered": 2}, {"tail_seg": 1}):
         for k, v in opts.items():
             pma.set_option(k, v)
         r = pma.scan_batch_host(D.FIND_OVERLAPPING, text, offs)
@@ -167,9 +168,7 @@ def test_kernel_options_do_not_change_results():
         pma.set_option("ctas_per_sm", 1)
         pma.set_option("kernel", DEFAULT_KERNEL)
         pma.set_option("l2_persist", 1)
-        pma.set_option("hot_entries", 0)
-        pma.set_option("profile_items", 2048)
-        pma.set_option("dbg", 0)
+        pma.set_option("hot_entries", -1)
         pma.set_option("gather_ordered", 1)
         pma.set_option("tail_seg", 0)
 
@@ -243,13 +242,16 @@ def test_config_c3_reduced_batch_all_standard_modes():
     check_batch(pma, opma, D.FIND_OVERLAPPING, text, offs)
     check_batch(pma, opma, D.FIND, text, offs)
     check_batch(pma, opma, D.FIND_OVERLAPPING_NO_SUFFIX, text[: 4096 * 2048], offs[:2049])
-    # the two bytewise Standard lane machines (kernel 1: StdMachine, kernel 2: StdMachine2) agree
+    # the three bytewise Standard lane machines (kernel 1: StdMachine, 2: StdMachine2, 3: StdMachine3 with and
+    # without its shared-memory records) agree
     for mode in (D.FIND_OVERLAPPING, D.FIND, D.FIND_OVERLAPPING_NO_SUFFIX):
         res = []
-        for k in (1, 2):
+        for k, hot in ((1, -1), (2, -1), (3, -1), (3, 0), (3, 4096)):
             pma.set_option("kernel", k)
+            pma.set_option("hot_entries", hot)
             res.append(pma.scan_batch_host(mode, text, offs))
-        assert res[0].matches.tobytes() == res[1].matches.tobytes() and np.array_equal(res[0].offsets, res[1].offsets)
+        for r in res[1:]:
+            assert r.matches.tobytes() == res[0].matches.tobytes() and np.array_equal(r.offsets, res[0].offsets)
 
 
 def test_config_c4_reduced_charwise_leftmost_longest():
