@@ -8,10 +8,10 @@ the crate's public interface.
 from .automaton import (FIND, FIND_OVERLAPPING, FIND_OVERLAPPING_NO_SUFFIX, LEFTMOST_FIND, MATCH_DTYPE,
                         BatchResult, CharwiseDoubleArrayAhoCorasick,
                         CharwiseDoubleArrayAhoCorasickBuilder, DaachorseError, DoubleArrayAhoCorasick,
-                        DoubleArrayAhoCorasickBuilder, Match, MatchKind)
+                        DoubleArrayAhoCorasickBuilder, Job, Match, MatchKind)
 
 __all__ = [
     "DoubleArrayAhoCorasick", "DoubleArrayAhoCorasickBuilder", "CharwiseDoubleArrayAhoCorasick",
-    "CharwiseDoubleArrayAhoCorasickBuilder", "MatchKind", "Match", "DaachorseError", "BatchResult",
+    "CharwiseDoubleArrayAhoCorasickBuilder", "MatchKind", "Match", "DaachorseError", "BatchResult", "Job",
     "FIND", "FIND_OVERLAPPING", "FIND_OVERLAPPING_NO_SUFFIX", "LEFTMOST_FIND", "MATCH_DTYPE",
 ]

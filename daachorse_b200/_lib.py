@@ -21,7 +21,11 @@ SYMBOLS = [
     "dach_scan_batch_host", "dach_dev_kernel_launches", "dach_dev_last_scan_kernel_ms",
     "dach_dev_last_total_ms", "dach_dev_last_h2d_bytes", "dach_dev_last_d2h_bytes",
     "dach_dev_set_option", "dach_last_error", "dach_abi_version",
+    "dach_job_create", "dach_job_free", "dach_job_scan", "dach_job_place", "dach_job_wait", "dach_job_scan_kernel_ms",
+    "dach_group_create", "dach_group_export", "dach_group_connect", "dach_group_place", "dach_group_finish",
+    "dach_group_result", "dach_group_free",
 ]
+GROUP_HANDLE_BYTES = 256
 
 _lib = None
 
@@ -80,7 +84,27 @@ def load():
         getattr(L, name).restype = C.c_uint64
     L.dach_dev_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.dach_dev_set_option.restype = C.c_int
-    if L.dach_abi_version() != 1:
+    u64 = C.c_uint64
+    L.dach_job_create.argtypes = [vp, pp]
+    L.dach_job_free.argtypes = [vp]
+    L.dach_job_free.restype = None
+    L.dach_job_scan.argtypes = [vp, C.c_int, vp, vp, u64, u64, u64, vp]
+    L.dach_job_place.argtypes = [vp, vp, u64, vp, vp, vp]
+    L.dach_job_wait.argtypes = [vp, C.POINTER(u64)]
+    L.dach_job_scan_kernel_ms.argtypes = [vp]
+    L.dach_job_scan_kernel_ms.restype = C.c_double
+    L.dach_group_create.argtypes = [C.c_int, C.c_int, C.c_int, u64, u64, pp]
+    L.dach_group_export.argtypes = [vp, vp]
+    L.dach_group_connect.argtypes = [vp, vp]
+    L.dach_group_place.argtypes = [vp, vp, u64, C.c_int, vp]
+    L.dach_group_finish.argtypes = [vp, C.POINTER(u64), vp]
+    L.dach_group_result.argtypes = [vp, pp, pp]
+    L.dach_group_free.argtypes = [vp]
+    L.dach_group_free.restype = None
+    for name in ("dach_job_create", "dach_job_scan", "dach_job_place", "dach_job_wait", "dach_group_create", "dach_group_export",
+                 "dach_group_connect", "dach_group_place", "dach_group_finish", "dach_group_result"):
+        getattr(L, name).restype = C.c_int
+    if L.dach_abi_version() != 2:
         raise ImportError("daachorse_b200: ABI version mismatch")
     _lib = L
     return L

@@ -346,6 +346,11 @@ class _Automaton:
             _check(rc)
             return BatchResult(out[: need.value], out_offs)
 
+    def job(self, device=None):
+        """An asynchronous scan with its own workspace (dach_job_*): ``scan`` and ``place`` only enqueue work,
+        ``wait`` blocks.  Several jobs of one automaton overlap across streams and host threads."""
+        return Job(self, device)
+
     def _batch(self, mode, haystacks):
         blob, offs = _pack(list(haystacks), self._charwise)
         return self.scan_batch_host(mode, blob, offs)
@@ -380,6 +385,56 @@ class _Automaton:
 
     def leftmost_find_iter(self, haystack):
         return self._iter(LEFTMOST_FIND, haystack)
+
+
+class Job:
+    """dach_job: one in-flight scan of device-resident buffers (include/daachorse_b200.h, "asynchronous scans")."""
+
+    def __init__(self, pma, device=None):
+        import torch
+
+        self._pma = pma
+        self._dev = torch.cuda.current_device() if device is None else int(device)
+        self._h = C.c_void_p()
+        _check(_lib.load().dach_job_create(pma.device_handle(self._dev), C.byref(self._h)))
+        self._keep = None
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.load().dach_job_free(self._h)
+            self._h = C.c_void_p()
+
+    @staticmethod
+    def _stream(stream, device):
+        import torch
+
+        if stream is None:
+            return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        return C.c_void_p(stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream))
+
+    def scan(self, mode, text, offs, cap_matches, stream=None):
+        """Enqueue the scan of ``text`` (uint8 CUDA tensor) / ``offs`` (int64, n+1) on ``stream``."""
+        self._pma._assert_mode(mode)
+        self._keep = (text, offs)  # the kernels read them after this call returns
+        _check(_lib.load().dach_job_scan(self._h, mode, C.c_void_p(text.data_ptr()), C.c_void_p(offs.data_ptr()),
+                                         offs.numel() - 1, text.numel(), int(cap_matches), self._stream(stream, text.device)))
+
+    def place(self, out, out_offs, base=None, stream=None):
+        """Enqueue the gather into ``out`` ((cap, 3) int32) / ``out_offs`` (int64, n+1); ``base``: optional
+        1-element int64 CUDA tensor, index of the first match in ``out``."""
+        self._out = (out, out_offs, base)
+        _check(_lib.load().dach_job_place(self._h, C.c_void_p(out.data_ptr()), out.shape[0], C.c_void_p(out_offs.data_ptr()),
+                                          C.c_void_p(base.data_ptr()) if base is not None else None,
+                                          self._stream(stream, out.device)))
+
+    def wait(self):
+        """Block until the placement is done; returns the number of matches (raises on overflow)."""
+        need = C.c_uint64()
+        _check(_lib.load().dach_job_wait(self._h, C.byref(need)))
+        return int(need.value)
+
+    def scan_kernel_ms(self):
+        return _lib.load().dach_job_scan_kernel_ms(self._h)
 
 
 def _current_device():

@@ -15,7 +15,10 @@
 // No CPU fallback exists: every entry point here fails with DACH_CUDA_ERROR without a device.
 #include <cuda_runtime.h>
 
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
     }
 
     const StdEnv Ev{P.crec,      s_hot,       smem_u32(s_hot), HOT ? P.hot_entries : 0u, P.opos_tab, P.text_end, P.text_lo, P.root_base, P.root_opos ? CF_OUT : 0u,
-                    s_queue + threadIdx.x, blockDim.x, P.dbg, P.mapper, P.mapper_len, ld_u4(P.crec + D_ROOT)};
+                    s_queue + threadIdx.x, blockDim.x, 0u, P.mapper, P.mapper_len, ld_u4(P.crec + D_ROOT)};
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     LANE L;
@@ -304,14 +307,19 @@ __global__ void __launch_bounds__(256) k_blk_index(const uint32_t* pool, const S
     }
 }
 
-// One warp per block.  Skipped entirely when the batch overflowed the pool or out_cap.
+// One warp per block.  Skipped entirely when the batch overflowed the pool or out_cap.  `base` (device pointer
+// or nullptr = 0) is the index of this batch's first match in `out_words` -- which may be peer-mapped memory
+// of another GPU (dach_group_place): the copy then IS the exchange step, NVLink stores straight into the
+// gathering rank's dense buffer.
 template <int U>
 __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const ScanCtrl* ctrl, uint32_t pool_blocks,
-                                                 const uint32_t* counts, const unsigned long long* out_offs,
-                                                 uint64_t n_items, unsigned long long out_cap, uint32_t* out_words, uint32_t dbg,
-                                                 const uint32_t* blkmap) {
+                                                 const uint32_t* counts, const unsigned long long* item_offs,
+                                                 uint64_t n_items, unsigned long long out_cap, const unsigned long long* base,
+                                                 uint32_t* out_words, const uint32_t* blkmap) {
     if (ctrl->overflow) return;
-    if (out_offs[n_items] > out_cap) return;
+    const unsigned long long b0m = base ? *base : 0ull;
+    if (b0m + item_offs[n_items] > out_cap) return;
+    out_words += b0m * 3ull;
     const uint32_t used = min(ctrl->blk_cursor, pool_blocks);
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -335,21 +343,24 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const Scan
             if (b0 + u >= used) continue;
             const uint32_t first = seq[u] * BLK_MATCHES;
             const uint32_t nw = min(BLK_MATCHES, counts[item[u]] - first) * 3;
-            uint32_t* dst = out_words + (out_offs[item[u]] + first) * 3ull;
-            if (dbg & 32u) {  // timing experiment: sequential (wrong) placement
-                if ((b0 + u + 1) * (uint64_t)BLK_MATCHES > out_cap) continue;
-                dst = out_words + (b0 + u) * (uint64_t)(BLK_MATCHES * 3);
-            }
+            uint32_t* dst = out_words + (item_offs[item[u]] + first) * 3ull;
             if (lane < nw) dst[lane] = w0[u];
             if (lane + 32 < nw) dst[lane + 32] = w1[u];
         }
     }
 }
 
-__global__ void k_zero_offsets(unsigned long long* out_offs) { out_offs[0] = 0; }
+// per-haystack offsets of the caller: out_offs[h] = base + item_offs[first item of haystack h]; entry n (the
+// batch's end) only if `last` -- a shard that is not the last one of a gathered result leaves it to its successor
+__global__ void __launch_bounds__(256) k_final_offsets(const unsigned long long* seg_first, const unsigned long long* item_offs,
+                                                        uint64_t n, const unsigned long long* base, int last,
+                                                        unsigned long long* out_offs) {
+    const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < n || (h == n && last)) out_offs[h] = (base ? *base : 0ull) + item_offs[seg_first ? seg_first[h] : h];
+}
 
-// Stream chunks: positions are reported in stream coordinates -- add the position of the chunk's first
-// byte to start and end of every match of that chunk (haystack found by binary search in out_offs).
+// Stream chunks: positions are reported in stream coordinates -- add the position of the chunk's first byte
+// to start and end of every match of that chunk (haystack found by binary search in out_offs).
 __global__ void __launch_bounds__(256) k_add_base(const ScanCtrl* ctrl, const unsigned long long* out_offs, uint64_t n,
                                                    unsigned long long out_cap, const uint32_t* pos_in, uint32_t* out_words) {
     const unsigned long long total = out_offs[n];
@@ -370,12 +381,124 @@ __global__ void __launch_bounds__(256) k_add_base(const ScanCtrl* ctrl, const un
     }
 }
 
-// ---- segment table (intra-haystack chunking for find_overlapping / no_suffix) --------------------
-__global__ void __launch_bounds__(256) k_seg_count(const uint64_t* offs, uint64_t n, uint32_t seg_len, uint32_t seg_from,
-                                                    uint32_t* nseg) {
+// L2 eviction policy descriptors (see c_l2pol in scan_lane.cuh): made once per device
+__global__ void k_make_policies(unsigned long long* out, int hints) {
+    unsigned long long keep, strm;
+    if (hints) {
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(strm));
+    } else {
+        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(keep));
+        strm = keep;
+    }
+    out[0] = keep;
+    out[1] = strm;
+}
+
+// ---- shard groups: the exchange step over NVLink peer memory --------------------------------------
+// Every rank owns one GroupCtl block in its HBM; peers write into it with system-scope releases and the owner
+// polls it locally.  `step` numbers the exchange steps (1, 2, ...); slots alternate by step parity.
+constexpr int kMaxRanks = 16;
+struct GroupCtl {
+    unsigned long long total[2][kMaxRanks];      // matches of rank j at the step named by total_seq
+    unsigned long long total_seq[2][kMaxRanks];
+    unsigned long long done_seq[kMaxRanks];      // gathering rank only: rank j's matches of that step have landed
+    unsigned long long free_seq;                 // the gathering rank has released the result buffer of that step
+    unsigned long long base[2];                  // this rank's first match index at the step (written locally)
+    unsigned long long sum[2];                   // gathering rank: matches of all ranks at the step
+    unsigned long long error;                    // a wait timed out
+};
+struct GroupPeers {
+    GroupCtl* ctl[kMaxRanks];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long kGroupTimeoutNs = 20ull * 1000 * 1000 * 1000;  // a peer that never arrives must not hang the GPU
+
+// this rank's match count of the step goes to every rank's control block
+__global__ void k_group_publish(GroupPeers peers, int world, int rank, unsigned long long step, const unsigned long long* total) {
+    const int j = threadIdx.x;
+    if (j >= world) return;
+    GroupCtl* c = peers.ctl[j];
+    c->total[step & 1][rank] = *total;
+    __threadfence_system();
+    st_release_sys(&c->total_seq[step & 1][rank], step);
+}
+// base = matches of the lower ranks at this step; the result buffer of the previous step must have been released
+__global__ void k_group_wait_base(GroupCtl* mine, int rank, unsigned long long step) {
+    const unsigned long long t0 = global_ns();
+    unsigned long long base = 0;
+    for (int j = 0; j < rank; ++j) {
+        while (ld_acquire_sys(&mine->total_seq[step & 1][j]) != step)
+            if (global_ns() - t0 > kGroupTimeoutNs) {
+                mine->error = 1;
+                break;
+            }
+        base += mine->total[step & 1][j];
+    }
+    if (rank != 0)
+        while (ld_acquire_sys(&mine->free_seq) + 1 < step)
+            if (global_ns() - t0 > kGroupTimeoutNs) {
+                mine->error = 1;
+                break;
+            }
+    mine->base[step & 1] = base;
+}
+__global__ void k_group_signal_done(GroupCtl* gather_ctl, int rank, unsigned long long step) {
+    __threadfence_system();
+    st_release_sys(&gather_ctl->done_seq[rank], step);
+}
+// gathering rank: all ranks' matches of the step have landed in its buffers
+__global__ void k_group_wait_all(GroupCtl* mine, int world, unsigned long long step) {
+    const unsigned long long t0 = global_ns();
+    unsigned long long sum = 0;
+    for (int j = 0; j < world; ++j) {
+        while (ld_acquire_sys(&mine->done_seq[j]) != step)
+            if (global_ns() - t0 > kGroupTimeoutNs) {
+                mine->error = 1;
+                break;
+            }
+        sum += mine->total[step & 1][j];
+    }
+    mine->sum[step & 1] = sum;
+}
+// gathering rank: the result of `step` has been consumed, its buffers may be overwritten
+__global__ void k_group_release(GroupPeers peers, int world, unsigned long long step) {
+    const int j = threadIdx.x;
+    if (j < world) st_release_sys(&peers.ctl[j]->free_seq, step);
+}
+
+// ---- offsets of a device-resident batch are the caller's: check them before anything indexes with them ----
+// ascending, inside text_bytes, no haystack of 4 GiB or more (positions are u32).  A bad batch scans nothing
+// (the item counter is pushed past every item) and the call reports DACH_INVALID_ARGUMENT.
+__global__ void __launch_bounds__(256) k_check_offsets(const uint64_t* offs, uint64_t n, uint64_t text_bytes, ScanCtrl* ctrl) {
     const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= n) return;
-    const uint64_t len = offs[h + 1] - offs[h];
+    const uint64_t a = offs[h], b = offs[h + 1];
+    if (b < a || b - a > 0xffffffffull || b > text_bytes) {
+        ctrl->bad_offsets = 1u;
+        ctrl->next_item = 1ull << 62;
+    }
+}
+
+// ---- segment table (intra-haystack chunking for find_overlapping / no_suffix) --------------------
+__global__ void __launch_bounds__(256) k_seg_count(const uint64_t* offs, uint64_t n, uint32_t seg_len, uint32_t seg_from,
+                                                    uint32_t* nseg, const ScanCtrl* ctrl) {
+    const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n) return;
+    const uint64_t len = ctrl->bad_offsets ? 0 : offs[h + 1] - offs[h];
     const uint64_t k = h < seg_from ? 1 : (len + seg_len - 1) / seg_len;
     nseg[h] = k ? (uint32_t)k : 1u;  // an empty haystack still is one item (ROOT's outputs at position 0)
 }
@@ -392,13 +515,6 @@ __global__ void __launch_bounds__(256) k_seg_fill(const unsigned long long* seg_
         item_hay[first + j] = (uint32_t)h;
         item_beg[first + j] = j * seg_len;
     }
-}
-
-// per-haystack offsets from per-item offsets
-__global__ void __launch_bounds__(256) k_hay_offsets(const unsigned long long* seg_first, const unsigned long long* item_offs,
-                                                      uint64_t n, unsigned long long* out_offs) {
-    const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (h <= n) out_offs[h] = item_offs[seg_first[h]];
 }
 
 }  // namespace dach
@@ -439,13 +555,21 @@ struct HostPinned {
     unsigned long long tail_offs[2];  // offs[seg_from], offs[n]: exact size of the segmented tail
 };
 
-// Everything one in-flight scan needs besides the automaton image.
+// Everything one in-flight scan needs besides the automaton image.  A scan runs in two phases that may sit on
+// different streams: enqueue_scan (items, scan kernel, offsets, block index) and enqueue_place (gather into the
+// caller's -- possibly peer-mapped -- buffers); finish_scan waits for the second and reports.
 struct Workspace {
     DevBuf counts, tiles, ctrl, pool;
-    DevBuf nseg, seg_first, item_hay, item_beg, item_offs, n_items_dev;  // segment table
+    DevBuf nseg, seg_first, item_hay, item_beg, item_offs, n_items_dev;  // segment table, per-item offsets
     DevBuf blk_first, blkmap, tiles2;  // pool blocks in output order (k_blk_index)
     HostPinned* pinned = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // pipeline start, scan end, pipeline end, scan start
+    cudaEvent_t ev_scanned = nullptr, ev_placed = nullptr;
+    // the scan in flight (phase 1 -> phase 2)
+    uint64_t job_n = 0, job_items = 0;
+    uint32_t job_pool_blocks = 0;
+    bool job_seg = false, job_ordered = false, job_open = false;
+    cudaStream_t job_stream = nullptr;
     // host-batch slices only: device staging and the slice's stream
     DevBuf text, offs, out, out_offs;
     void* offs_stage = nullptr;  // pinned staging of the slice's offsets (the caller's array may be pageable)
@@ -456,6 +580,8 @@ struct Workspace {
             return false;
         for (int i = 0; i < 4; ++i)
             if (!ev[i] && !cuda_ok(cudaEventCreate(&ev[i]), "cudaEventCreate")) return false;
+        if (!ev_scanned && !cuda_ok(cudaEventCreateWithFlags(&ev_scanned, cudaEventDisableTiming), "cudaEventCreate")) return false;
+        if (!ev_placed && !cuda_ok(cudaEventCreateWithFlags(&ev_placed, cudaEventDisableTiming), "cudaEventCreate")) return false;
         if (with_stream && !stream && !cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate"))
             return false;
         return true;
@@ -478,6 +604,9 @@ struct Workspace {
                 cudaEventDestroy(ev[i]);
                 ev[i] = nullptr;
             }
+        if (ev_scanned) cudaEventDestroy(ev_scanned);
+        if (ev_placed) cudaEventDestroy(ev_placed);
+        ev_scanned = ev_placed = nullptr;
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr;
     }
@@ -505,37 +634,42 @@ struct dach_dev {
     uint32_t root_base = 0;
     uint32_t* d_mapper = nullptr;
     void* image_base = nullptr;
-    size_t image_alloc = 0, l2_window = 0, l2_persist = 0;
-    // workspace (guarded by mu)
+    size_t image_alloc = 0;
+    // workspaces (guarded by mu; dach_job handles own theirs)
     std::mutex mu;
     Workspace ws;        // dach_dev_scan_batch
     static constexpr int kSlots = 4;
     Workspace slot[kSlots];  // dach_scan_batch_host: slices in flight (H2D of k+1 and k+2 | scan of k | D2H of k-1)
+    // ---- options (dach_dev_set_option) ----
     int64_t opt_slice_mib = 64;
-    // Records of the hot region staged in shared memory by StdMachine3: -1 = as many as fit next to the
-    // event queues (the region is laid out hottest first, so any prefix is the best set of its size), 0 = none
-    int64_t opt_hot_entries = -1;
+    // Records of the hot region staged in shared memory by StdMachine3 (the region is laid out hottest first, so
+    // any prefix is the best set of its size).  Every KiB of shared memory is a KiB less L1 for the records
+    // that are not staged: 4096 records (64 KiB) measured best on the C3 bench (profiles/r2a_ab.txt).
+    // -1 = as many as fit next to the event queues, 0 = none.
+    int64_t opt_hot_entries = 4096;
     int64_t opt_slice_ramp = 1;      // host path: small slices at the head and the tail of a batch
     int64_t opt_tail_seg = 0;        // cut only the last 2 x lanes haystacks of a large batch (measured: -2 %, off)
     int64_t opt_gather_ordered = 1;  // copy pool blocks in output order (sequential writes)
     int64_t opt_gather_u = 4;     // pooled blocks in flight per warp of k_gather (2, 4 or 8)
-    int64_t opt_reserve_sms = 0;  // SMs left free for concurrent kernels (e.g. the NCCL gather of the previous chunk)
-    int64_t opt_dbg = 0;
+    int64_t opt_reserve_sms = 0;  // SMs left free for concurrent kernels
     int64_t opt_seg_len = 0;  // 0: automatic; > 0: forced segment length; < 0: no segmentation
-    // options
-    // Leading records staged in shared memory: -1 = as many as fit, 0 = none.  Default 0: in the
-    // reference's slot order the first slots are not the hot ones and L1 caches the hot states
-    // better on its own (profiles/r1_v1_summary.md: 116 vs 76 GB/s).
-    int64_t opt_hot_records = 0;
+    int64_t opt_hot_records = 0;  // lane-per-haystack kernels: leading wide records staged in shared memory (-1 = as many as fit)
     int64_t opt_threads = 1024;
     int64_t opt_ctas_per_sm = 1;
-    int64_t opt_l2_persist = 1;  // 1: access-policy window over the image during the scan kernel
+    int64_t opt_l2_hints = 1;  // L2 eviction policies: image evict_last, text and match blocks evict_first
     int64_t opt_kernel = 3;  // 3: lane machines, StdMachine3 for the bytewise Standard iterators; 2: StdMachine2 instead;
                              // 1: StdMachine instead; 0: always the lane-per-haystack kernels
     // stats
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
     double last_scan_ms = 0, last_total_ms = 0;
     uint64_t last_h2d = 0, last_d2h = 0;
+};
+
+// one asynchronous scan with its own workspace (dach_job_*)
+struct dach_job {
+    dach_dev* d = nullptr;
+    Workspace W;
+    uint64_t out_cap = ~0ull;  // capacity the placement was given (for the overflow report)
 };
 
 namespace {
@@ -566,82 +700,59 @@ cudaError_t launch_scan_t(const ScanParams& P, int grid, int threads, size_t sme
     return cudaGetLastError();
 }
 
-struct L2Window {
-    void* base = nullptr;
-    size_t bytes = 0;
-    float hit_ratio = 1.0f;
-};
-
 template <class M, class LANE, int MAXT, int MINB, bool HOT>
-cudaError_t launch_machine_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
+cudaError_t launch_machine_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
     static bool attr_done[kMaxDevices] = {};  // per instantiation and per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= kMaxDevices || !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_scan_machine<M, LANE, MAXT, MINB, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_scan_machine<M, LANE, MAXT, MINB, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < kMaxDevices) attr_done[dev] = true;
     }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(threads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    if (w.bytes) {
-        // keep the automaton image resident in L2 while text and match blocks stream through it
-        at[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        at[0].val.accessPolicyWindow.base_ptr = w.base;
-        at[0].val.accessPolicyWindow.num_bytes = w.bytes;
-        at[0].val.accessPolicyWindow.hitRatio = w.hit_ratio;
-        at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-    }
-    return cudaLaunchKernelEx(&cfg, k_scan_machine<M, LANE, MAXT, MINB, HOT>, P);
+    k_scan_machine<M, LANE, MAXT, MINB, HOT><<<grid, threads, smem, st>>>(P);
+    return cudaGetLastError();
 }
 
 template <template <int> class M, class LANE, int MAXT, int MINB, bool HOT>
-cudaError_t launch_std_modes(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
+cudaError_t launch_std_modes(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
     switch (mode) {
-        case M_FIND: return launch_machine_t<M<M_FIND>, LANE, MAXT, MINB, HOT>(P, grid, threads, smem, st, w);
-        case M_NO_SUFFIX: return launch_machine_t<M<M_NO_SUFFIX>, LANE, MAXT, MINB, HOT>(P, grid, threads, smem, st, w);
-        case M_OVERLAPPING: return launch_machine_t<M<M_OVERLAPPING>, LANE, MAXT, MINB, HOT>(P, grid, threads, smem, st, w);
+        case M_FIND: return launch_machine_t<M<M_FIND>, LANE, MAXT, MINB, HOT>(P, grid, threads, smem, st);
+        case M_NO_SUFFIX: return launch_machine_t<M<M_NO_SUFFIX>, LANE, MAXT, MINB, HOT>(P, grid, threads, smem, st);
+        case M_OVERLAPPING: return launch_machine_t<M<M_OVERLAPPING>, LANE, MAXT, MINB, HOT>(P, grid, threads, smem, st);
     }
     return cudaErrorInvalidValue;
 }
 
 // bytewise Standard iterators: which = 3 StdMachine3 (hot records in shared memory if P.hot_entries), 2 StdMachine2,
 // 1 StdMachine; dense = two CTAs of up to 768 threads per SM (40 registers) instead of one of 1024
-cudaError_t launch_std(int which, int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w,
+cudaError_t launch_std(int which, int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st,
                        bool dense) {
     if (which >= 3) {
         if (P.hot_entries)
-            return dense ? launch_std_modes<StdMachine3, Lane3, 768, 2, true>(mode, P, grid, threads, smem, st, w)
-                         : launch_std_modes<StdMachine3, Lane3, 1024, 1, true>(mode, P, grid, threads, smem, st, w);
-        return dense ? launch_std_modes<StdMachine3, Lane3, 768, 2, false>(mode, P, grid, threads, smem, st, w)
-                     : launch_std_modes<StdMachine3, Lane3, 1024, 1, false>(mode, P, grid, threads, smem, st, w);
+            return dense ? launch_std_modes<StdMachine3, Lane3, 768, 2, true>(mode, P, grid, threads, smem, st)
+                         : launch_std_modes<StdMachine3, Lane3, 1024, 1, true>(mode, P, grid, threads, smem, st);
+        return dense ? launch_std_modes<StdMachine3, Lane3, 768, 2, false>(mode, P, grid, threads, smem, st)
+                     : launch_std_modes<StdMachine3, Lane3, 1024, 1, false>(mode, P, grid, threads, smem, st);
     }
     if (which == 2)
-        return dense ? launch_std_modes<StdMachine2, Lane2, 768, 2, false>(mode, P, grid, threads, smem, st, w)
-                     : launch_std_modes<StdMachine2, Lane2, 1024, 1, false>(mode, P, grid, threads, smem, st, w);
-    return dense ? launch_std_modes<StdMachine, LaneStd, 768, 2, false>(mode, P, grid, threads, smem, st, w)
-                 : launch_std_modes<StdMachine, LaneStd, 1024, 1, false>(mode, P, grid, threads, smem, st, w);
+        return dense ? launch_std_modes<StdMachine2, Lane2, 768, 2, false>(mode, P, grid, threads, smem, st)
+                     : launch_std_modes<StdMachine2, Lane2, 1024, 1, false>(mode, P, grid, threads, smem, st);
+    return dense ? launch_std_modes<StdMachine, LaneStd, 768, 2, false>(mode, P, grid, threads, smem, st)
+                 : launch_std_modes<StdMachine, LaneStd, 1024, 1, false>(mode, P, grid, threads, smem, st);
 }
 
-cudaError_t launch_cw(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
+cudaError_t launch_cw(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
     switch (mode) {
-        case M_FIND: return launch_machine_t<CwMachine<M_FIND>, LaneCw, 1024, 1, false>(P, grid, threads, smem, st, w);
-        case M_OVERLAPPING: return launch_machine_t<CwMachine<M_OVERLAPPING>, LaneCw, 1024, 1, false>(P, grid, threads, smem, st, w);
-        case M_NO_SUFFIX: return launch_machine_t<CwMachine<M_NO_SUFFIX>, LaneCw, 1024, 1, false>(P, grid, threads, smem, st, w);
-        default: return launch_machine_t<CwMachine<M_LEFTMOST>, LaneCw, 1024, 1, false>(P, grid, threads, smem, st, w);
+        case M_FIND: return launch_machine_t<CwMachine<M_FIND>, LaneCw, 1024, 1, false>(P, grid, threads, smem, st);
+        case M_OVERLAPPING: return launch_machine_t<CwMachine<M_OVERLAPPING>, LaneCw, 1024, 1, false>(P, grid, threads, smem, st);
+        case M_NO_SUFFIX: return launch_machine_t<CwMachine<M_NO_SUFFIX>, LaneCw, 1024, 1, false>(P, grid, threads, smem, st);
+        default: return launch_machine_t<CwMachine<M_LEFTMOST>, LaneCw, 1024, 1, false>(P, grid, threads, smem, st);
     }
 }
 
-cudaError_t launch_lm(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st, const L2Window& w) {
-    return launch_machine_t<LmMachine, LaneLm, 1024, 1, false>(P, grid, threads, smem, st, w);
+cudaError_t launch_lm(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
+    return launch_machine_t<LmMachine, LaneLm, 1024, 1, false>(P, grid, threads, smem, st);
 }
 
 cudaError_t launch_scan(bool cw, int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
@@ -671,21 +782,43 @@ int check_mode(const dach_dev* d, int mode) {
     return DACH_OK;
 }
 
-// the device-side pipeline; caller holds d->mu and has set the device
-// d_text + d_offs[i] addresses haystack i; text_end is one past the last text byte on the device;
-// text_bytes is the number of text bytes this call covers (sizing only).
-int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, const uint8_t* text_lo, const uint8_t* text_end, uint64_t text_bytes,
-                const uint64_t* d_offs, uint64_t n, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs, uint64_t* needed, cudaStream_t st,
-                uint32_t* d_state_io = nullptr, const uint32_t* d_pos_in = nullptr) {
+// L2 policy descriptors of this device (c_l2pol): made by a one-thread kernel, kept in constant memory
+bool install_policies(int hints) {
+    unsigned long long* d_pol = nullptr;
+    unsigned long long h_pol[2] = {0, 0};
+    if (!cuda_ok(cudaMalloc(reinterpret_cast<void**>(&d_pol), 16), "cudaMalloc policies")) return false;
+    k_make_policies<<<1, 1>>>(d_pol, hints);
+    bool ok = cuda_ok(cudaMemcpy(h_pol, d_pol, 16, cudaMemcpyDeviceToHost), "read policies");
+    cudaFree(d_pol);
+    return ok && cuda_ok(cudaMemcpyToSymbol(c_l2pol, h_pol, 16), "install policies");
+}
+
+// ---- phase 1: items, scan kernel, per-item offsets, block index.  No synchronisation. ------------------
+// d_text + d_offs[i] addresses haystack i; [text_lo, text_end) bounds what may be read; text_bytes is the
+// number of text bytes this call covers (sizing only); cap_matches sizes the block pool.
+int enqueue_scan(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, const uint8_t* text_lo, const uint8_t* text_end,
+                 uint64_t text_bytes, const uint64_t* d_offs, uint64_t n, uint64_t cap_matches, cudaStream_t st,
+                 uint32_t* d_state_io = nullptr) {
     if (n > 0xfffffff0ull) {
         set_error("too many haystacks in one batch (max 2^32-16)");
         return DACH_INVALID_ARGUMENT;
     }
+    // the previous placement out of this workspace must be done before its buffers are rewritten
+    if (W.job_open && W.job_stream != st) cudaStreamWaitEvent(st, W.ev_placed, 0);
+    W.job_n = n;
+    W.job_items = n;
+    W.job_seg = false;
+    W.job_ordered = false;
+    W.job_stream = st;
+    W.job_open = true;
+    if (!ensure(W.ctrl, sizeof(ScanCtrl)) || !ensure(W.item_offs, 16)) return DACH_CUDA_ERROR;
+    if (!cuda_ok(cudaMemsetAsync(W.ctrl.p, 0, sizeof(ScanCtrl), st), "memset ctrl")) return DACH_CUDA_ERROR;
+    cudaEventRecord(W.ev[0], st);
+    cudaEventRecord(W.ev[3], st);
     if (n == 0) {
-        k_zero_offsets<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(d_out_offs));
-        ++d->launches;
-        if (!cuda_ok(cudaStreamSynchronize(st), "sync")) return DACH_CUDA_ERROR;
-        if (needed) *needed = 0;
+        cudaMemsetAsync(W.item_offs.p, 0, 8, st);
+        cudaEventRecord(W.ev[1], st);
+        cudaEventRecord(W.ev_scanned, st);
         return DACH_OK;
     }
     int threads = (int)std::min<int64_t>(std::max<int64_t>(d->opt_threads, 32), kMaxThreads);
@@ -747,15 +880,14 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
         }
     }
     const uint64_t n_tiles = (n_items_max + kScanTile - 1) / kScanTile;
-    uint64_t pool_blocks64 = out_cap / BLK_MATCHES + n_items_max + 1024;
+    uint64_t pool_blocks64 = cap_matches / BLK_MATCHES + n_items_max + 1024;
     if (pool_blocks64 > 0xffffff00ull) pool_blocks64 = 0xffffff00ull;
     const uint32_t pool_blocks = (uint32_t)pool_blocks64;
-    if (!ensure(W.counts, n_items_max * 4) || !ensure(W.tiles, n_tiles * 8) || !ensure(W.ctrl, sizeof(ScanCtrl)) ||
+    if (!ensure(W.counts, n_items_max * 4) || !ensure(W.tiles, n_tiles * 8) || !ensure(W.item_offs, (n_items_max + 1) * 8) ||
         !ensure(W.pool, (size_t)pool_blocks * BLK_WORDS * 4))
         return DACH_CUDA_ERROR;
     if (seg && (!ensure(W.nseg, n * 4) || !ensure(W.seg_first, (n + 1) * 8) || !ensure(W.item_hay, n_items_max * 4) ||
-                !ensure(W.item_beg, n_items_max * 4) || !ensure(W.item_offs, (n_items_max + 1) * 8) ||
-                !ensure(W.n_items_dev, 8)))
+                !ensure(W.item_beg, n_items_max * 4) || !ensure(W.n_items_dev, 8)))
         return DACH_CUDA_ERROR;
 
     ScanParams P;
@@ -781,25 +913,22 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     P.pool = static_cast<uint32_t*>(W.pool.p);
     P.pool_blocks = pool_blocks;
     P.ctrl = static_cast<ScanCtrl*>(W.ctrl.p);
-    P.dbg = (uint32_t)d->opt_dbg;
     P.state_io = d_state_io;
 
     const size_t smem_budget = std::min<size_t>(d->smem_optin, 226 * 1024) / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
     size_t smem;
-    uint32_t hot_entries = 0;
     if (v1) {
         const size_t queues = (size_t)LANE_Q * threads * sizeof(QEntry);
-        // StdMachine3: as much of the hot region as fits next to the queues (whole 256-slot blocks)
+        // StdMachine3: the front of the hot region next to the queues (whole 256-slot blocks)
         uint64_t want = 0;
         if (std3 && d->opt_hot_entries != 0 && smem_budget > queues + 512) {
             want = std::min<uint64_t>(d->hot_slots, (smem_budget - queues - 512) / 16);
             if (d->opt_hot_entries > 0) want = std::min<uint64_t>(want, (uint64_t)d->opt_hot_entries);
             want &= ~uint64_t(255);
         }
-        hot_entries = (uint32_t)want;
-        smem = (size_t)hot_entries * 16 + queues;
+        smem = (size_t)want * 16 + queues;
         P.hot_n = 0;
-        P.hot_entries = hot_entries;
+        P.hot_entries = (uint32_t)want;
     } else {
         uint64_t hot = smem_budget > kRootBytes ? (smem_budget - kRootBytes) / 16 : 0;
         if (d->opt_hot_records >= 0) hot = std::min<uint64_t>(hot, (uint64_t)d->opt_hot_records);
@@ -808,19 +937,18 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
         smem = kRootBytes + (size_t)hot * 16;
     }
 
-    unsigned long long* offs64 = reinterpret_cast<unsigned long long*>(d_out_offs);
     unsigned long long* tiles = static_cast<unsigned long long*>(W.tiles.p);
     unsigned long long* seg_first = static_cast<unsigned long long*>(W.seg_first.p);
-    unsigned long long* item_offs = seg ? static_cast<unsigned long long*>(W.item_offs.p) : offs64;
-    if (!cuda_ok(cudaMemsetAsync(W.ctrl.p, 0, sizeof(ScanCtrl), st), "memset ctrl")) return DACH_CUDA_ERROR;
-    cudaEventRecord(W.ev[0], st);
+    unsigned long long* item_offs = static_cast<unsigned long long*>(W.item_offs.p);
+    k_check_offsets<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_offs, n, (uint64_t)(text_end - d_text), P.ctrl);
+    ++d->launches;
     if (seg) {
         // segment table: counts per haystack -> first item per haystack -> (haystack, begin) per item
         const unsigned hb = (unsigned)((n + 255) / 256), hb1 = (unsigned)((n + 1 + 255) / 256);
         const uint64_t nt = (n + kScanTile - 1) / kScanTile;
         uint32_t* nseg = static_cast<uint32_t*>(W.nseg.p);
         cudaMemsetAsync(W.counts.p, 0, n_items_max * 4, st);  // items past the real count stay empty
-        k_seg_count<<<hb, 256, 0, st>>>(d_offs, n, seg_len, seg_from, nseg);
+        k_seg_count<<<hb, 256, 0, st>>>(d_offs, n, seg_len, seg_from, nseg, P.ctrl);
         k_offsets_tile_sums<false><<<(unsigned)nt, kScanThreads, 0, st>>>(nseg, n, tiles);
         k_offsets_scan_tiles<<<1, kScanThreads, 0, st>>>(tiles, nt);
         k_offsets_apply<false><<<(unsigned)nt, kScanThreads, 0, st>>>(nseg, n, tiles, seg_first);
@@ -834,29 +962,22 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
         P.seg_from = seg_from;
         P.warm = d->max_pattern_len ? d->max_pattern_len - 1 : 0;
     }
-    L2Window win;
-    if (d->opt_l2_persist && d->l2_persist > 0 && v1) {
-        // the lane-machine kernels touch the compact records, the opos table and the outputs
-        win.base = d->d_outputs;
-        win.bytes = std::min<size_t>(d->l2_window, (size_t)((char*)d->image_base + d->image_alloc - (char*)d->d_outputs));
-        win.hit_ratio = (float)std::min(1.0, (double)d->l2_persist / (double)win.bytes);
-    }
     cudaEventRecord(W.ev[3], st);
-    if (!cuda_ok(cw_machine   ? launch_cw(mode, P, grid, std::min(threads, 1024), smem, st, win)
-                 : lm_machine ? launch_lm(P, grid, std::min(threads, 1024), smem, st, win)
-                 : v1         ? launch_std(std3 ? 3 : std2 ? 2 : 1, mode, P, grid, threads, smem, st, win,
+    if (!cuda_ok(cw_machine   ? launch_cw(mode, P, grid, std::min(threads, 1024), smem, st)
+                 : lm_machine ? launch_lm(P, grid, std::min(threads, 1024), smem, st)
+                 : v1         ? launch_std(std3 ? 3 : std2 ? 2 : 1, mode, P, grid, threads, smem, st,
                                            ctas_per_sm >= 2 && threads <= 768 && grid % 2 == 0)
-                            : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
+                              : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
                  "k_scan launch"))
         return DACH_CUDA_ERROR;
     cudaEventRecord(W.ev[1], st);
     k_offsets_tile_sums<false><<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n_items_max, tiles);
     k_offsets_scan_tiles<<<1, kScanThreads, 0, st>>>(tiles, n_tiles);
     k_offsets_apply<false><<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n_items_max, tiles, item_offs);
-    const int gather_grid = d->sm_count * 8;
-    const uint32_t* blkmap = nullptr;
+    d->launches += 4;
     // batches whose match blocks stay in L2 anyway are copied in pool order (four launches fewer)
-    if (d->opt_gather_ordered >= 2 || (d->opt_gather_ordered == 1 && text_bytes >= (256ull << 20))) {
+    const bool ordered = d->opt_gather_ordered >= 2 || (d->opt_gather_ordered == 1 && text_bytes >= (256ull << 20));
+    if (ordered) {
         if (!ensure(W.blk_first, (n_items_max + 1) * 8) || !ensure(W.blkmap, (size_t)pool_blocks * 4) || !ensure(W.tiles2, n_tiles * 8))
             return DACH_CUDA_ERROR;
         unsigned long long* tiles2 = static_cast<unsigned long long*>(W.tiles2.p);
@@ -864,42 +985,77 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
         k_offsets_tile_sums<true><<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n_items_max, tiles2);
         k_offsets_scan_tiles<<<1, kScanThreads, 0, st>>>(tiles2, n_tiles);
         k_offsets_apply<true><<<(unsigned)n_tiles, kScanThreads, 0, st>>>(P.counts, n_items_max, tiles2, blk_first);
-        k_blk_index<<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, blk_first, static_cast<uint32_t*>(W.blkmap.p));
+        k_blk_index<<<d->sm_count * 8, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, blk_first, static_cast<uint32_t*>(W.blkmap.p));
         d->launches += 4;
-        blkmap = static_cast<const uint32_t*>(W.blkmap.p);
     }
-    if (d->opt_gather_u >= 8)
-        k_gather<8><<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, item_offs, n_items_max, out_cap,
-                                                reinterpret_cast<uint32_t*>(d_out), P.dbg, blkmap);
-    else if (d->opt_gather_u <= 2)
-        k_gather<2><<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, item_offs, n_items_max, out_cap,
-                                                reinterpret_cast<uint32_t*>(d_out), P.dbg, blkmap);
-    else
-        k_gather<4><<<gather_grid, 256, 0, st>>>(P.pool, P.ctrl, pool_blocks, P.counts, item_offs, n_items_max, out_cap,
-                                                reinterpret_cast<uint32_t*>(d_out), P.dbg, blkmap);
-    d->launches += 5;
-    if (seg) {
-        k_hay_offsets<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(seg_first, item_offs, n, offs64);
-        d->launches += 1;
+    if (!cuda_ok(cudaGetLastError(), "kernel launch")) return DACH_CUDA_ERROR;
+    cudaEventRecord(W.ev_scanned, st);
+    W.job_items = n_items_max;
+    W.job_seg = seg;
+    W.job_ordered = ordered;
+    W.job_pool_blocks = pool_blocks;
+    return DACH_OK;
+}
+
+// ---- phase 2: gather into the caller's buffers.  No synchronisation. -----------------------------------
+// d_out / d_out_offs may be peer-mapped memory of another GPU.  d_base (device pointer or nullptr): index of
+// this batch's first match in d_out, added to the offsets too; `last`: also write out_offs[n].
+int enqueue_place(dach_dev* d, Workspace& W, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs,
+                  const unsigned long long* d_base, bool last, cudaStream_t st, const uint32_t* d_pos_in = nullptr) {
+    if (!W.job_open) {
+        set_error("no scan to place");
+        return DACH_INVALID_ARGUMENT;
     }
-    if (d_pos_in) {
-        k_add_base<<<gather_grid, 256, 0, st>>>(P.ctrl, offs64, n, out_cap, d_pos_in, reinterpret_cast<uint32_t*>(d_out));
-        d->launches += 1;
+    if (st != W.job_stream) cudaStreamWaitEvent(st, W.ev_scanned, 0);
+    const uint64_t n = W.job_n, n_items = W.job_items;
+    const ScanCtrl* ctrl = static_cast<const ScanCtrl*>(W.ctrl.p);
+    const unsigned long long* item_offs = static_cast<const unsigned long long*>(W.item_offs.p);
+    unsigned long long* offs64 = reinterpret_cast<unsigned long long*>(d_out_offs);
+    const int gather_grid = d->sm_count * 8;
+    if (n) {
+        const uint32_t* pool = static_cast<const uint32_t*>(W.pool.p);
+        const uint32_t* counts = static_cast<const uint32_t*>(W.counts.p);
+        const uint32_t* blkmap = W.job_ordered ? static_cast<const uint32_t*>(W.blkmap.p) : nullptr;
+        uint32_t* out_words = reinterpret_cast<uint32_t*>(d_out);
+        if (d->opt_gather_u >= 8)
+            k_gather<8><<<gather_grid, 256, 0, st>>>(pool, ctrl, W.job_pool_blocks, counts, item_offs, n_items, out_cap, d_base, out_words, blkmap);
+        else if (d->opt_gather_u <= 2)
+            k_gather<2><<<gather_grid, 256, 0, st>>>(pool, ctrl, W.job_pool_blocks, counts, item_offs, n_items, out_cap, d_base, out_words, blkmap);
+        else
+            k_gather<4><<<gather_grid, 256, 0, st>>>(pool, ctrl, W.job_pool_blocks, counts, item_offs, n_items, out_cap, d_base, out_words, blkmap);
+        ++d->launches;
+    }
+    k_final_offsets<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(
+        W.job_seg ? static_cast<const unsigned long long*>(W.seg_first.p) : nullptr, item_offs, n, d_base, last ? 1 : 0, offs64);
+    ++d->launches;
+    if (d_pos_in && n) {
+        k_add_base<<<gather_grid, 256, 0, st>>>(ctrl, offs64, n, out_cap, d_pos_in, reinterpret_cast<uint32_t*>(d_out));
+        ++d->launches;
     }
     if (!cuda_ok(cudaGetLastError(), "kernel launch")) return DACH_CUDA_ERROR;
     cudaEventRecord(W.ev[2], st);
-    cudaMemcpyAsync(&W.pinned->total, offs64 + n, 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&W.pinned->total, item_offs + n_items, 8, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&W.pinned->ctrl, W.ctrl.p, sizeof(ScanCtrl), cudaMemcpyDeviceToHost, st);
-    if (!cuda_ok(cudaStreamSynchronize(st), "scan pipeline")) return DACH_CUDA_ERROR;
+    cudaEventRecord(W.ev_placed, st);
+    return DACH_OK;
+}
+
+// ---- wait for the placement, report ----------------------------------------------------------------------
+int finish_scan(dach_dev* d, Workspace& W, uint64_t out_cap, uint64_t* needed) {
+    if (!cuda_ok(cudaEventSynchronize(W.ev_placed), "scan pipeline")) return DACH_CUDA_ERROR;
     float ms = 0;
     if (cudaEventElapsedTime(&ms, W.ev[3], W.ev[1]) == cudaSuccess) d->last_scan_ms = ms;
-    if (cudaEventElapsedTime(&ms, W.ev[0], W.ev[2]) == cudaSuccess) d->last_total_ms = ms;
+    if (W.job_stream && cudaEventElapsedTime(&ms, W.ev[0], W.ev[2]) == cudaSuccess) d->last_total_ms = ms;
     const uint64_t total = W.pinned->total;
     if (needed) *needed = total;
+    if (W.pinned->ctrl.bad_offsets) {
+        set_error("haystack offsets must be ascending and inside text_bytes, and no haystack may reach 4 GiB (match positions are u32)");
+        return DACH_INVALID_ARGUMENT;
+    }
     if (W.pinned->ctrl.overflow || total > out_cap) {
         char buf[256];
         snprintf(buf, sizeof(buf), "output capacity too small (needed %llu, out_cap %llu, pool blocks used %u of %u, overflow flag %u)",
-                 (unsigned long long)total, (unsigned long long)out_cap, W.pinned->ctrl.blk_cursor, pool_blocks,
+                 (unsigned long long)total, (unsigned long long)out_cap, W.pinned->ctrl.blk_cursor, W.job_pool_blocks,
                  W.pinned->ctrl.overflow);
         set_error(buf);
         return DACH_OUTPUT_OVERFLOW;
@@ -907,137 +1063,18 @@ int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, cons
     return DACH_OK;
 }
 
-}  // namespace
-
-extern "C" {
-
-int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
-    if (!out) return DACH_INVALID_ARGUMENT;
-    *out = nullptr;
-    if (!pma) {
-        set_error("null automaton");
-        return DACH_INVALID_ARGUMENT;
-    }
-    HostImage img;
-    const int rc = build_image(pma, &img);
+// the synchronous pipeline on one stream; caller holds d->mu (or owns W) and has set the device
+int scan_locked(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, const uint8_t* text_lo, const uint8_t* text_end, uint64_t text_bytes,
+                const uint64_t* d_offs, uint64_t n, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs, uint64_t* needed, cudaStream_t st,
+                uint32_t* d_state_io = nullptr, const uint32_t* d_pos_in = nullptr) {
+    int rc = enqueue_scan(d, W, mode, d_text, text_lo, text_end, text_bytes, d_offs, n, out_cap, st, d_state_io);
     if (rc) return rc;
-    int ndev = 0;
-    if (!cuda_ok(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount")) return DACH_CUDA_ERROR;
-    if (device < 0 || device >= ndev) {
-        set_error("no such CUDA device");
-        return DACH_CUDA_ERROR;
-    }
-    DeviceGuard g(device);
-    if (!g.ok) return DACH_CUDA_ERROR;
-    std::unique_ptr<dach_dev> d(new dach_dev());
-    d->device = device;
-    d->charwise = img.charwise;
-    d->match_kind = img.match_kind;
-    d->n_slots = img.n_slots;
-    d->root_opos = img.root_opos;
-    d->max_pattern_len = img.max_pattern_len;
-    d->mapper_len = (uint32_t)img.mapper.size();
-    cudaDeviceProp prop;
-    if (!cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return DACH_CUDA_ERROR;
-    d->sm_count = prop.multiProcessorCount;
-    d->smem_optin = prop.sharedMemPerBlockOptin;
-    // one allocation for the whole image (records | outputs | root rows | mapper), 256-byte aligned
-    // parts, so that a single L2 access-policy window can cover it
-    constexpr int kParts = 8;
-    const std::vector<uint32_t>* parts[kParts] = {&img.rec, &img.outputs, &img.root_table, &img.mapper, &img.crec, &img.opos_tab,
-                                                   &img.new_of_old, &img.old_of_new};
-    size_t part_off[kParts], total = 0;
-    for (int i = 0; i < kParts; ++i) {
-        part_off[i] = total;
-        total += (std::max<size_t>(parts[i]->size() * 4, 16) + 511) & ~size_t(511);
-        d->image_bytes += parts[i]->size() * 4;
-    }
-    bool ok = cuda_ok(cudaMalloc(&d->image_base, total), "cudaMalloc image");
-    d->image_alloc = total;
-    for (int i = 0; ok && i < kParts; ++i)
-        if (!parts[i]->empty())
-            ok = cuda_ok(cudaMemcpy(static_cast<char*>(d->image_base) + part_off[i], parts[i]->data(), parts[i]->size() * 4,
-                                    cudaMemcpyHostToDevice),
-                         "upload image");
-    if (ok) {
-        char* b = static_cast<char*>(d->image_base);
-        d->d_rec = reinterpret_cast<uint4*>(b + part_off[0]);
-        d->d_outputs = reinterpret_cast<uint4*>(b + part_off[1]);
-        d->d_root = reinterpret_cast<uint32_t*>(b + part_off[2]);
-        d->d_mapper = reinterpret_cast<uint32_t*>(b + part_off[3]);
-        if (!img.crec.empty()) {
-            d->d_crec = reinterpret_cast<uint4*>(b + part_off[4]);
-            d->d_opos = reinterpret_cast<uint32_t*>(b + part_off[5]);
-            if (img.hot_slots) {  // the compact image is renumbered: stream chunks translate state ids
-                d->d_id_in = reinterpret_cast<uint32_t*>(b + part_off[6]);
-                d->d_id_out = reinterpret_cast<uint32_t*>(b + part_off[7]);
-            }
-            d->hot_slots = img.hot_slots;
-        }
-        d->root_base = img.root_base;
-        // let the automaton persist in L2 while text and match streams pass through it
-        d->l2_window = std::min<size_t>(total, (size_t)prop.accessPolicyMaxWindowSize);
-        d->l2_persist = std::min<size_t>(d->l2_window, (size_t)prop.persistingL2CacheMaxSize);
-        if (d->l2_persist) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, d->l2_persist);
-        cudaGetLastError();
-    }
-    ok = ok && d->ws.init(false);
-    if (!ok) {
-        dach_dev_free(d.release());
-        return DACH_CUDA_ERROR;
-    }
-    *out = d.release();
-    return DACH_OK;
-}
-
-void dach_dev_free(dach_dev* d) {
-    if (!d) return;
-    DeviceGuard g(d->device);
-    cudaFree(d->image_base);
-    d->ws.release();
-    for (Workspace& w : d->slot) w.release();
-    delete d;
-}
-
-size_t dach_dev_image_bytes(const dach_dev* d) { return d ? d->image_bytes : 0; }
-
-int dach_dev_scan_batch(dach_dev* d, int mode, const uint8_t* d_text, const uint64_t* d_offs, uint64_t n,
-                        uint64_t text_bytes, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs,
-                        uint64_t* needed, void* stream) {
-    if (!d || !d_offs || !d_out_offs || (out_cap && !d_out)) {
-        set_error("null argument");
-        return DACH_INVALID_ARGUMENT;
-    }
-    const int rc = check_mode(d, mode);
+    rc = enqueue_place(d, W, d_out, out_cap, d_out_offs, nullptr, true, st, d_pos_in);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(d->mu);
-    DeviceGuard g(d->device);
-    if (!g.ok) return DACH_CUDA_ERROR;
-    return scan_locked(d, d->ws, mode, d_text, d_text, d_text + text_bytes, text_bytes, d_offs, n, d_out, out_cap, d_out_offs, needed,
-                       static_cast<cudaStream_t>(stream));
+    return finish_scan(d, W, out_cap, needed);
 }
 
-int dach_dev_scan_stream(dach_dev* d, int mode, const uint8_t* d_text, const uint64_t* d_offs, uint64_t n, uint64_t text_bytes,
-                         uint32_t* d_state, const uint32_t* d_pos, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs,
-                         uint64_t* needed, void* stream) {
-    if (!d || !d_offs || !d_out_offs || !d_state || (out_cap && !d_out)) {
-        set_error("null argument");
-        return DACH_INVALID_ARGUMENT;
-    }
-    if (mode != DACH_FIND && mode != DACH_FIND_OVERLAPPING) {
-        set_error("stream chunks: mode must be DACH_FIND or DACH_FIND_OVERLAPPING (the crate's two steppers)");
-        return DACH_INVALID_ARGUMENT;
-    }
-    const int rc = check_mode(d, mode);
-    if (rc) return rc;
-    std::lock_guard<std::mutex> lk(d->mu);
-    DeviceGuard g(d->device);
-    if (!g.ok) return DACH_CUDA_ERROR;
-    return scan_locked(d, d->ws, mode, d_text, d_text, d_text + text_bytes, text_bytes, d_offs, n, d_out, out_cap, d_out_offs, needed,
-                       static_cast<cudaStream_t>(stream), d_state, d_pos);
-}
-
-int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint64_t* offs, uint64_t n,
+int scan_batch_host_impl(dach_dev* d, int mode, const uint8_t* text, const uint64_t* offs, uint64_t n,
                          dach_match* out, uint64_t out_cap, uint64_t* out_offs, uint64_t* needed) {
     if (!d || !offs || !out_offs || (out_cap && !out)) {
         set_error("null argument");
@@ -1054,11 +1091,25 @@ int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint6
         if (needed) *needed = 0;
         return DACH_OK;
     }
-    for (uint64_t i = 0; i < n; ++i)
+    for (uint64_t i = 0; i < n; ++i) {
         if (offs[i + 1] < offs[i]) {
             set_error("haystack offsets must be ascending");
             return DACH_INVALID_ARGUMENT;
         }
+        if (offs[i + 1] - offs[i] > 0xffffffffull) {
+            set_error("a haystack is longer than 4 GiB - 1 (match positions are u32)");
+            return DACH_INVALID_ARGUMENT;
+        }
+    }
+    // whatever is still queued on the slots' streams reads the caller's text or writes the caller's buffers:
+    // no exit from here on may leave it in flight
+    struct Drain {
+        dach_dev* d;
+        ~Drain() {
+            for (Workspace& w : d->slot)
+                if (w.stream) cudaStreamSynchronize(w.stream);
+        }
+    } drain_on_exit{d};
     // Slices of ~slice_mib MiB of text, three in flight: while slice k is scanned, slice k+1 is
     // on its way to the device and the matches of slice k-1 are on their way back.
     const uint64_t slice_bytes = (uint64_t)std::max<int64_t>(d->opt_slice_mib, 1) << 20;
@@ -1205,7 +1256,450 @@ int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint6
     return DACH_OK;
 }
 
-uint64_t dach_dev_kernel_launches(const dach_dev* d) { return d ? d->launches : 0; }
+// maps every exception to a status: nothing may unwind through the C ABI
+template <class F>
+int guarded(F&& f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc&) {
+        set_error("out of memory");
+        return DACH_AUTOMATON_SCALE;
+    } catch (const std::exception& e) {
+        set_error(std::string("internal error: ") + e.what());
+        return DACH_INVALID_ARGUMENT;
+    } catch (...) {
+        set_error("internal error");
+        return DACH_INVALID_ARGUMENT;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
+    if (!out) return DACH_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!pma) {
+        set_error("null automaton");
+        return DACH_INVALID_ARGUMENT;
+    }
+    return guarded([&]() -> int {
+        HostImage img;
+        const int rc = build_image(pma, &img);
+        if (rc) return rc;
+        int ndev = 0;
+        if (!cuda_ok(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount")) return DACH_CUDA_ERROR;
+        if (device < 0 || device >= ndev) {
+            set_error("no such CUDA device");
+            return DACH_CUDA_ERROR;
+        }
+        DeviceGuard g(device);
+        if (!g.ok) return DACH_CUDA_ERROR;
+        std::unique_ptr<dach_dev> d(new dach_dev());
+        d->device = device;
+        d->charwise = img.charwise;
+        d->match_kind = img.match_kind;
+        d->n_slots = img.n_slots;
+        d->root_opos = img.root_opos;
+        d->max_pattern_len = img.max_pattern_len;
+        d->mapper_len = (uint32_t)img.mapper.size();
+        cudaDeviceProp prop;
+        if (!cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return DACH_CUDA_ERROR;
+        d->sm_count = prop.multiProcessorCount;
+        d->smem_optin = prop.sharedMemPerBlockOptin;
+        // one allocation for the whole image, 512-byte aligned parts
+        constexpr int kParts = 8;
+        const std::vector<uint32_t>* parts[kParts] = {&img.rec, &img.outputs, &img.root_table, &img.mapper, &img.crec, &img.opos_tab,
+                                                       &img.new_of_old, &img.old_of_new};
+        size_t part_off[kParts], total = 0;
+        for (int i = 0; i < kParts; ++i) {
+            part_off[i] = total;
+            total += (std::max<size_t>(parts[i]->size() * 4, 16) + 511) & ~size_t(511);
+            d->image_bytes += parts[i]->size() * 4;
+        }
+        bool ok = cuda_ok(cudaMalloc(&d->image_base, total), "cudaMalloc image");
+        d->image_alloc = total;
+        for (int i = 0; ok && i < kParts; ++i)
+            if (!parts[i]->empty())
+                ok = cuda_ok(cudaMemcpy(static_cast<char*>(d->image_base) + part_off[i], parts[i]->data(), parts[i]->size() * 4,
+                                        cudaMemcpyHostToDevice),
+                             "upload image");
+        if (ok) {
+            char* b = static_cast<char*>(d->image_base);
+            d->d_rec = reinterpret_cast<uint4*>(b + part_off[0]);
+            d->d_outputs = reinterpret_cast<uint4*>(b + part_off[1]);
+            d->d_root = reinterpret_cast<uint32_t*>(b + part_off[2]);
+            d->d_mapper = reinterpret_cast<uint32_t*>(b + part_off[3]);
+            if (!img.crec.empty()) {
+                d->d_crec = reinterpret_cast<uint4*>(b + part_off[4]);
+                d->d_opos = reinterpret_cast<uint32_t*>(b + part_off[5]);
+                if (img.hot_slots) {  // the compact image is renumbered: stream chunks translate state ids
+                    d->d_id_in = reinterpret_cast<uint32_t*>(b + part_off[6]);
+                    d->d_id_out = reinterpret_cast<uint32_t*>(b + part_off[7]);
+                }
+                d->hot_slots = img.hot_slots;
+            }
+            d->root_base = img.root_base;
+        }
+        ok = ok && install_policies(1) && d->ws.init(false);
+        if (!ok) {
+            dach_dev_free(d.release());
+            return DACH_CUDA_ERROR;
+        }
+        *out = d.release();
+        return DACH_OK;
+    });
+}
+
+void dach_dev_free(dach_dev* d) {
+    if (!d) return;
+    DeviceGuard g(d->device);
+    cudaFree(d->image_base);
+    d->ws.release();
+    for (Workspace& w : d->slot) w.release();
+    delete d;
+}
+
+size_t dach_dev_image_bytes(const dach_dev* d) { return d ? d->image_bytes : 0; }
+
+int dach_dev_scan_batch(dach_dev* d, int mode, const uint8_t* d_text, const uint64_t* d_offs, uint64_t n,
+                        uint64_t text_bytes, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs,
+                        uint64_t* needed, void* stream) {
+    if (!d || !d_offs || !d_out_offs || (out_cap && !d_out)) {
+        set_error("null argument");
+        return DACH_INVALID_ARGUMENT;
+    }
+    const int rc = check_mode(d, mode);
+    if (rc) return rc;
+    return guarded([&]() -> int {
+        std::lock_guard<std::mutex> lk(d->mu);
+        DeviceGuard g(d->device);
+        if (!g.ok) return DACH_CUDA_ERROR;
+        return scan_locked(d, d->ws, mode, d_text, d_text, d_text + text_bytes, text_bytes, d_offs, n, d_out, out_cap, d_out_offs, needed,
+                           static_cast<cudaStream_t>(stream));
+    });
+}
+
+int dach_dev_scan_stream(dach_dev* d, int mode, const uint8_t* d_text, const uint64_t* d_offs, uint64_t n, uint64_t text_bytes,
+                         uint32_t* d_state, const uint32_t* d_pos, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs,
+                         uint64_t* needed, void* stream) {
+    if (!d || !d_offs || !d_out_offs || !d_state || (out_cap && !d_out)) {
+        set_error("null argument");
+        return DACH_INVALID_ARGUMENT;
+    }
+    if (mode != DACH_FIND && mode != DACH_FIND_OVERLAPPING) {
+        set_error("stream chunks: mode must be DACH_FIND or DACH_FIND_OVERLAPPING (the crate's two steppers)");
+        return DACH_INVALID_ARGUMENT;
+    }
+    const int rc = check_mode(d, mode);
+    if (rc) return rc;
+    return guarded([&]() -> int {
+        std::lock_guard<std::mutex> lk(d->mu);
+        DeviceGuard g(d->device);
+        if (!g.ok) return DACH_CUDA_ERROR;
+        return scan_locked(d, d->ws, mode, d_text, d_text, d_text + text_bytes, text_bytes, d_offs, n, d_out, out_cap, d_out_offs, needed,
+                           static_cast<cudaStream_t>(stream), d_state, d_pos);
+    });
+}
+
+int dach_scan_batch_host(dach_dev* d, int mode, const uint8_t* text, const uint64_t* offs, uint64_t n,
+                         dach_match* out, uint64_t out_cap, uint64_t* out_offs, uint64_t* needed) {
+    return guarded([&]() -> int { return scan_batch_host_impl(d, mode, text, offs, n, out, out_cap, out_offs, needed); });
+}
+
+// ---- asynchronous jobs ------------------------------------------------------------------------------
+
+int dach_job_create(dach_dev* d, dach_job** out) {
+    if (!d || !out) return DACH_INVALID_ARGUMENT;
+    *out = nullptr;
+    return guarded([&]() -> int {
+        DeviceGuard g(d->device);
+        if (!g.ok) return DACH_CUDA_ERROR;
+        std::unique_ptr<dach_job> j(new dach_job());
+        j->d = d;
+        if (!j->W.init(false)) {
+            j->W.release();
+            return DACH_CUDA_ERROR;
+        }
+        *out = j.release();
+        return DACH_OK;
+    });
+}
+
+void dach_job_free(dach_job* j) {
+    if (!j) return;
+    DeviceGuard g(j->d->device);
+    if (j->W.job_open) cudaEventSynchronize(j->W.ev_placed);
+    j->W.release();
+    delete j;
+}
+
+int dach_job_scan(dach_job* j, int mode, const uint8_t* d_text, const uint64_t* d_offs, uint64_t n, uint64_t text_bytes,
+                  uint64_t cap_matches, void* stream) {
+    if (!j || !d_offs) {
+        set_error("null argument");
+        return DACH_INVALID_ARGUMENT;
+    }
+    const int rc = check_mode(j->d, mode);
+    if (rc) return rc;
+    return guarded([&]() -> int {
+        DeviceGuard g(j->d->device);
+        if (!g.ok) return DACH_CUDA_ERROR;
+        return enqueue_scan(j->d, j->W, mode, d_text, d_text, d_text + text_bytes, text_bytes, d_offs, n, cap_matches,
+                            static_cast<cudaStream_t>(stream));
+    });
+}
+
+int dach_job_place(dach_job* j, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs, const uint64_t* d_base, void* stream) {
+    if (!j || !d_out_offs || (out_cap && !d_out)) {
+        set_error("null argument");
+        return DACH_INVALID_ARGUMENT;
+    }
+    return guarded([&]() -> int {
+        DeviceGuard g(j->d->device);
+        if (!g.ok) return DACH_CUDA_ERROR;
+        j->out_cap = out_cap;
+        return enqueue_place(j->d, j->W, d_out, out_cap, d_out_offs, reinterpret_cast<const unsigned long long*>(d_base), true,
+                             static_cast<cudaStream_t>(stream));
+    });
+}
+
+int dach_job_wait(dach_job* j, uint64_t* needed) {
+    if (!j) return DACH_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        DeviceGuard g(j->d->device);
+        if (!g.ok) return DACH_CUDA_ERROR;
+        return finish_scan(j->d, j->W, j->out_cap, needed);
+    });
+}
+
+double dach_job_scan_kernel_ms(const dach_job* j) {
+    float ms = 0;
+    if (j && cudaEventElapsedTime(&ms, j->W.ev[3], j->W.ev[1]) == cudaSuccess) return ms;
+    return 0;
+}
+
+// ---- shard groups -----------------------------------------------------------------------------------
+
+struct dach_group {
+    int rank = 0, world = 1, device = 0;
+    uint64_t match_cap = 0, n_total = 0;
+    GroupCtl* ctl = nullptr;       // this rank's control block
+    dach_match* out = nullptr;     // the gathering rank's dense match buffer (peer-mapped on the other ranks)
+    uint64_t* offs = nullptr;      // ... and its n_total + 1 offsets
+    GroupPeers peers;
+    void* ipc_opened[3 * kMaxRanks];
+    int n_ipc = 0;
+    unsigned long long step = 0;
+    GroupCtl* pinned = nullptr;    // host copy of the control block (finish)
+    bool connected = false;
+};
+
+namespace {
+struct GroupHandle {
+    uint64_t pid;
+    int32_t device, rank;
+    uint64_t ctl_ptr, out_ptr, offs_ptr;
+    cudaIpcMemHandle_t ctl, out, offs;
+};
+static_assert(sizeof(GroupHandle) <= DACH_GROUP_HANDLE_BYTES, "DACH_GROUP_HANDLE_BYTES too small");
+}  // namespace
+
+int dach_group_create(int rank, int world, int device, uint64_t match_cap, uint64_t n_haystacks_total, dach_group** out) {
+    if (!out) return DACH_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) {
+        set_error("shard group: rank / world out of range (at most 16 ranks)");
+        return DACH_INVALID_ARGUMENT;
+    }
+    return guarded([&]() -> int {
+        DeviceGuard g(device);
+        if (!g.ok) return DACH_CUDA_ERROR;
+        std::unique_ptr<dach_group> G(new dach_group());
+        G->rank = rank;
+        G->world = world;
+        G->device = device;
+        G->match_cap = match_cap;
+        G->n_total = n_haystacks_total;
+        memset(&G->peers, 0, sizeof(G->peers));
+        bool ok = cuda_ok(cudaMalloc(reinterpret_cast<void**>(&G->ctl), sizeof(GroupCtl)), "cudaMalloc group control") &&
+                  cuda_ok(cudaMemset(G->ctl, 0, sizeof(GroupCtl)), "memset group control") &&
+                  cuda_ok(cudaMallocHost(reinterpret_cast<void**>(&G->pinned), sizeof(GroupCtl)), "cudaMallocHost");
+        if (ok && rank == 0)
+            ok = cuda_ok(cudaMalloc(reinterpret_cast<void**>(&G->out), std::max<uint64_t>(match_cap, 1) * sizeof(dach_match)), "cudaMalloc gathered matches") &&
+                 cuda_ok(cudaMalloc(reinterpret_cast<void**>(&G->offs), (n_haystacks_total + 1) * 8), "cudaMalloc gathered offsets");
+        if (!ok) {
+            dach_group_free(G.release());
+            return DACH_CUDA_ERROR;
+        }
+        *out = G.release();
+        return DACH_OK;
+    });
+}
+
+int dach_group_export(const dach_group* G, void* handle) {
+    if (!G || !handle) return DACH_INVALID_ARGUMENT;
+    DeviceGuard g(G->device);
+    if (!g.ok) return DACH_CUDA_ERROR;
+    GroupHandle h;
+    memset(&h, 0, sizeof(h));
+    h.pid = (uint64_t)getpid();
+    h.device = G->device;
+    h.rank = G->rank;
+    h.ctl_ptr = (uint64_t)(uintptr_t)G->ctl;
+    if (!cuda_ok(cudaIpcGetMemHandle(&h.ctl, G->ctl), "cudaIpcGetMemHandle")) return DACH_CUDA_ERROR;
+    if (G->rank == 0) {
+        h.out_ptr = (uint64_t)(uintptr_t)G->out;
+        h.offs_ptr = (uint64_t)(uintptr_t)G->offs;
+        if (!cuda_ok(cudaIpcGetMemHandle(&h.out, G->out), "cudaIpcGetMemHandle") ||
+            !cuda_ok(cudaIpcGetMemHandle(&h.offs, G->offs), "cudaIpcGetMemHandle"))
+            return DACH_CUDA_ERROR;
+    }
+    memset(handle, 0, DACH_GROUP_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof(h));
+    return DACH_OK;
+}
+
+int dach_group_connect(dach_group* G, const void* handles) {
+    if (!G || !handles) return DACH_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        DeviceGuard g(G->device);
+        if (!g.ok) return DACH_CUDA_ERROR;
+        const uint64_t me = (uint64_t)getpid();
+        auto map = [&](const GroupHandle& h, uint64_t raw, const cudaIpcMemHandle_t& ipc, void** out) -> bool {
+            if (h.pid == me) {  // same process: the pointer itself, peer access between the two devices
+                if (h.device != G->device) {
+                    int can = 0;
+                    cudaDeviceCanAccessPeer(&can, G->device, h.device);
+                    if (!can) {
+                        set_error("shard group: no peer access between the devices");
+                        return false;
+                    }
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_ok(e, "cudaDeviceEnablePeerAccess");
+                    cudaGetLastError();
+                }
+                *out = reinterpret_cast<void*>((uintptr_t)raw);
+                return true;
+            }
+            void* p = nullptr;
+            if (!cuda_ok(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return false;
+            G->ipc_opened[G->n_ipc++] = p;
+            *out = p;
+            return true;
+        };
+        for (int j = 0; j < G->world; ++j) {
+            GroupHandle h;
+            memcpy(&h, static_cast<const char*>(handles) + (size_t)j * DACH_GROUP_HANDLE_BYTES, sizeof(h));
+            if (h.rank != j) {
+                set_error("shard group: handles must be in rank order");
+                return DACH_INVALID_ARGUMENT;
+            }
+            if (j == G->rank) {
+                G->peers.ctl[j] = G->ctl;
+            } else {
+                void* p = nullptr;
+                if (!map(h, h.ctl_ptr, h.ctl, &p)) return DACH_CUDA_ERROR;
+                G->peers.ctl[j] = static_cast<GroupCtl*>(p);
+            }
+            if (j == 0 && G->rank != 0) {
+                void *po = nullptr, *pf = nullptr;
+                if (!map(h, h.out_ptr, h.out, &po) || !map(h, h.offs_ptr, h.offs, &pf)) return DACH_CUDA_ERROR;
+                G->out = static_cast<dach_match*>(po);
+                G->offs = static_cast<uint64_t*>(pf);
+            }
+        }
+        G->connected = true;
+        return DACH_OK;
+    });
+}
+
+int dach_group_place(dach_group* G, dach_job* j, uint64_t hay_base, int last, void* stream) {
+    if (!G || !j || !G->connected) {
+        set_error("shard group: not connected");
+        return DACH_INVALID_ARGUMENT;
+    }
+    if (hay_base + j->W.job_n > G->n_total) {
+        set_error("shard group: haystack range outside the gathered batch");
+        return DACH_INVALID_ARGUMENT;
+    }
+    return guarded([&]() -> int {
+        DeviceGuard g(G->device);
+        if (!g.ok) return DACH_CUDA_ERROR;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        Workspace& W = j->W;
+        if (!W.job_open) {
+            set_error("no scan to place");
+            return DACH_INVALID_ARGUMENT;
+        }
+        const unsigned long long step = ++G->step;
+        if (st != W.job_stream) cudaStreamWaitEvent(st, W.ev_scanned, 0);
+        // calling for step s says the result of step s-1 has been consumed: its buffers are free again
+        if (G->rank == 0 && step > 1) k_group_release<<<1, kMaxRanks, 0, st>>>(G->peers, G->world, step - 1);
+        const unsigned long long* total = static_cast<const unsigned long long*>(W.item_offs.p) + W.job_items;
+        k_group_publish<<<1, kMaxRanks, 0, st>>>(G->peers, G->world, G->rank, step, total);
+        k_group_wait_base<<<1, 1, 0, st>>>(G->ctl, G->rank, step);
+        j->d->launches += 3;
+        j->out_cap = G->match_cap;
+        const int rc = enqueue_place(j->d, W, G->out, G->match_cap, G->offs + hay_base, &G->ctl->base[step & 1], last != 0, st);
+        if (rc) return rc;
+        k_group_signal_done<<<1, 1, 0, st>>>(G->peers.ctl[0], G->rank, step);
+        ++j->d->launches;
+        if (!cuda_ok(cudaGetLastError(), "shard group kernels")) return DACH_CUDA_ERROR;
+        cudaEventRecord(W.ev_placed, st);  // the job's buffers are free once the done signal is out
+        return DACH_OK;
+    });
+}
+
+int dach_group_finish(dach_group* G, uint64_t* total, void* stream) {
+    if (!G || !G->connected) return DACH_INVALID_ARGUMENT;
+    return guarded([&]() -> int {
+        DeviceGuard g(G->device);
+        if (!g.ok) return DACH_CUDA_ERROR;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (G->rank == 0 && G->step) k_group_wait_all<<<1, 1, 0, st>>>(G->ctl, G->world, G->step);
+        cudaMemcpyAsync(G->pinned, G->ctl, sizeof(GroupCtl), cudaMemcpyDeviceToHost, st);
+        if (!cuda_ok(cudaStreamSynchronize(st), "shard group finish")) return DACH_CUDA_ERROR;
+        if (G->pinned->error) {
+            set_error("shard group: a rank did not arrive within 20 s");
+            return DACH_CUDA_ERROR;
+        }
+        const uint64_t sum = G->rank == 0 ? G->pinned->sum[G->step & 1] : 0;
+        if (total) *total = sum;
+        if (G->rank == 0 && sum > G->match_cap) {
+            set_error("shard group: gathered matches exceed the capacity of the result buffer");
+            return DACH_OUTPUT_OVERFLOW;
+        }
+        return DACH_OK;
+    });
+}
+
+int dach_group_result(const dach_group* G, dach_match** d_out, uint64_t** d_offs) {
+    if (!G || G->rank != 0) {
+        set_error("shard group: only the gathering rank (0) holds the result");
+        return DACH_INVALID_ARGUMENT;
+    }
+    if (d_out) *d_out = G->out;
+    if (d_offs) *d_offs = G->offs;
+    return DACH_OK;
+}
+
+void dach_group_free(dach_group* G) {
+    if (!G) return;
+    DeviceGuard g(G->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < G->n_ipc; ++i) cudaIpcCloseMemHandle(G->ipc_opened[i]);
+    if (G->rank == 0) {
+        cudaFree(G->out);
+        cudaFree(G->offs);
+    }
+    cudaFree(G->ctl);
+    if (G->pinned) cudaFreeHost(G->pinned);
+    delete G;
+}
+
+uint64_t dach_dev_kernel_launches(const dach_dev* d) { return d ? d->launches.load() : 0; }
 double dach_dev_last_scan_kernel_ms(const dach_dev* d) { return d ? d->last_scan_ms : 0; }
 double dach_dev_last_total_ms(const dach_dev* d) { return d ? d->last_total_ms : 0; }
 uint64_t dach_dev_last_h2d_bytes(const dach_dev* d) { return d ? d->last_h2d : 0; }
@@ -1223,14 +1717,10 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
         d->opt_ctas_per_sm = value;
     else if (k == "kernel")
         d->opt_kernel = value;
-    else if (k == "l2_persist")
-        d->opt_l2_persist = value;
     else if (k == "slice_mib")
         d->opt_slice_mib = value;
     else if (k == "seg_len")
         d->opt_seg_len = value;
-    else if (k == "dbg")
-        d->opt_dbg = value;
     else if (k == "slice_ramp")
         d->opt_slice_ramp = value;
     else if (k == "tail_seg")
@@ -1243,7 +1733,11 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
         d->opt_reserve_sms = value;
     else if (k == "hot_entries")
         d->opt_hot_entries = value;
-    else {
+    else if (k == "l2_hints") {
+        d->opt_l2_hints = value;
+        DeviceGuard g(d->device);
+        if (!g.ok || !install_policies(value != 0)) return DACH_CUDA_ERROR;  // device-wide: all handles on this device
+    } else {
         set_error("unknown option " + k);
         return DACH_INVALID_ARGUMENT;
     }

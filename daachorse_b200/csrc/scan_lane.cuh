@@ -85,6 +85,7 @@ struct ScanCtrl {
     unsigned long long next_item;  // dynamic work counter
     unsigned int blk_cursor;       // bump allocator
     unsigned int overflow;         // pool exhausted
+    unsigned int bad_offsets;      // the haystack offsets are not ascending, exceed text_bytes, or a haystack is >= 4 GiB
 };
 
 struct ScanParams {
@@ -120,8 +121,6 @@ struct ScanParams {
     uint32_t* state_io;  // stream chunks (dach_dev_scan_stream): state id per haystack, read at its start and
                          // written at its end; nullptr for ordinary scans (every haystack starts in ROOT)
     uint32_t seg_from;  // haystacks below this index stay whole (one item each): only the tail of a batch is cut
-    uint32_t dbg;  // experiment switches (bench --option dbg=): 1 = count matches but do not store them,
-                   // 2 = text via ld.global.cs, 4 = text via ld.global.nc.L1::no_allocate
     // results
     uint32_t* counts;  // matches per item
     uint32_t* pool;
@@ -129,29 +128,43 @@ struct ScanParams {
     ScanCtrl* ctrl;
 };
 
+// L2 eviction policies (64-bit descriptors made once per device by k_make_policies, dev_scan.cu):
+//   [0] automaton image (records, output_pos, outputs, mapper): evict_last -- the scan is latency-bound
+//       on these dependent random fetches, and a fetch that misses L2 stalls all 32 lanes of its warp;
+//   [1] streams (haystack text, match blocks): evict_first -- each byte passes through once.
+// Without them the text and the match blocks push 6-7 % of the record sectors out of the 126 MB L2
+// (profiles/r1d_*: 2.4 B of DRAM reads per scanned byte, 1.0 of it text).  Option l2_hints = 0 stores
+// evict_normal in both.
+#if defined(__CUDACC__)
+__constant__ unsigned long long c_l2pol[2];
+#endif
+
 DACH_HD uint4 ld_u4(const uint4* p) {
-#if defined(__CUDA_ARCH__) && defined(DACH_L2HINT)
-    // Experiment build (-DDACH_L2HINT, not the default library): automaton records carry an L2 evict_last
-    // policy so that the text and match-block streams do not push them out of L2 (the scan kernel reads
-    // 2.4 B of DRAM per scanned byte; 1.0 of it is the text).  To be measured: DESIGN.md section 8.
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#if defined(__CUDA_ARCH__)
     uint4 v;
     asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p), "l"(pol));
+                 : "l"(p), "l"(c_l2pol[0]));
     return v;
-#elif defined(__CUDA_ARCH__)
-    return __ldg(p);
 #else
     return *p;
 #endif
 }
 DACH_HD uint32_t ld_u32(const uint32_t* p) {
 #if defined(__CUDA_ARCH__)
-    return __ldg(p);
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(c_l2pol[0]));
+    return v;
 #else
     return *p;
+#endif
+}
+// match blocks: written once here, read once by k_gather
+DACH_HD void st_stream_u32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(c_l2pol[1]) : "memory");
+#else
+    *p = v;
 #endif
 }
 
@@ -197,9 +210,9 @@ struct TextWin {
             cur = blk;
 #if defined(__CUDA_ARCH__)
             const uint4* q = reinterpret_cast<const uint4*>((uintptr_t)(blk << 4));
-            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                          : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
-                         : "l"(q));
+                         : "l"(q), "l"(c_l2pol[1]));
 #elif defined(DACH_EMU)
             // CPU emulation (tests/emu): gather only bytes inside [emu_lo, emu_hi)
             const uint8_t* q = reinterpret_cast<const uint8_t*>((uintptr_t)(blk << 4));
@@ -244,18 +257,18 @@ struct Emitter {
             const uint32_t b = bump_u32(&P.ctrl->blk_cursor);
             if (b < P.pool_blocks) {
                 blk = P.pool + (size_t)b * BLK_WORDS;
-                blk[0] = item;
-                blk[1] = count / BLK_MATCHES;
+                st_stream_u32(blk + 0, item);
+                st_stream_u32(blk + 1, count / BLK_MATCHES);
             } else {
                 blk = nullptr;
                 P.ctrl->overflow = 1u;
             }
         }
-        if (blk && !(P.dbg & 1u)) {
+        if (blk) {
             uint32_t* q = blk + 2 + 3 * fill;
-            q[0] = start;
-            q[1] = end;
-            q[2] = value;
+            st_stream_u32(q + 0, start);
+            st_stream_u32(q + 1, end);
+            st_stream_u32(q + 2, value);
         }
         fill = (fill + 1 == BLK_MATCHES) ? 0 : fill + 1;
         ++count;
@@ -636,14 +649,9 @@ DACH_HD uint4 ld_text16(const uint8_t* q, const uint8_t* text_end, const uint8_t
     // Default: read-only path WITH L1 allocation.  A lane comes back to the same 32-byte sector for
     // its next 16 bytes; with L1::no_allocate every one of those loads went to DRAM (8.2 GB read per
     // GiB scanned vs 2.5 GB, profiles/r1_cache_experiments.md).
-    if (dbg & 2u)
-        asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(q));
-    else if (dbg & 4u)
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
-                     : "l"(q));
-    else
-        asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(q));
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                 : "l"(q), "l"(c_l2pol[1]));
 #elif defined(DACH_EMU)
     uint32_t v[4] = {0, 0, 0, 0};
     for (int i = 0; i < 16; ++i) {
@@ -1457,7 +1465,7 @@ DACH_HD uint2 ld_text8(const uint8_t* q, const uint8_t* text_end, const uint8_t*
     (void)emu_lo;
     if (q >= text_end) return w;
 #if defined(__CUDA_ARCH__)
-    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(q));
+    asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(w.x), "=r"(w.y) : "l"(q), "l"(c_l2pol[1]));
 #elif defined(DACH_EMU)
     uint32_t v[2] = {0, 0};
     for (int i = 0; i < 8; ++i) {
@@ -1693,7 +1701,7 @@ DACH_HD uint2 ld_text8_safe(const uint8_t* q, const uint8_t* text_lo, const uint
     if (q >= text_end || q + 8 <= text_lo) return w;
     if (q >= text_lo && q + 8 <= text_end) {
 #if defined(__CUDA_ARCH__)
-        asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(q));
+        asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(w.x), "=r"(w.y) : "l"(q), "l"(c_l2pol[1]));
 #else
         for (int i = 0; i < 8; ++i) (i < 4 ? w.x : w.y) |= (uint32_t)q[i] << ((i & 3) * 8);
 #endif

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DACH_ABI_VERSION 1
+#define DACH_ABI_VERSION 2
 
 /* Status codes.  1-4 mirror DaachorseError (src/errors.rs:10-22); 5 stands for the
  * `assert!(self.match_kind.is_standard())` / `is_leftmost()` panics of
@@ -157,9 +157,9 @@ int dach_scan_batch_host(dach_dev *dev, int mode, const uint8_t *text, const uin
  * or DACH_FIND_OVERLAPPING.
  *   d_state  device pointer, n u32, in/out: the stepper's state_id.  In: the state the
  *            previous chunk of the stream ended in (0 = ROOT for a new stream).  Out: the
- *            state after the chunk's last byte.  State ids are the crate's (the device image
- *            keeps the reference's numbering), so chunks may alternate between this library
- *            and the crate's own steppers.
+ *            state after the chunk's last byte.  State ids are the crate's (the device image is
+ *            renumbered hot-first; ids are translated at the boundary), so chunks may alternate
+ *            between this library and the crate's own steppers.
  *   d_pos    device pointer, n u32, or NULL: the stepper's pos at the chunk's first byte;
  *            it is added to start and end of the chunk's matches (stream coordinates,
  *            modulo 2^32).  NULL = positions relative to the chunk.
@@ -174,6 +174,63 @@ int dach_dev_scan_stream(dach_dev *dev, int mode, const uint8_t *d_text, const u
                          dach_match *d_out, uint64_t out_cap, uint64_t *d_out_offs,
                          uint64_t *needed, void *stream);
 
+/* ---- asynchronous scans (jobs) ----------------------------------------------------------
+ *
+ * dach_dev_scan_batch is one call that synchronises its stream and serialises per handle.  A job is
+ * the same pipeline cut in two phases that only ENQUEUE work, with a workspace of its own, so that
+ * host threads, streams and GPUs overlap (the crate's iterators are `&self`: any number of scans run
+ * concurrently on one automaton -- src/bytewise.rs:190-197 takes `&self`).
+ *   dach_job_scan   enqueues items + scan kernel + offsets on `stream`; returns at once.
+ *                   cap_matches sizes the staging pool (as out_cap does in dach_dev_scan_batch).
+ *   dach_job_place  enqueues the gather on `stream` (may differ from the scan's stream; ordered by an
+ *                   event): matches -> d_out + *d_base, offsets (+ *d_base) -> d_out_offs[0..n].
+ *                   d_base is a DEVICE pointer to the index of this batch's first match in d_out, or
+ *                   NULL for 0; d_out / d_out_offs may be peer-mapped memory of another GPU.
+ *   dach_job_wait   blocks until the placement is done; status and *needed as dach_dev_scan_batch.
+ * A job holds one scan at a time: scan -> place -> (wait) -> scan ...; the next dach_job_scan is
+ * ordered after the previous placement by the library.  Options are read from the dach_dev. */
+typedef struct dach_job dach_job;
+int dach_job_create(dach_dev *dev, dach_job **out);
+void dach_job_free(dach_job *job);
+int dach_job_scan(dach_job *job, int mode, const uint8_t *d_text, const uint64_t *d_offs, uint64_t n,
+                  uint64_t text_bytes, uint64_t cap_matches, void *stream);
+int dach_job_place(dach_job *job, dach_match *d_out, uint64_t out_cap, uint64_t *d_out_offs,
+                   const uint64_t *d_base, void *stream);
+int dach_job_wait(dach_job *job, uint64_t *needed);
+double dach_job_scan_kernel_ms(const dach_job *job); /* CUDA-event time of the job's last scan kernel */
+
+/* ---- shard groups: the exchange step of a batch sharded over the GPUs of one node ---------
+ *
+ * Haystacks are independent, so a batch shards with no data-path collective; the one exchange is
+ * the gather of the per-shard match buffers to rank 0 (north_star).  Here that gather is not a
+ * separate collective: every rank's placement kernel stores its matches straight into rank 0's
+ * dense result buffer over NVLink peer memory, at the base it learns from the lower ranks' counts
+ * (published into every rank's control block with system-scope releases, polled locally).  Rank 0
+ * ends a step holding exactly what one GPU would have produced for the concatenated batch:
+ * matches dense and in shard order, n_total + 1 rebased offsets.
+ *
+ *   create   every rank: control block; rank 0 also the result buffers (match_cap matches,
+ *            n_haystacks_total + 1 offsets).
+ *   export / connect   DACH_GROUP_HANDLE_BYTES per rank, exchanged by the caller (any transport:
+ *            torch.distributed, MPI, a pipe), passed in rank order.  Ranks may be processes (CUDA IPC)
+ *            or handles inside one process (peer access).
+ *   place    the exchange step of one job: hay_base = index of the shard's first haystack in the
+ *            whole batch, last = this shard ends the batch (it also writes offsets[n_total]).
+ *            Calling place for step s releases the result of step s-1 (rank 0).
+ *   finish   rank 0: enqueues the wait for all ranks on `stream`, synchronises it, reports the total
+ *            (DACH_OUTPUT_OVERFLOW if it exceeds match_cap); other ranks: synchronise `stream`.
+ *   result   rank 0's device pointers. */
+#define DACH_GROUP_HANDLE_BYTES 256
+typedef struct dach_group dach_group;
+int dach_group_create(int rank, int world, int device, uint64_t match_cap, uint64_t n_haystacks_total,
+                      dach_group **out);
+int dach_group_export(const dach_group *group, void *handle);
+int dach_group_connect(dach_group *group, const void *handles);
+int dach_group_place(dach_group *group, dach_job *job, uint64_t hay_base, int last, void *stream);
+int dach_group_finish(dach_group *group, uint64_t *total, void *stream);
+int dach_group_result(const dach_group *group, dach_match **d_out, uint64_t **d_offs);
+void dach_group_free(dach_group *group);
+
 /* ---- introspection for the bench / tests ------------------------------------------ */
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
@@ -185,8 +242,9 @@ double dach_dev_last_total_ms(const dach_dev *dev);
 /* Bytes moved host<->device by the most recent dach_scan_batch_host call. */
 uint64_t dach_dev_last_h2d_bytes(const dach_dev *dev);
 uint64_t dach_dev_last_d2h_bytes(const dach_dev *dev);
-/* Tuning knobs (0 keeps the default): hot records staged in shared memory, CTAs per SM,
- * threads per CTA, segment length for intra-haystack chunking of find_overlapping. */
+/* Tuning knobs: kernel (3 = StdMachine3, the default; 2, 1 = its predecessors; 0 = lane per haystack),
+ * hot_entries (records of the hot region staged in shared memory), threads, ctas_per_sm, seg_len
+ * (segment length for intra-haystack chunking of find_overlapping), l2_hints, slice_mib, ... */
 int dach_dev_set_option(dach_dev *dev, const char *name, int64_t value);
 
 /* Human-readable text of the last error on this thread ("" if none). */

@@ -5,9 +5,11 @@
  * reference file:line (relative to /root/reference/) whose control flow it follows.
  * V (the pattern value type) is fixed to u32.
  */
+#define _GNU_SOURCE
 #include "dach_oracle.h"
 
 #include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -452,7 +454,54 @@ struct orc_pma {
     uint32_t alphabet_size;
     output_t *outputs;
     size_t n_outputs;
+    /* The crate's in-memory records, one array of structs each -- what its scan loops actually walk:
+     *   bytewise Standard  State<u32>{base, fail, opos_ch}      12 B  (src/bytewise.rs:1131-1137)
+     *   bytewise leftmost  State<Empty>{base, opos_ch} 8 B + fails[] 4 B  (src/bytewise.rs:61-63)
+     *   charwise           State{base, check, fail, output_pos} 16 B  (src/charwise.rs:1096-1101)
+     * Built from the arrays above when construction / deserialisation ends; every scan below reads these,
+     * so that the CPU baseline timed with this file pays one cache line per visited state like the crate
+     * does (three parallel arrays cost up to three). */
+    struct bw_state *st12;
+    struct lm_state *st8;
+    struct cw_state *st16;
 };
+struct bw_state {
+    uint32_t base, fail, opos_ch;
+};
+struct lm_state {
+    uint32_t base, opos_ch;
+};
+struct cw_state {
+    uint32_t base, check, fail, output_pos;
+};
+
+static void build_scan_records(orc_pma *p) {
+    const size_t n = p->n_slots;
+    free(p->st12), free(p->st8), free(p->st16);
+    p->st12 = NULL, p->st8 = NULL, p->st16 = NULL;
+    if (p->charwise) {
+        p->st16 = (struct cw_state *)xrealloc(NULL, (n ? n : 1) * sizeof(struct cw_state));
+        for (size_t i = 0; i < n; i++) {
+            p->st16[i].base = p->base[i];
+            p->st16[i].check = p->check[i];
+            p->st16[i].fail = p->fail[i];
+            p->st16[i].output_pos = p->output_pos[i];
+        }
+    } else if (p->match_kind == ORC_LEFTMOST_LONGEST || p->match_kind == ORC_LEFTMOST_FIRST) {
+        p->st8 = (struct lm_state *)xrealloc(NULL, (n ? n : 1) * sizeof(struct lm_state));
+        for (size_t i = 0; i < n; i++) {
+            p->st8[i].base = p->base[i];
+            p->st8[i].opos_ch = p->opos_ch[i];
+        }
+    } else {
+        p->st12 = (struct bw_state *)xrealloc(NULL, (n ? n : 1) * sizeof(struct bw_state));
+        for (size_t i = 0; i < n; i++) {
+            p->st12[i].base = p->base[i];
+            p->st12[i].fail = p->fail[i];
+            p->st12[i].opos_ch = p->opos_ch[i];
+        }
+    }
+}
 
 void orc_free(orc_pma *p) {
     if (!p) return;
@@ -463,6 +512,9 @@ void orc_free(orc_pma *p) {
     free(p->output_pos);
     free(p->table);
     free(p->outputs);
+    free(p->st12);
+    free(p->st8);
+    free(p->st16);
     free(p);
 }
 
@@ -897,6 +949,7 @@ int orc_build(int charwise, const uint8_t *bytes, const uint64_t *offs, const ui
     free(labels);
     free(freqs);
     nfa_destroy(&nfa);
+    build_scan_records(p);
     *out = p;
     return ORC_OK;
 fail:
@@ -1153,6 +1206,7 @@ int orc_deserialize(int charwise, const uint8_t *src, size_t len, orc_pma **out,
 #undef BADL
 #undef BAD
     if (consumed) *consumed = len - r.left;
+    build_scan_records(p);
     *out = p;
     return ORC_OK;
 }
@@ -1207,24 +1261,26 @@ uint32_t orc_mapper_get(const orc_pma *p, uint32_t c) { return mapper_get(p, c);
 
 /* next_state_id_unchecked (src/bytewise.rs:1063-1088) */
 static inline uint32_t bw_next(const orc_pma *p, uint32_t s, uint32_t c) {
+    const struct bw_state *st = p->st12;
     for (;;) {
         if (s == ROOT) return p->root_table[c];
-        uint32_t b = p->base[s];
+        uint32_t b = st[s].base;
         if (b != 0) {
             uint32_t child = b ^ c;
-            if ((p->opos_ch[child] & 0xff) == c) return child;
+            if ((st[child].opos_ch & 0xff) == c) return child;
         }
-        s = p->fail[s];
+        s = st[s].fail;
     }
 }
 
 /* next_state_id_leftmost_unchecked (src/bytewise.rs:1094-1128) */
 static inline uint32_t bw_next_leftmost(const orc_pma *p, uint32_t s, uint32_t c) {
+    const struct lm_state *st = p->st8;
     for (;;) {
-        uint32_t b = p->base[s];
+        uint32_t b = st[s].base;
         if (b != 0) {
             uint32_t child = b ^ c;
-            if ((p->opos_ch[child] & 0xff) == c) return child;
+            if ((st[child].opos_ch & 0xff) == c) return child;
         }
         if (s == ROOT) return ROOT;
         uint32_t f = p->fail[s];
@@ -1237,14 +1293,15 @@ static inline uint32_t bw_next_leftmost(const orc_pma *p, uint32_t s, uint32_t c
 static inline uint32_t cw_next(const orc_pma *p, uint32_t s, uint32_t cp) {
     uint32_t mc = mapper_get(p, cp);
     if (mc == INVALID_CODE) return ROOT;
+    const struct cw_state *st = p->st16;
     for (;;) {
-        uint32_t b = p->base[s];
+        uint32_t b = st[s].base;
         if (b != 0) {
             uint32_t child = b ^ mc;
-            if (p->check[child] == s) return child;
+            if (st[child].check == s) return child;
         }
         if (s == ROOT) return ROOT;
-        s = p->fail[s];
+        s = st[s].fail;
     }
 }
 
@@ -1252,21 +1309,24 @@ static inline uint32_t cw_next(const orc_pma *p, uint32_t s, uint32_t cp) {
 static inline uint32_t cw_next_leftmost(const orc_pma *p, uint32_t s, uint32_t cp) {
     uint32_t mc = mapper_get(p, cp);
     if (mc == INVALID_CODE) return ROOT;
+    const struct cw_state *st = p->st16;
     for (;;) {
-        uint32_t b = p->base[s];
+        uint32_t b = st[s].base;
         if (b != 0) {
             uint32_t child = b ^ mc;
-            if (p->check[child] == s) return child;
+            if (st[child].check == s) return child;
         }
         if (s == ROOT) return ROOT;
-        uint32_t f = p->fail[s];
+        uint32_t f = st[s].fail;
         if (f == DEAD) return ROOT;
         s = f;
     }
 }
 
 static inline uint32_t st_opos(const orc_pma *p, uint32_t s) {
-    return p->charwise ? p->output_pos[s] : (p->opos_ch[s] >> 8);
+    if (p->st12) return p->st12[s].opos_ch >> 8;
+    if (p->st16) return p->st16[s].output_pos;
+    return p->st8[s].opos_ch >> 8;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -1289,6 +1349,10 @@ typedef struct {
     orc_match *out;
     size_t cap, n;
     uint64_t hash;
+    int want_hash;   /* 0: the timed baseline does not pay for the checker's hash */
+    orc_match *ring; /* timed baseline: every match is stored like a consumer collecting them would, into a
+                        small per-thread ring (ring_mask + 1 entries) instead of an unbounded Vec */
+    size_t ring_mask;
 } sink_t;
 
 static inline void emit(sink_t *k, size_t end, uint32_t length, uint32_t value) {
@@ -1298,7 +1362,13 @@ static inline void emit(sink_t *k, size_t end, uint32_t length, uint32_t value) 
         k->out[k->n].end = en;
         k->out[k->n].value = value;
     }
-    k->hash = orc_hash_step(k->hash, st, en, value);
+    if (k->ring) {
+        orc_match *m = &k->ring[k->n & k->ring_mask];
+        m->start = st;
+        m->end = en;
+        m->value = value;
+    }
+    if (k->want_hash) k->hash = orc_hash_step(k->hash, st, en, value);
     k->n++;
 }
 
@@ -1546,7 +1616,7 @@ int orc_scan(const orc_pma *p, int mode, const uint8_t *hay, size_t len, orc_mat
              size_t *n_out) {
     if (mode < 0 || mode > ORC_FIND_OVERLAPPING_STEPPER) return ORC_INVALID_ARGUMENT;
     if (!mode_ok(p, mode)) return ORC_MATCH_KIND_MISMATCH;
-    sink_t k = {out, cap, 0, 0};
+    sink_t k = {out, cap, 0, 0, 1, NULL, 0};
     scan_one(p, mode, hay, len, &k);
     if (n_out) *n_out = k.n;
     return ORC_OK;
@@ -1559,23 +1629,45 @@ typedef struct {
     int mode;
     const uint8_t *text;
     const uint64_t *offs;
-    uint64_t lo, hi;
+    uint64_t n;
     uint64_t *counts, *hashes;
     orc_match *out;
     const uint64_t *out_offs; /* pass 2: per-haystack start in out */
     uint64_t out_cap;
+    int store_ring; /* timed baseline: matches go to a per-thread ring */
 } job_t;
 
-static void *batch_worker(void *arg) {
-    job_t *j = (job_t *)arg;
-    for (uint64_t i = j->lo; i < j->hi; i++) {
+/* A persistent pool of worker threads, each pinned to one of the CPUs this process may run on (the crate's
+ * users would use rayon or std::thread the same way); haystacks are handed out in chunks from one atomic
+ * counter.  The pool is (re)built when the requested thread count changes. */
+#define POOL_CHUNK 16
+#define RING_ENTRIES 4096
+typedef struct {
+    pthread_t th;
+    int index;
+    orc_match *ring;
+} worker_t;
+static struct {
+    pthread_mutex_t mu;
+    pthread_cond_t go, done;
+    worker_t *w;
+    int n_workers, running, generation, quit;
+    job_t job;
+    volatile uint64_t next;
+} g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0, 0, {0}, 0};
+
+static void run_chunk(const job_t *j, uint64_t lo, uint64_t hi, orc_match *ring) {
+    for (uint64_t i = lo; i < hi; i++) {
         const uint8_t *hay = j->text + j->offs[i];
         size_t len = (size_t)(j->offs[i + 1] - j->offs[i]);
-        sink_t k = {NULL, 0, 0, 0};
+        sink_t k = {NULL, 0, 0, 0, j->hashes != NULL, NULL, 0};
         if (j->out_offs) {
             uint64_t o = j->out_offs[i];
             k.out = j->out + o;
             k.cap = o < j->out_cap ? (size_t)(j->out_cap - o) : 0;
+        } else if (j->store_ring) {
+            k.ring = ring;
+            k.ring_mask = RING_ENTRIES - 1;
         }
         scan_one(j->p, j->mode, hay, len, &k);
         if (!j->out_offs) {
@@ -1583,27 +1675,119 @@ static void *batch_worker(void *arg) {
             if (j->hashes) j->hashes[i] = k.hash;
         }
     }
+}
+
+static void drain_items(const job_t *j, orc_match *ring) {
+    for (;;) {
+        const uint64_t lo = __atomic_fetch_add(&g_pool.next, POOL_CHUNK, __ATOMIC_RELAXED);
+        if (lo >= j->n) break;
+        run_chunk(j, lo, lo + POOL_CHUNK < j->n ? lo + POOL_CHUNK : j->n, ring);
+    }
+}
+
+static void *pool_worker(void *arg) {
+    worker_t *w = (worker_t *)arg;
+    int seen = 0;
+    pthread_mutex_lock(&g_pool.mu);
+    for (;;) {
+        while (!g_pool.quit && g_pool.generation == seen) pthread_cond_wait(&g_pool.go, &g_pool.mu);
+        if (g_pool.quit) break;
+        seen = g_pool.generation;
+        pthread_mutex_unlock(&g_pool.mu);
+        drain_items(&g_pool.job, w->ring);
+        pthread_mutex_lock(&g_pool.mu);
+        if (--g_pool.running == 0) pthread_cond_signal(&g_pool.done);
+    }
+    pthread_mutex_unlock(&g_pool.mu);
     return NULL;
+}
+
+static void pool_stop(void) {
+    if (!g_pool.w) return;
+    pthread_mutex_lock(&g_pool.mu);
+    g_pool.quit = 1;
+    pthread_cond_broadcast(&g_pool.go);
+    pthread_mutex_unlock(&g_pool.mu);
+    for (int t = 0; t < g_pool.n_workers; t++) {
+        pthread_join(g_pool.w[t].th, NULL);
+        free(g_pool.w[t].ring);
+    }
+    free(g_pool.w);
+    g_pool.w = NULL;
+    g_pool.n_workers = 0;
+    g_pool.quit = 0;
+}
+
+static void pool_start(int nthreads) {
+    cpu_set_t allowed;
+    int cpus[1024], n_cpus = 0;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0)
+        for (int c = 0; c < 1024 && c < CPU_SETSIZE; c++)
+            if (CPU_ISSET(c, &allowed)) cpus[n_cpus++] = c;
+    g_pool.w = (worker_t *)xrealloc(NULL, sizeof(worker_t) * (size_t)nthreads);
+    g_pool.n_workers = nthreads;
+    for (int t = 0; t < nthreads; t++) {
+        g_pool.w[t].index = t;
+        g_pool.w[t].ring = (orc_match *)xrealloc(NULL, sizeof(orc_match) * RING_ENTRIES);
+        if (pthread_create(&g_pool.w[t].th, NULL, pool_worker, &g_pool.w[t]) != 0) abort();
+        if (n_cpus > 0) {
+            cpu_set_t one;
+            CPU_ZERO(&one);
+            CPU_SET(cpus[t % n_cpus], &one);
+            pthread_setaffinity_np(g_pool.w[t].th, sizeof(one), &one);
+        }
+    }
 }
 
 static void run_jobs(job_t *proto, uint64_t n, int nthreads) {
     if (nthreads < 1) nthreads = 1;
-    if ((uint64_t)nthreads > n) nthreads = n ? (int)n : 1;
-    pthread_t *th = (pthread_t *)xrealloc(NULL, sizeof(pthread_t) * (size_t)nthreads);
-    job_t *jobs = (job_t *)xrealloc(NULL, sizeof(job_t) * (size_t)nthreads);
-    for (int t = 0; t < nthreads; t++) {
-        jobs[t] = *proto;
-        jobs[t].lo = n * (uint64_t)t / (uint64_t)nthreads;
-        jobs[t].hi = n * (uint64_t)(t + 1) / (uint64_t)nthreads;
-        if (nthreads == 1)
-            batch_worker(&jobs[t]);
-        else if (pthread_create(&th[t], NULL, batch_worker, &jobs[t]) != 0)
-            abort();
+    proto->n = n;
+    if (nthreads == 1 || n <= POOL_CHUNK) {
+        orc_match *ring = proto->store_ring ? (orc_match *)xrealloc(NULL, sizeof(orc_match) * RING_ENTRIES) : NULL;
+        run_chunk(proto, 0, n, ring);
+        free(ring);
+        return;
     }
-    if (nthreads > 1)
-        for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
-    free(th);
-    free(jobs);
+    static pthread_mutex_t serial = PTHREAD_MUTEX_INITIALIZER; /* one batch at a time owns the pool */
+    pthread_mutex_lock(&serial);
+    if (g_pool.n_workers != nthreads) {
+        pool_stop();
+        pool_start(nthreads);
+    }
+    pthread_mutex_lock(&g_pool.mu);
+    g_pool.job = *proto;
+    g_pool.next = 0;
+    g_pool.running = g_pool.n_workers;
+    g_pool.generation++;
+    pthread_cond_broadcast(&g_pool.go);
+    while (g_pool.running) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+    pthread_mutex_unlock(&g_pool.mu);
+    pthread_mutex_unlock(&serial);
+}
+
+/* The timed CPU baseline (bench.py cpu_baseline / --impl reference): the scan loops above on the crate's
+ * record layout, persistent pinned threads, every match stored into a per-thread ring, no checker hash.
+ * Returns the total match count in *total. */
+int orc_bench_batch(const orc_pma *p, int mode, const uint8_t *text, const uint64_t *offs, uint64_t n, int nthreads,
+                    uint64_t *counts, uint64_t *total) {
+    if (mode < 0 || mode > ORC_FIND_OVERLAPPING_STEPPER) return ORC_INVALID_ARGUMENT;
+    if (!mode_ok(p, mode)) return ORC_MATCH_KIND_MISMATCH;
+    uint64_t *own = NULL;
+    if (!counts) counts = own = (uint64_t *)xrealloc(NULL, (n ? n : 1) * 8);
+    job_t proto;
+    memset(&proto, 0, sizeof(proto));
+    proto.p = p;
+    proto.mode = mode;
+    proto.text = text;
+    proto.offs = offs;
+    proto.counts = counts;
+    proto.store_ring = 1;
+    run_jobs(&proto, n, nthreads);
+    uint64_t tot = 0;
+    for (uint64_t i = 0; i < n; i++) tot += counts[i];
+    if (total) *total = tot;
+    free(own);
+    return ORC_OK;
 }
 
 int orc_scan_batch(const orc_pma *p, int mode, const uint8_t *text, const uint64_t *offs, uint64_t n,

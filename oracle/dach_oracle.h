@@ -103,6 +103,12 @@ int orc_scan_batch(const orc_pma *p, int mode, const uint8_t *text, const uint64
                    int nthreads, uint64_t *counts, uint64_t *hashes, orc_match *out, uint64_t out_cap,
                    uint64_t *total);
 
+/* The timed CPU baseline of bench.py: same scan loops, on the crate's array-of-structs record layout, on a
+ * persistent pool of threads pinned to the CPUs the process may use, every match stored into a per-thread
+ * ring (a consumer collecting them), no checker hash.  counts may be NULL. */
+int orc_bench_batch(const orc_pma *p, int mode, const uint8_t *text, const uint64_t *offs, uint64_t n, int nthreads,
+                    uint64_t *counts, uint64_t *total);
+
 /* The order-sensitive tuple hash used by orc_scan_batch (also implemented on the
  * Python side and on the GPU side for full-size parity). */
 uint64_t orc_hash_step(uint64_t h, uint32_t start, uint32_t end, uint32_t value);

@@ -272,6 +272,70 @@ class OraclePma:
         return res
 
 
+_native = None
+
+
+def native_lib():
+    """liboracle_native.so: the same source built with -march=native ON THIS BOX (the timed CPU baseline);
+    falls back to the portable build if the box has no compiler."""
+    global _native
+    if _native is None:
+        path = os.path.join(ORACLE_DIR, "liboracle_native.so")
+        try:
+            subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "-B", "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            L = C.CDLL(path)
+        except Exception:
+            L = lib()
+        L.orc_bench_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p,
+                                      C.POINTER(C.c_uint64)]
+        L.orc_bench_batch.restype = C.c_int
+        _native = L
+    return _native
+
+
+def bench_batch(pma, mode, text, offs, nthreads):
+    """The timed CPU baseline (orc_bench_batch): returns the total match count."""
+    L = native_lib()
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    total = C.c_uint64()
+    rc = L.orc_bench_batch(pma._h, mode, text.ctypes.data, offs.ctypes.data, len(offs) - 1, int(nthreads), None, C.byref(total))
+    if rc != OK:
+        raise OracleError(rc)
+    return int(total.value)
+
+
+def cpu_budget():
+    """How many CPUs this process may really use: the affinity mask, cut by the cgroup CPU quota if one is set
+    (a container that sees 128 CPUs but is given 16 CPUs' worth of time runs 128 busy threads 8x slower)."""
+    info = {"os_cpu_count": os.cpu_count() or 1}
+    try:
+        info["affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        info["affinity"] = info["os_cpu_count"]
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    quota = q / per
+            break
+        except Exception:
+            continue
+    info["cgroup_cpu_quota"] = quota
+    use = info["affinity"]
+    if quota:
+        use = max(1, min(use, int(quota + 0.5)))
+    info["threads"] = use
+    return info
+
+
 def utf8_next(data, pos):
     buf = np.frombuffer(bytes(data), dtype=np.uint8)
     p = C.c_size_t(pos)

@@ -486,3 +486,136 @@ def test_stream_chunks_equal_the_stepper_over_the_whole_stream(mode):
     st = state.cpu().numpy().view(np.uint32)
     for i in range(0, n, 97):
         assert int(st[i]) == opma.state_after(bytes(streams[i]), find_mode=(mode == D.FIND))
+
+
+def _c3_small(n=2048, hay_len=4096, seed=5):
+    cfg = S.config("C3")
+    ps = S.make_patterns(cfg, n=20000)
+    pool, b = S.make_pool(cfg, ps, 8 << 20, seed=seed)
+    starts = S.window_starts(b, len(pool), n, hay_len, seed=seed + 1)
+    text, offs = S.materialise_host(pool, starts, hay_len)
+    return ps, text, offs
+
+
+def test_jobs_on_two_streams_equal_the_blocking_call():
+    """dach_job_*: scan and place only enqueue; two jobs of one automaton run on two streams at once and each
+    reproduces dach_dev_scan_batch on its batch (also with the placement on a third stream and a device-side base)."""
+    import torch
+
+    ps, text, offs = _c3_small()
+    pma = D.DoubleArrayAhoCorasick.new(ps.as_list())
+    dev = torch.device("cuda", 0)
+    half = (len(offs) - 1) // 2
+    t = torch.from_numpy(text).to(dev)
+    o = torch.from_numpy(offs.astype(np.int64)).to(dev)
+    parts = [(t, o[: half + 1]), (t, o[half:])]
+    want = [pma.scan_batch_device(D.FIND_OVERLAPPING, tt, oo) for tt, oo in parts]
+    streams = [torch.cuda.Stream(dev) for _ in range(3)]
+    jobs = [pma.job(0), pma.job(0)]
+    outs = [torch.zeros((w.matches.shape[0] + 7, 3), dtype=torch.int32, device=dev) for w in want]
+    oofs = [torch.zeros(p[1].numel(), dtype=torch.int64, device=dev) for p in parts]
+    torch.cuda.synchronize()
+    for rep in range(3):  # jobs are reused: scan -> place -> wait -> scan ...
+        for k in range(2):
+            jobs[k].scan(D.FIND_OVERLAPPING, parts[k][0], parts[k][1], outs[k].shape[0], stream=streams[k])
+        jobs[0].place(outs[0], oofs[0], stream=streams[0])
+        jobs[1].place(outs[1], oofs[1], stream=streams[2])  # another stream than the scan's
+        for k in range(2):
+            assert jobs[k].wait() == want[k].matches.shape[0]
+            assert torch.equal(outs[k][: want[k].matches.shape[0]], want[k].matches)
+            assert torch.equal(oofs[k], want[k].offsets)
+    # a device-side base shifts the placement and the offsets
+    base = torch.tensor([5], dtype=torch.int64, device=dev)
+    big = torch.zeros((outs[0].shape[0] + 5, 3), dtype=torch.int32, device=dev)
+    jobs[0].scan(D.FIND_OVERLAPPING, parts[0][0], parts[0][1], big.shape[0], stream=streams[0])
+    jobs[0].place(big, oofs[0], base=base, stream=streams[0])
+    k = jobs[0].wait()
+    assert torch.equal(big[5: 5 + k], want[0].matches) and torch.equal(oofs[0], want[0].offsets + 5)
+
+
+def _group_case(world, devices):
+    """One process drives `world` ranks (rank r on devices[r]): every rank scans its shard with a job and places
+    it through the group; rank 0's buffers must equal the single-device result of the whole batch."""
+    import torch
+
+    from daachorse_b200 import shard
+
+    ps, text, offs = _c3_small(n=1536)
+    pma = D.DoubleArrayAhoCorasick.new(ps.as_list())
+    n = len(offs) - 1
+    d0 = torch.device("cuda", devices[0])
+    whole = pma.scan_batch_device(D.FIND_OVERLAPPING, torch.from_numpy(text).to(d0), torch.from_numpy(offs.astype(np.int64)).to(d0))
+    bounds = shard.byte_balanced_ranges(offs, world)
+    cap = int(whole.matches.shape[0]) + 64
+    groups = [shard.PeerGroup(r, world, devices[r], cap, n, exchange=None) for r in range(world)]
+    blobs = [g.handle for g in groups]
+    for g in groups:
+        g.connect(blobs)
+    jobs, inputs, streams = [], [], []
+    for r in range(world):
+        dev = torch.device("cuda", devices[r])
+        lo, hi = bounds[r], bounds[r + 1]
+        tt = torch.from_numpy(text[int(offs[lo]): int(offs[hi])]).to(dev)
+        oo = torch.from_numpy((offs[lo: hi + 1] - offs[lo]).astype(np.int64)).to(dev)
+        inputs.append((tt, oo))
+        with torch.cuda.device(dev):
+            jobs.append(pma.job(devices[r]))
+            streams.append(torch.cuda.Stream(dev))
+    for step in range(3):  # the buffers are reused step after step
+        order = range(world) if step % 2 == 0 else reversed(range(world))  # issue order must not matter
+        for r in order:
+            with torch.cuda.device(devices[r]):
+                jobs[r].scan(D.FIND_OVERLAPPING, inputs[r][0], inputs[r][1], cap, stream=streams[r])
+                groups[r].place(jobs[r], bounds[r], r == world - 1, stream=streams[r])
+        for r in reversed(range(1, world)):
+            with torch.cuda.device(devices[r]):
+                groups[r].finish(stream=streams[r])
+        with torch.cuda.device(devices[0]):
+            total = groups[0].finish(stream=streams[0])
+            m, o = groups[0].result(total)
+            assert total == whole.matches.shape[0]
+            assert torch.equal(m, whole.matches) and torch.equal(o, whole.offsets)
+            m.zero_()
+            o.zero_()
+            torch.cuda.synchronize()
+    for g in groups:
+        g.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_shard_group_ranks_on_one_device(world):
+    """The exchange protocol of dach_group_* (counts published, base waited for, matches stored into rank 0's
+    buffer, done signalled) with all ranks on cuda:0 -- what needs two GPUs is only the NVLink under it."""
+    _group_case(world, [0] * world)
+
+
+def test_shard_group_across_devices():
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _group_case(2, [0, 1])
+    if torch.cuda.device_count() >= 4:
+        _group_case(4, [0, 1, 2, 3])
+
+
+def test_bad_offsets_are_refused_on_both_paths():
+    """a haystack of 4 GiB or more would be truncated silently (positions are u32); descending offsets
+    or offsets past text_bytes would index outside the text.  Host path: checked before anything is copied.
+    Device path: checked by a kernel before anything indexes with them; nothing is scanned."""
+    import torch
+
+    pma = D.DoubleArrayAhoCorasick.new(["ab", "b"])
+    text = np.frombuffer(b"abab" * 64, dtype=np.uint8)
+    for bad in ([0, 5 << 30], [0, 8, 4], [4, 0]):
+        with pytest.raises(D.DaachorseError) as e:
+            pma.scan_batch_host(D.FIND_OVERLAPPING, text, np.array(bad, dtype=np.uint64))
+        assert e.value.code == 1
+    dev = torch.device("cuda", 0)
+    t = torch.from_numpy(text).to(dev)
+    for bad in ([0, 8, 4, 16], [0, 1 << 33], [0, 100, 300]):
+        with pytest.raises(D.DaachorseError) as e:
+            pma.scan_batch_device(D.FIND_OVERLAPPING, t, torch.tensor(bad, dtype=torch.int64, device=dev))
+        assert e.value.code == 1
+    good = pma.scan_batch_device(D.FIND_OVERLAPPING, t, torch.tensor([0, 8, 8, 256], dtype=torch.int64, device=dev))
+    assert good.matches.shape[0] == 4 + 4 + 124 + 124

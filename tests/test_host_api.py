@@ -34,7 +34,7 @@ def test_abi_exports_every_declared_symbol():
     L = C.CDLL(_lib.LIB_PATH)
     for s in declared:
         assert hasattr(L, s), s
-    assert _lib.load().dach_abi_version() == 1
+    assert _lib.load().dach_abi_version() == 2
 
 
 @pytest.mark.parametrize("cw", [False, True])
