@@ -196,6 +196,89 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
     }
 }
 
+// ---- StdMachine3, two haystacks per lane ------------------------------------------------------------------
+// The lane machine is latency-bound: one dependent record fetch per lane and iteration, and a warp moves at
+// the pace of its slowest lane (profiles/r2a_*: issue slots 29-47 %, L1 data pipe 36-61 %, LTS 27-52 %,
+// 57-67 % of the stall samples on the fetch's scoreboard).  Here every lane walks TWO independent haystacks:
+// both fetches of an iteration are in flight before either result is looked at, so an SM has twice the loads
+// outstanding with the same number of warps.  Lane logic: StdMachine3's probe / resolve, unchanged; the two
+// walkers have their own event queues and take their items from the same counter.
+template <int MODE, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_scan_duo(ScanParams P) {
+    using M = StdMachine3<MODE>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    QEntry* s_queue = reinterpret_cast<QEntry*>(smem_raw);
+    const StdEnv Ev0{P.crec, nullptr, 0u, 0u, P.opos_tab, P.text_end, P.text_lo, P.root_base, P.root_opos ? CF_OUT : 0u,
+                     s_queue + threadIdx.x, blockDim.x, 0u, P.mapper, P.mapper_len, ld_u4(P.crec + D_ROOT)};
+    StdEnv Ev1 = Ev0;
+    Ev1.q = s_queue + (size_t)LANE_Q * blockDim.x + threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    Lane3 L0, L1;
+    L0.fl = L1.fl = M::IDLE;
+    L0.qn = L1.qn = 0;
+    Emitter E0, E1;
+    E0.begin(0);
+    E1.begin(0);
+    bool exhausted = false;
+    const unsigned long long n_items = P.n_items_dev ? *P.n_items_dev : P.n_items;
+    constexpr uint32_t WAIT = F_ACTIVE | F3_STOP;
+    for (;;) {
+        // ---- service phase (the warp is converged here) ----
+        if (L0.fl & F_ACTIVE) M::drain(L0, Ev0, P, E0);
+        if (L1.fl & F_ACTIVE) M::drain(L1, Ev1, P, E1);
+        if ((L0.fl & (F_ACTIVE | F_DONE)) == (F_ACTIVE | F_DONE)) {
+            E0.finish(P);
+            M::finish_item(L0, P);
+            L0.fl = M::IDLE;
+        }
+        if ((L1.fl & (F_ACTIVE | F_DONE)) == (F_ACTIVE | F_DONE)) {
+            E1.finish(P);
+            M::finish_item(L1, P);
+            L1.fl = M::IDLE;
+        }
+        const bool need0 = !(L0.fl & F_ACTIVE) && !exhausted, need1 = !(L1.fl & F_ACTIVE) && !exhausted;
+        const unsigned m0 = __ballot_sync(FULL, need0), m1 = __ballot_sync(FULL, need1);
+        if (m0 | m1) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&P.ctrl->next_item, (unsigned long long)(__popc(m0) + __popc(m1)));
+            base = __shfl_sync(FULL, base, 0);
+            if (need0) {
+                const unsigned long long item = base + __popc(m0 & lt);
+                if (item < n_items)
+                    M::begin_item(L0, P, Ev0, E0, item, nullptr);
+                else
+                    exhausted = true;
+            }
+            if (need1) {
+                const unsigned long long item = base + __popc(m0) + __popc(m1 & lt);
+                if (item < n_items)
+                    M::begin_item(L1, P, Ev1, E1, item, nullptr);
+                else
+                    exhausted = true;
+            }
+        }
+        if (!__any_sync(FULL, ((L0.fl | L1.fl) & F_ACTIVE) != 0)) break;
+        // ---- lock-step iterations until some walker needs service ----
+        bool stop = false;
+        while (!stop) {
+            M::text_topup(L0, Ev0, nullptr);
+            M::text_topup(L1, Ev1, nullptr);
+#pragma unroll 1
+            for (int k = 0; k < M::TOPUP; ++k) {
+                uint32_t own0, own1;
+                const uint32_t a0 = M::probe(L0, own0), a1 = M::probe(L1, own1);
+                const uint4 x0 = M::fetch(Ev0, a0);
+                const uint4 x1 = M::fetch(Ev1, a1);
+                M::resolve(L0, Ev0, x0, a0, own0);
+                M::resolve(L1, Ev1, x1, a1, own1);
+            }
+            stop = __any_sync(FULL, (L0.fl & WAIT) == WAIT || (L1.fl & WAIT) == WAIT);
+        }
+    }
+}
+
 // ---- exclusive scan of counts (u32) into offsets (u64) -----------------------------------
 constexpr int kScanThreads = 256;
 constexpr int kScanPerThread = 8;
@@ -383,16 +466,13 @@ __global__ void __launch_bounds__(256) k_add_base(const ScanCtrl* ctrl, const un
 
 // L2 eviction policy descriptors (see c_l2pol in scan_lane.cuh): made once per device
 __global__ void k_make_policies(unsigned long long* out, int hints) {
-    unsigned long long keep, strm;
-    if (hints) {
-        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(strm));
-    } else {
-        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(keep));
-        strm = keep;
-    }
-    out[0] = keep;
-    out[1] = strm;
+    unsigned long long normal, last, first;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(normal));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(last));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(first));
+    out[0] = hints ? last : normal;                     // automaton image
+    out[1] = hints == 1 ? first : normal;               // haystack text
+    out[2] = hints ? first : normal;                    // match blocks
 }
 
 // ---- shard groups: the exchange step over NVLink peer memory --------------------------------------
@@ -643,10 +723,11 @@ struct dach_dev {
     // ---- options (dach_dev_set_option) ----
     int64_t opt_slice_mib = 64;
     // Records of the hot region staged in shared memory by StdMachine3 (the region is laid out hottest first, so
-    // any prefix is the best set of its size).  Every KiB of shared memory is a KiB less L1 for the records
-    // that are not staged: 4096 records (64 KiB) measured best on the C3 bench (profiles/r2a_ab.txt).
-    // -1 = as many as fit next to the event queues, 0 = none.
-    int64_t opt_hot_entries = 4096;
+    // any prefix is the best set of its size).  Measured on the C3 bench (profiles/r2_hot_region.md): 9216 staged
+    // records serve 61 % of the fetches and cut the L1 wavefronts per byte by 31 %, yet the kernel gets SLOWER
+    // (124 vs 173 GB/s) -- it is bound by the latency of the fetches that still go to L2, and every KiB of shared
+    // memory is a KiB less L1 for those.  Off by default; -1 = as many as fit next to the event queues.
+    int64_t opt_hot_entries = 0;
     int64_t opt_slice_ramp = 1;      // host path: small slices at the head and the tail of a batch
     int64_t opt_tail_seg = 0;        // cut only the last 2 x lanes haystacks of a large batch (measured: -2 %, off)
     int64_t opt_gather_ordered = 1;  // copy pool blocks in output order (sequential writes)
@@ -656,9 +737,11 @@ struct dach_dev {
     int64_t opt_hot_records = 0;  // lane-per-haystack kernels: leading wide records staged in shared memory (-1 = as many as fit)
     int64_t opt_threads = 1024;
     int64_t opt_ctas_per_sm = 1;
-    int64_t opt_l2_hints = 1;  // L2 eviction policies: image evict_last, text and match blocks evict_first
-    int64_t opt_kernel = 3;  // 3: lane machines, StdMachine3 for the bytewise Standard iterators; 2: StdMachine2 instead;
-                             // 1: StdMachine instead; 0: always the lane-per-haystack kernels
+    int64_t opt_l2_hints = 2;  // L2 eviction policies: 2 = image evict_last, match blocks evict_first, text normal; 1 = text
+                               // evict_first too; 0 = none
+    int64_t opt_kernel = 3;  // 3: lane machines, StdMachine3 for the bytewise Standard iterators; 4: StdMachine3 with two
+                             // haystacks per lane; 2: StdMachine2 instead; 1: StdMachine instead; 0: always the
+                             // lane-per-haystack kernels
     // stats
     std::atomic<uint64_t> launches{0};
     double last_scan_ms = 0, last_total_ms = 0;
@@ -742,6 +825,34 @@ cudaError_t launch_std(int which, int mode, const ScanParams& P, int grid, int t
                  : launch_std_modes<StdMachine, LaneStd, 1024, 1, false>(mode, P, grid, threads, smem, st);
 }
 
+template <int MODE, int MAXT>
+cudaError_t launch_duo_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
+    static bool attr_done[kMaxDevices] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices || !attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_scan_duo<MODE, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < kMaxDevices) attr_done[dev] = true;
+    }
+    k_scan_duo<MODE, MAXT><<<grid, threads, smem, st>>>(P);
+    return cudaGetLastError();
+}
+// two haystacks per lane (option kernel = 4): 1024 threads (64 registers) or up to 768 (85 registers)
+cudaError_t launch_duo(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
+    if (threads > 768) switch (mode) {
+            case M_FIND: return launch_duo_t<M_FIND, 1024>(P, grid, threads, smem, st);
+            case M_NO_SUFFIX: return launch_duo_t<M_NO_SUFFIX, 1024>(P, grid, threads, smem, st);
+            case M_OVERLAPPING: return launch_duo_t<M_OVERLAPPING, 1024>(P, grid, threads, smem, st);
+        }
+    switch (mode) {
+        case M_FIND: return launch_duo_t<M_FIND, 768>(P, grid, threads, smem, st);
+        case M_NO_SUFFIX: return launch_duo_t<M_NO_SUFFIX, 768>(P, grid, threads, smem, st);
+        case M_OVERLAPPING: return launch_duo_t<M_OVERLAPPING, 768>(P, grid, threads, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_cw(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
     switch (mode) {
         case M_FIND: return launch_machine_t<CwMachine<M_FIND>, LaneCw, 1024, 1, false>(P, grid, threads, smem, st);
@@ -785,12 +896,12 @@ int check_mode(const dach_dev* d, int mode) {
 // L2 policy descriptors of this device (c_l2pol): made by a one-thread kernel, kept in constant memory
 bool install_policies(int hints) {
     unsigned long long* d_pol = nullptr;
-    unsigned long long h_pol[2] = {0, 0};
-    if (!cuda_ok(cudaMalloc(reinterpret_cast<void**>(&d_pol), 16), "cudaMalloc policies")) return false;
+    unsigned long long h_pol[3] = {0, 0, 0};
+    if (!cuda_ok(cudaMalloc(reinterpret_cast<void**>(&d_pol), 24), "cudaMalloc policies")) return false;
     k_make_policies<<<1, 1>>>(d_pol, hints);
-    bool ok = cuda_ok(cudaMemcpy(h_pol, d_pol, 16, cudaMemcpyDeviceToHost), "read policies");
+    bool ok = cuda_ok(cudaMemcpy(h_pol, d_pol, 24, cudaMemcpyDeviceToHost), "read policies");
     cudaFree(d_pol);
-    return ok && cuda_ok(cudaMemcpyToSymbol(c_l2pol, h_pol, 16), "install policies");
+    return ok && cuda_ok(cudaMemcpyToSymbol(c_l2pol, h_pol, 24), "install policies");
 }
 
 // ---- phase 1: items, scan kernel, per-item offsets, block index.  No synchronisation. ------------------
@@ -803,8 +914,9 @@ int enqueue_scan(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, con
         set_error("too many haystacks in one batch (max 2^32-16)");
         return DACH_INVALID_ARGUMENT;
     }
-    // the previous placement out of this workspace must be done before its buffers are rewritten
-    if (W.job_open && W.job_stream != st) cudaStreamWaitEvent(st, W.ev_placed, 0);
+    // the previous placement out of this workspace (possibly on another stream) must be done before its
+    // buffers are rewritten
+    if (W.job_open) cudaStreamWaitEvent(st, W.ev_placed, 0);
     W.job_n = n;
     W.job_items = n;
     W.job_seg = false;
@@ -834,6 +946,7 @@ int enqueue_scan(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, con
     // StdMachine2 / StdMachine3 keep ROOT's record in registers and probe it like any state: needs BASE(ROOT) != 0
     const bool std2 = v1 && !d->charwise && mode != M_LEFTMOST && d->opt_kernel >= 2 && d->root_base != 0;
     const bool std3 = std2 && d->opt_kernel >= 3;
+    const bool duo = std3 && d->opt_kernel >= 4 && ctas_per_sm == 1;
 
     if (d_state_io && !std2) {
         set_error("stream chunks need the bytewise Standard lane machine (find / find_overlapping, at most 2^24 states, "
@@ -918,10 +1031,10 @@ int enqueue_scan(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, con
     const size_t smem_budget = std::min<size_t>(d->smem_optin, 226 * 1024) / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
     size_t smem;
     if (v1) {
-        const size_t queues = (size_t)LANE_Q * threads * sizeof(QEntry);
+        const size_t queues = (size_t)LANE_Q * threads * sizeof(QEntry) * (duo ? 2 : 1);
         // StdMachine3: the front of the hot region next to the queues (whole 256-slot blocks)
         uint64_t want = 0;
-        if (std3 && d->opt_hot_entries != 0 && smem_budget > queues + 512) {
+        if (std3 && !duo && d->opt_hot_entries != 0 && smem_budget > queues + 512) {
             want = std::min<uint64_t>(d->hot_slots, (smem_budget - queues - 512) / 16);
             if (d->opt_hot_entries > 0) want = std::min<uint64_t>(want, (uint64_t)d->opt_hot_entries);
             want &= ~uint64_t(255);
@@ -965,6 +1078,7 @@ int enqueue_scan(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, con
     cudaEventRecord(W.ev[3], st);
     if (!cuda_ok(cw_machine   ? launch_cw(mode, P, grid, std::min(threads, 1024), smem, st)
                  : lm_machine ? launch_lm(P, grid, std::min(threads, 1024), smem, st)
+                 : duo        ? launch_duo(mode, P, grid, threads, smem, st)
                  : v1         ? launch_std(std3 ? 3 : std2 ? 2 : 1, mode, P, grid, threads, smem, st,
                                            ctas_per_sm >= 2 && threads <= 768 && grid % 2 == 0)
                               : launch_scan(d->charwise, mode, P, grid, threads, smem, st),
@@ -1045,7 +1159,7 @@ int finish_scan(dach_dev* d, Workspace& W, uint64_t out_cap, uint64_t* needed) {
     if (!cuda_ok(cudaEventSynchronize(W.ev_placed), "scan pipeline")) return DACH_CUDA_ERROR;
     float ms = 0;
     if (cudaEventElapsedTime(&ms, W.ev[3], W.ev[1]) == cudaSuccess) d->last_scan_ms = ms;
-    if (W.job_stream && cudaEventElapsedTime(&ms, W.ev[0], W.ev[2]) == cudaSuccess) d->last_total_ms = ms;
+    if (cudaEventElapsedTime(&ms, W.ev[0], W.ev[2]) == cudaSuccess) d->last_total_ms = ms;
     const uint64_t total = W.pinned->total;
     if (needed) *needed = total;
     if (W.pinned->ctrl.bad_offsets) {
@@ -1112,7 +1226,14 @@ int scan_batch_host_impl(dach_dev* d, int mode, const uint8_t* text, const uint6
     } drain_on_exit{d};
     // Slices of ~slice_mib MiB of text, three in flight: while slice k is scanned, slice k+1 is
     // on its way to the device and the matches of slice k-1 are on their way back.
-    const uint64_t slice_bytes = (uint64_t)std::max<int64_t>(d->opt_slice_mib, 1) << 20;
+    uint64_t slice_bytes = (uint64_t)std::max<int64_t>(d->opt_slice_mib, 1) << 20;
+    {
+        // find_iter / leftmost_find_iter / charwise work on whole haystacks: a slice should bring at least one
+        // haystack per lane (find_overlapping slices are cut into segments on the device instead)
+        const bool segmentable = !d->charwise && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX) && d->d_crec && d->opt_seg_len >= 0;
+        const uint64_t lanes = (uint64_t)d->sm_count * 1024, avg = (offs[n] - offs[0]) / n + 1;
+        if (!segmentable) slice_bytes = std::min<uint64_t>(std::max(slice_bytes, lanes * avg), 1ull << 30);
+    }
     struct Slice {
         uint64_t first, last;  // haystacks [first, last)
         uint64_t base;         // matches before this slice
@@ -1286,6 +1407,7 @@ int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
     }
     return guarded([&]() -> int {
         HostImage img;
+        if (const char* e = getenv("DACH_HOT_SLOTS")) img.want_hot_slots = (uint32_t)strtoul(e, nullptr, 10);  // layout experiments
         const int rc = build_image(pma, &img);
         if (rc) return rc;
         int ndev = 0;
@@ -1342,7 +1464,7 @@ int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
             }
             d->root_base = img.root_base;
         }
-        ok = ok && install_policies(1) && d->ws.init(false);
+        ok = ok && install_policies((int)d->opt_l2_hints) && d->ws.init(false);
         if (!ok) {
             dach_dev_free(d.release());
             return DACH_CUDA_ERROR;
@@ -1736,7 +1858,7 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
     else if (k == "l2_hints") {
         d->opt_l2_hints = value;
         DeviceGuard g(d->device);
-        if (!g.ok || !install_policies(value != 0)) return DACH_CUDA_ERROR;  // device-wide: all handles on this device
+        if (!g.ok || !install_policies((int)value)) return DACH_CUDA_ERROR;  // device-wide: all handles on this device
     } else {
         set_error("unknown option " + k);
         return DACH_INVALID_ARGUMENT;

@@ -129,14 +129,15 @@ struct ScanParams {
 };
 
 // L2 eviction policies (64-bit descriptors made once per device by k_make_policies, dev_scan.cu):
-//   [0] automaton image (records, output_pos, outputs, mapper): evict_last -- the scan is latency-bound
-//       on these dependent random fetches, and a fetch that misses L2 stalls all 32 lanes of its warp;
-//   [1] streams (haystack text, match blocks): evict_first -- each byte passes through once.
+//   [0] automaton image (records, output_pos, outputs, mapper): evict_last -- the scan is latency-bound on
+//       these dependent random fetches, and a fetch that misses L2 stalls all 32 lanes of its warp;
+//   [1] haystack text: a lane returns to its 32-byte sector for the next 8 bytes a few microseconds later;
+//   [2] match blocks: written once here, read once by k_gather: evict_first.
 // Without them the text and the match blocks push 6-7 % of the record sectors out of the 126 MB L2
-// (profiles/r1d_*: 2.4 B of DRAM reads per scanned byte, 1.0 of it text).  Option l2_hints = 0 stores
-// evict_normal in both.
+// (profiles/r1d_*: 2.4 B of DRAM reads per scanned byte, 1.0 of it text).  Option l2_hints: 0 = evict_normal
+// everywhere, 1 = text evict_first, 2 = text evict_normal (profiles/r2_l2_policies.md).
 #if defined(__CUDACC__)
-__constant__ unsigned long long c_l2pol[2];
+__constant__ unsigned long long c_l2pol[3];
 #endif
 
 DACH_HD uint4 ld_u4(const uint4* p) {
@@ -162,7 +163,7 @@ DACH_HD uint32_t ld_u32(const uint32_t* p) {
 // match blocks: written once here, read once by k_gather
 DACH_HD void st_stream_u32(uint32_t* p, uint32_t v) {
 #if defined(__CUDA_ARCH__)
-    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(c_l2pol[1]) : "memory");
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(c_l2pol[2]) : "memory");
 #else
     *p = v;
 #endif
@@ -1682,7 +1683,8 @@ struct StdMachine2 {
 // Semantics are StdMachine2's (src/bytewise.rs:1063-1088, src/bytewise/iter.rs:58-243, 344-475).
 // =============================================================================================
 
-constexpr uint32_t F3_STOP = 0x10u;  // the lane does not step: idle, finished, or its queue is full
+constexpr uint32_t F3_STOP = 0x10u;   // the lane does not step: idle, finished, or its queue is full
+constexpr uint32_t F3_LEARN = 0x20u;  // the record being fetched is the failure state's: take its (efail, fbase) and go on
 
 struct Lane3 {
     uint32_t hay_lo, hay_hi;  // address of the haystack's first byte
@@ -1791,15 +1793,31 @@ struct StdMachine3 {
         }
     }
 
-    static DACH_HD bool step(Lane3& L, const StdEnv& Ev, const uint8_t* emu_lo = nullptr) {
-        (void)emu_lo;
-        if (L.fl & F3_STOP) return false;
-        DACH_STAT(steps);
+    // One iteration = probe() -> the fetch -> resolve().  They are separate so that a lane walking two haystacks
+    // (k_scan_duo) can put both fetches in flight before it looks at either result.
+    // probe: the slot to fetch for the byte under the cursor; `own` = it is a child slot of the lane's own state
+    // (else of its failure state).  A stopped lane probes slot 0 (ROOT's record: always there) and ignores it.
+    static DACH_HD uint32_t probe(const Lane3& L, uint32_t& own) {
         const uint32_t c = L.w0 & 0xffu;
-        const uint32_t own = (L.sig >> (L.w0 & 31u)) & 1u;  // may this state have a child labelled c?
+        own = (L.sig >> (L.w0 & 31u)) & 1u;  // may this state have a child labelled c?
         const uint32_t a = ((own ? L.r0 : L.r2) >> 8) ^ c;  // its child, or the failure state's
+        return (L.fl & F3_STOP) ? 0u : a;
+    }
+    static DACH_HD void resolve(Lane3& L, const StdEnv& Ev, const uint4& x, uint32_t a, uint32_t own) {
+        if (L.fl & (F3_STOP | F3_LEARN)) {  // one test keeps both rare cases out of the common path
+            if (L.fl & F3_STOP) return;
+            // x is the failure state's record (fetched through the own-child path: r0 held its slot ^ c and the
+            // signature bit of c was set, so probe() needed no extra case): go on from its failure link
+            DACH_STAT(steps);
+            DACH_STAT(learns);
+            L.nf = x.y;
+            L.r2 = x.z;
+            L.sig &= ~(1u << (L.w0 & 31u));
+            L.fl &= ~F3_LEARN;
+            return;
+        }
+        DACH_STAT(steps);
         DACH_STAT(probes);
-        const uint4 x = fetch(Ev, a);
         if (((x.x ^ L.w0) & 0xffu) == 0) {  // CHECK == c: adopt the record
             DACH_STAT(hits);
             L.r0 = x.x;
@@ -1819,12 +1837,22 @@ struct StdMachine3 {
             DACH_STAT(miss_f2root);
             L.r2 = Ev.root_base << 8;
             L.nf |= CF_FROOT;
-        } else {  // go on from the failure state's record (rare: 0.003 per byte on the bench text)
-            DACH_STAT(learns);
-            const uint4 y = fetch(Ev, L.nf >> 8);
-            L.nf = y.y;
-            L.r2 = y.z;
+        } else {
+            // The failure state's record is needed to go on (0.003 per byte on the C3 text, 0.21 on C2's): it is
+            // the NEXT iteration's fetch -- a second dependent fetch inside this one would hold the whole warp.
+            // r0 := (its slot ^ c) << 8 with c's signature bit set makes probe() address exactly that slot.
+            L.r0 = ((L.nf >> 8) ^ (L.w0 & 0xffu)) << 8;
+            L.sig |= 1u << (L.w0 & 31u);
+            L.fl |= F3_LEARN;
         }
+    }
+    static DACH_HD bool step(Lane3& L, const StdEnv& Ev, const uint8_t* emu_lo = nullptr) {
+        (void)emu_lo;
+        if (L.fl & F3_STOP) return false;
+        uint32_t own;
+        const uint32_t a = probe(L, own);
+        const uint4 x = fetch(Ev, a);
+        resolve(L, Ev, x, a, own);
         return true;
     }
 

@@ -256,10 +256,16 @@ def pad_to_char_boundary(rows, pad=0x20):
 
 def materialise_host(pool, starts, hay_len):
     """(n * hay_len) uint8 batch + offsets on the host (small n only)."""
-    idx = starts[:, None] + np.arange(hay_len, dtype=np.int64)[None, :]
-    text = pool[idx].reshape(-1)
-    offs = (np.arange(len(starts) + 1, dtype=np.uint64) * np.uint64(hay_len))
-    return np.ascontiguousarray(text), offs
+    n = len(starts)
+    text = np.empty(n * hay_len, dtype=np.uint8)
+    rows = text.reshape(n, hay_len) if n else text.reshape(0, hay_len)
+    step = max(1, (64 << 20) // max(hay_len, 1))  # index matrices of at most 64 Mi entries at a time
+    ar = np.arange(hay_len, dtype=np.int64)[None, :]
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        rows[lo:hi] = pool[starts[lo:hi, None] + ar]
+    offs = (np.arange(n + 1, dtype=np.uint64) * np.uint64(hay_len))
+    return text, offs
 
 
 def materialise_on_device(pool_t, starts_t, hay_len, chunk=1 << 16):
@@ -269,11 +275,31 @@ def materialise_on_device(pool_t, starts_t, hay_len, chunk=1 << 16):
     n = starts_t.numel()
     out = torch.empty((n, hay_len), dtype=torch.uint8, device=pool_t.device)
     view = pool_t.unfold(0, hay_len, 1)
+    chunk = max(1, min(chunk, (1 << 30) // hay_len))  # at most 1 GiB of gathered rows at a time
     for lo in range(0, n, chunk):
         hi = min(n, lo + chunk)
         out[lo:hi] = view[starts_t[lo:hi]]
     offs = torch.arange(n + 1, dtype=torch.int64, device=pool_t.device) * hay_len
     return out.reshape(-1), offs
+
+
+def pad_to_char_boundary_device(text_t, n, hay_len, pad=0x20):
+    """pad_to_char_boundary on a device batch of n windows x hay_len bytes, in place."""
+    import torch
+
+    rows = text_t.view(n, hay_len)
+    done = torch.zeros(n, dtype=torch.bool, device=rows.device)
+    for t in range(1, 4):
+        if t > hay_len:
+            break
+        bt = rows[:, hay_len - t]
+        is_cont = (bt & 0xC0) == 0x80
+        need = torch.where(bt < 0x80, 1, torch.where(bt < 0xE0, 2, torch.where(bt < 0xF0, 3, 4)))
+        cut = (~done) & (~is_cont) & (need > t)
+        for k in range(1, t + 1):
+            rows[cut, hay_len - k] = pad
+        done |= ~is_cont
+    return text_t
 
 
 # ---- named configs --------------------------------------------------------------------------------

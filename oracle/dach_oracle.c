@@ -1345,6 +1345,17 @@ uint64_t orc_hash_step(uint64_t h, uint32_t start, uint32_t end, uint32_t value)
     return h;
 }
 
+/* per-haystack order-sensitive hashes of an existing result (matches + n+1 offsets): what orc_scan_batch
+ * reports in `hashes`, computed from another implementation's output so that the two can be compared
+ * without moving the tuples around */
+void orc_hash_matches(const orc_match *m, const uint64_t *offs, uint64_t n, uint64_t *hashes) {
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t h = 0;
+        for (uint64_t k = offs[i]; k < offs[i + 1]; k++) h = orc_hash_step(h, m[k].start, m[k].end, m[k].value);
+        hashes[i] = h;
+    }
+}
+
 typedef struct {
     orc_match *out;
     size_t cap, n;

@@ -112,6 +112,8 @@ int orc_bench_batch(const orc_pma *p, int mode, const uint8_t *text, const uint6
 /* The order-sensitive tuple hash used by orc_scan_batch (also implemented on the
  * Python side and on the GPU side for full-size parity). */
 uint64_t orc_hash_step(uint64_t h, uint32_t start, uint32_t end, uint32_t value);
+/* per-haystack hashes (as orc_scan_batch's `hashes`) of an existing result: matches + n+1 offsets */
+void orc_hash_matches(const orc_match *m, const uint64_t *offs, uint64_t n, uint64_t *hashes);
 
 #ifdef __cplusplus
 }

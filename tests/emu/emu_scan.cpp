@@ -129,6 +129,95 @@ static void run_machine(const ScanParams& P, const StdEnv& Ev0, const uint8_t* l
     }
 }
 
+// k_scan_duo: StdMachine3 with two haystacks per lane (mirrors the kernel in dev_scan.cu)
+template <int MODE>
+static void run_duo(const ScanParams& P, const StdEnv& Ev0, int n_warps) {
+    using M = StdMachine3<MODE>;
+    struct Warp {
+        Lane3 L[2][32];
+        Emitter E[2][32];
+        StdEnv Ev[2][32];
+        std::vector<QEntry> queue;
+        bool exhausted[32];
+        bool finished;
+    };
+    std::vector<Warp> warps(n_warps);
+    for (auto& w : warps) {
+        w.queue.assign((size_t)LANE_Q * 32 * 2, QEntry{0, 0});
+        for (int l = 0; l < 32; ++l) {
+            for (int k = 0; k < 2; ++k) {
+                w.L[k][l].fl = M::IDLE;
+                w.L[k][l].qn = 0;
+                w.E[k][l].begin(0);
+                w.Ev[k][l] = Ev0;
+                w.Ev[k][l].q = w.queue.data() + (size_t)k * LANE_Q * 32 + l;
+                w.Ev[k][l].q_stride = 32;
+            }
+            w.exhausted[l] = false;
+        }
+        w.finished = false;
+    }
+    constexpr uint32_t WAIT = F_ACTIVE | F3_STOP;
+    bool any_left = true;
+    while (any_left) {
+        any_left = false;
+        for (auto& w : warps) {
+            if (w.finished) continue;
+            for (int k = 0; k < 2; ++k)
+                for (int l = 0; l < 32; ++l)
+                    if (w.L[k][l].fl & F_ACTIVE) M::drain(w.L[k][l], w.Ev[k][l], P, w.E[k][l]);
+            for (int k = 0; k < 2; ++k)
+                for (int l = 0; l < 32; ++l)
+                    if ((w.L[k][l].fl & (F_ACTIVE | F_DONE)) == (F_ACTIVE | F_DONE)) {
+                        w.E[k][l].finish(P);
+                        M::finish_item(w.L[k][l], P);
+                        w.L[k][l].fl = M::IDLE;
+                    }
+            unsigned m[2] = {0, 0};
+            for (int k = 0; k < 2; ++k)
+                for (int l = 0; l < 32; ++l)
+                    if (!(w.L[k][l].fl & F_ACTIVE) && !w.exhausted[l]) m[k] |= 1u << l;
+            if (m[0] | m[1]) {
+                const unsigned long long base = P.ctrl->next_item;
+                P.ctrl->next_item += __builtin_popcount(m[0]) + __builtin_popcount(m[1]);
+                for (int l = 0; l < 32; ++l) {
+                    const unsigned lt = (1u << l) - 1u;
+                    for (int k = 0; k < 2; ++k)
+                        if (m[k] & (1u << l)) {
+                            const unsigned long long item = base + (k ? __builtin_popcount(m[0]) : 0) + __builtin_popcount(m[k] & lt);
+                            if (item < P.n_items)
+                                M::begin_item(w.L[k][l], P, w.Ev[k][l], w.E[k][l], item, nullptr);
+                            else
+                                w.exhausted[l] = true;
+                        }
+                }
+            }
+            bool any_active = false;
+            for (int l = 0; l < 32; ++l) any_active |= ((w.L[0][l].fl | w.L[1][l].fl) & F_ACTIVE) != 0;
+            if (!any_active) {
+                w.finished = true;
+                continue;
+            }
+            any_left = true;
+            bool stop = false;
+            while (!stop) {
+                for (int k = 0; k < 2; ++k)
+                    for (int l = 0; l < 32; ++l) M::text_topup(w.L[k][l], w.Ev[k][l], nullptr);
+                for (int it = 0; it < M::TOPUP; ++it)
+                    for (int l = 0; l < 32; ++l) {
+                        uint32_t own0, own1;
+                        const uint32_t a0 = M::probe(w.L[0][l], own0), a1 = M::probe(w.L[1][l], own1);
+                        const uint4 x0 = M::fetch(w.Ev[0][l], a0), x1 = M::fetch(w.Ev[1][l], a1);
+                        M::resolve(w.L[0][l], w.Ev[0][l], x0, a0, own0);
+                        M::resolve(w.L[1][l], w.Ev[1][l], x1, a1, own1);
+                    }
+                for (int l = 0; l < 32; ++l)
+                    if ((w.L[0][l].fl & WAIT) == WAIT || (w.L[1][l].fl & WAIT) == WAIT) stop = true;
+            }
+        }
+    }
+}
+
 template <int MODE>
 static void run_items_v1(const ScanParams& P, const StdEnv& Ev0, const uint8_t* lo, int n_warps) {
     run_machine<StdMachine<MODE>, LaneStd>(P, Ev0, lo, n_warps);
@@ -242,6 +331,12 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
             if (mode == M_OVERLAPPING) run_machine<CwMachine<M_OVERLAPPING>, LaneCw>(P, Ev, lo, n_warps);
             if (mode == M_NO_SUFFIX) run_machine<CwMachine<M_NO_SUFFIX>, LaneCw>(P, Ev, lo, n_warps);
             if (mode == M_LEFTMOST) run_machine<CwMachine<M_LEFTMOST>, LaneCw>(P, Ev, lo, n_warps);
+        } else if (mode != M_LEFTMOST && kernel_version >= 4 && img.root_base != 0) {
+            if (getenv("DACH_EMU_TRACE")) fprintf(stderr, "emu: StdMachine3, two haystacks per lane\n");
+            Ev.hot_n = 0;
+            if (mode == M_FIND) run_duo<M_FIND>(P, Ev, n_warps);
+            if (mode == M_OVERLAPPING) run_duo<M_OVERLAPPING>(P, Ev, n_warps);
+            if (mode == M_NO_SUFFIX) run_duo<M_NO_SUFFIX>(P, Ev, n_warps);
         } else if (mode != M_LEFTMOST && kernel_version >= 3 && img.root_base != 0) {
             if (getenv("DACH_EMU_TRACE")) fprintf(stderr, "emu: StdMachine3, %u hot records\n", entries);
             if (mode == M_FIND) run_machine<StdMachine3<M_FIND>, Lane3>(P, Ev, lo, n_warps);

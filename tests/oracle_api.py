@@ -305,6 +305,23 @@ def bench_batch(pma, mode, text, offs, nthreads):
     return int(total.value)
 
 
+def hash_matches(matches, offs):
+    """Per-haystack order-sensitive hashes of a result produced elsewhere (the GPU): structured or (k, 3)
+    u32/i32 matches + n+1 offsets.  Comparable with scan_batch(...)["hashes"]."""
+    m = np.ascontiguousarray(matches)
+    if m.dtype != MATCH_DTYPE:
+        m = np.ascontiguousarray(m.reshape(-1, 3)).view(np.uint32).reshape(-1).view(MATCH_DTYPE)
+    offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    n = len(offs) - 1
+    out = np.zeros(max(n, 1), dtype=np.uint64)
+    L = lib()
+    L.orc_hash_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.orc_hash_matches.restype = None
+    pad = m if m.size else np.zeros(1, dtype=MATCH_DTYPE)
+    L.orc_hash_matches(pad.ctypes.data, offs.ctypes.data, n, out.ctypes.data)
+    return out[:n]
+
+
 def cpu_budget():
     """How many CPUs this process may really use: the affinity mask, cut by the cgroup CPU quota if one is set
     (a container that sees 128 CPUs but is given 16 CPUs' worth of time runs 128 busy threads 8x slower)."""

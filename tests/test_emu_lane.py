@@ -36,7 +36,7 @@ def test_golden_vectors(variant, iterator, kind, t):
     wire = O.OraclePma.build(t["patterns"], charwise=cw, match_kind=O.KIND[kind]).serialize()
     hay = t["haystack"].encode()
     text = np.frombuffer(hay, dtype=np.uint8)
-    for hot, kernel in ((0, 1), (3, 0), (0, 2), (0, 3), (256, 3), (1 << 16, 3)):
+    for hot, kernel in ((0, 1), (3, 0), (0, 2), (0, 3), (256, 3), (1 << 16, 3), (0, 4)):
         rc, m, oo, need = E.scan(wire, cw, MODE[iterator], text, np.array([0, len(hay)], dtype=np.uint64), hot_n=hot,
                                  kernel=kernel)
         assert rc == 0
@@ -75,7 +75,7 @@ def test_random_batches(seed, kind, cw):
     modes = [3] if kind else [0, 1, 2]
     for mode in modes:
         ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
-        for hot, kernel in ((0, 1), (5, 0), (0, 2), (0, 3), (256, 3), (512, 3), (1 << 16, 3)):
+        for hot, kernel in ((0, 1), (5, 0), (0, 2), (0, 3), (256, 3), (512, 3), (1 << 16, 3), (0, 4)):
             rc, m, oo, need = E.scan(wire, cw, mode, text, offs, hot_n=hot, kernel=kernel)
             assert rc == 0
             assert need == ref["total"]
@@ -93,7 +93,7 @@ def test_unaligned_offsets_and_long_chains():
         text = np.frombuffer(b"x" * shift + b"a" * 70 + b"b" + b"a" * 40, dtype=np.uint8)
         offs = np.array([shift, shift + 50, shift + 50, shift + 111], dtype=np.uint64)
         ref = pma.scan_batch(O.FIND_OVERLAPPING, text, offs, want_matches=True)
-        for kernel in (0, 1, 2, 3):
+        for kernel in (0, 1, 2, 3, 4):
             rc, m, oo, need = E.scan(wire, False, 1, text, offs, kernel=kernel, hot_n=256 if kernel == 3 else 0)
             assert rc == 0 and m.tobytes() == ref["matches"].tobytes()
             assert list(oo) == [0] + list(np.cumsum(ref["counts"]))
@@ -136,7 +136,7 @@ def test_segments_reproduce_the_sequential_scan(seed):
     for mode in (1, 2):
         ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
         for seg_len in (1, 3, 16, 64, 100, 1000):
-            for kernel in (1, 2, 3):
+            for kernel in (1, 2, 3, 4):
                 for seg_from in (0, 11, len(hays) - 3):  # > 0: only the tail of the batch is cut
                     rc, m, oo, need = E.scan(wire, False, mode, text, offs, seg_len=seg_len, kernel=kernel, seg_from=seg_from,
                                              hot_n=256 if kernel == 3 else 0)
@@ -186,7 +186,7 @@ def _stream_case(seed):
 
 @pytest.mark.parametrize("seed", range(24))
 @pytest.mark.parametrize("mode", [0, 1])
-@pytest.mark.parametrize("kernel", [3, 2])
+@pytest.mark.parametrize("kernel", [3, 2, 4])
 def test_stream_chunks_equal_the_stepper_over_the_whole_stream(seed, mode, kernel):
     """dach_dev_scan_stream (lane machine, emulated): streams cut into ragged chunks and scanned round
     by round with the state carried over report exactly what the crate's stepper reports over the
@@ -249,7 +249,7 @@ def test_hot_first_relayout_at_dictionary_shape(seed, hot_slots):
             text = np.frombuffer(b"".join(hays), dtype=np.uint8)
             for mode in ([3] if kind else [0, 1, 2]):
                 ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
-                for hot, kernel in ((0, 1), (0, 2), (0, 3), (256, 3), (768, 3), (1 << 16, 3)):
+                for hot, kernel in ((0, 1), (0, 2), (0, 3), (256, 3), (768, 3), (1 << 16, 3), (0, 4)):
                     rc, m, oo, need = E.scan(wire, False, mode, text, offs, hot_n=hot, kernel=kernel)
                     assert rc == 0 and need == ref["total"]
                     assert m.tobytes() == ref["matches"].tobytes(), (mode, hot, kernel)

@@ -157,7 +157,7 @@ def test_kernel_options_do_not_change_results():
     base = pma.scan_batch_host(D.FIND_OVERLAPPING, text, offs)
     for opts in ({"hot_records": -1}, {"hot_records": 17}, {"threads": 128}, {"threads": 512, "ctas_per_sm": 2},
                  {"kernel": 0}, {"kernel": 1}, {"kernel": 2}, {"kernel": 2, "threads": 256}, {"kernel": 3, "threads": 256},
-                 {"kernel": 3, "threads": 768, "ctas_per_sm": 2}, {"kernel": 0, "hot_records": 100}, {"l2_persist": 0}, {"hot_entries": 0},
+                 {"kernel": 3, "threads": 768, "ctas_per_sm": 2}, {"kernel": 4}, {"kernel": 4, "threads": 768}, {"kernel": 4, "threads": 256}, {"kernel": 0, "hot_records": 100}, {"l2_hints": 0}, {"l2_hints": 1}, {"hot_entries": 4096},
                  {"hot_entries": 256}, {"hot_entries": 8192}, {"hot_entries": 1 << 20}, {"gather_ordered": 0}, {"gather_ordered": 2}, {"tail_seg": 1}):
         for k, v in opts.items():
             pma.set_option(k, v)
@@ -167,8 +167,8 @@ def test_kernel_options_do_not_change_results():
         pma.set_option("threads", 1024)
         pma.set_option("ctas_per_sm", 1)
         pma.set_option("kernel", DEFAULT_KERNEL)
-        pma.set_option("l2_persist", 1)
-        pma.set_option("hot_entries", -1)
+        pma.set_option("l2_hints", 2)
+        pma.set_option("hot_entries", 0)
         pma.set_option("gather_ordered", 1)
         pma.set_option("tail_seg", 0)
 
@@ -246,7 +246,7 @@ def test_config_c3_reduced_batch_all_standard_modes():
     # without its shared-memory records) agree
     for mode in (D.FIND_OVERLAPPING, D.FIND, D.FIND_OVERLAPPING_NO_SUFFIX):
         res = []
-        for k, hot in ((1, -1), (2, -1), (3, -1), (3, 0), (3, 4096)):
+        for k, hot in ((1, -1), (2, -1), (3, -1), (3, 0), (3, 4096), (4, 0)):
             pma.set_option("kernel", k)
             pma.set_option("hot_entries", hot)
             res.append(pma.scan_batch_host(mode, text, offs))
