@@ -44,6 +44,8 @@ CONFIGS = {
     "C4": dict(synth="C4", mode="leftmost_find_iter", what="100k-pat CJK charwise LeftmostLongest", batches=1, steps=20),
     "C5": dict(synth="C5", mode="find_overlapping_iter", what="1M-pat bytewise, 12.5 GiB resident per GPU in 1 GiB windows",
                batches=13, steps=13, window=1024),
+    # not a BASELINE.json config: C4's data on a bytewise LeftmostLongest automaton (the LmMachine kernel)
+    "C4-bw": dict(synth="C4", mode="leftmost_find_iter", what="100k-pat CJK bytewise LeftmostLongest", batches=1, steps=20, variant="bytewise"),
 }
 
 
@@ -130,7 +132,7 @@ class Workload:
         nb = (pool_mib << 20) if pool_mib else self.cfg["pool_bytes"]
         self.pool, self.bounds = S.make_pool(self.cfg, self.ps, nb, seed=2 + 1000 * rank)
         self.starts = S.window_starts(self.bounds, len(self.pool), self.n_total, self.hay_len, seed=3 + 1000 * rank)
-        self.charwise = self.cfg["variant"] == "charwise"
+        self.charwise = self.spec.get("variant", self.cfg["variant"]) == "charwise"
         self.match_kind = self.cfg["match_kind"]
 
     def batch_ranges(self):
@@ -148,7 +150,7 @@ class Workload:
     def host_batch(self, lo, hi):
         """The same bytes the device batch holds, regenerated on the host (oracle side)."""
         text, offs = self.S.materialise_host(self.pool, self.starts[lo:hi], self.hay_len)
-        if self.name == "C4":
+        if self.spec["synth"] == "C4":
             text = self.S.pad_to_char_boundary(text.reshape(hi - lo, self.hay_len)).reshape(-1)
         return text, offs
 
@@ -305,7 +307,7 @@ def main():
         batches = []
         for lo, hi in ranges:
             t, o = S.materialise_on_device(pool_t, starts_t[lo:hi], hay_len)
-            if args.config == "C4":
+            if W.spec["synth"] == "C4":
                 S.pad_to_char_boundary_device(t, hi - lo, hay_len)
             batches.append((t, o))
     del pool_t
@@ -499,7 +501,8 @@ def main():
     achieved = step_bytes / (k_ms * 1e-3) / 1e9
     kname = {"C3": "k_scan_machine<StdMachine3<M_OVERLAPPING>, Lane3, 1024, 1, true>", "C3-find": "k_scan_machine<StdMachine3<M_FIND>, Lane3, 1024, 1, true>",
              "C2": "k_scan_machine<StdMachine3<M_OVERLAPPING>, Lane3, 1024, 1, true>", "C5": "k_scan_machine<StdMachine3<M_OVERLAPPING>, Lane3, 1024, 1, true>",
-             "C4": "k_scan_machine<CwMachine<M_LEFTMOST>, LaneCw, 1024, 1, false>"}[args.config]
+             "C4": "k_scan_machine<CwMachine<M_LEFTMOST>, LaneCw, 1024, 1, false>",
+             "C4-bw": "k_scan_machine<LmMachine, LaneLm, 1024, 1, false>"}[args.config]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": kname, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": step_bytes, "peak_source": peak_src,

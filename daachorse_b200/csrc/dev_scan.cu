@@ -203,12 +203,26 @@ __global__ void __launch_bounds__(MAXT, MINB) k_scan_machine(ScanParams P) {
 // both fetches of an iteration are in flight before either result is looked at, so an SM has twice the loads
 // outstanding with the same number of warps.  Lane logic: StdMachine3's probe / resolve, unchanged; the two
 // walkers have their own event queues and take their items from the same counter.
-template <int MODE, int MAXT>
+template <int MODE, int MAXT, bool HOT>
 __global__ void __launch_bounds__(MAXT, 1) k_scan_duo(ScanParams P) {
     using M = StdMachine3<MODE>;
+    // dynamic shared memory: [hot records hot_entries x 16 B (HOT only)][event queues 2 x LANE_Q x blockDim x 8 B]
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    QEntry* s_queue = reinterpret_cast<QEntry*>(smem_raw);
-    const StdEnv Ev0{P.crec, nullptr, 0u, 0u, P.opos_tab, P.text_end, P.text_lo, P.root_base, P.root_opos ? CF_OUT : 0u,
+    uint4* s_hot = reinterpret_cast<uint4*>(smem_raw);
+    QEntry* s_queue = reinterpret_cast<QEntry*>(smem_raw + (HOT ? (size_t)P.hot_entries * 16 : 0));
+    __shared__ __align__(8) uint64_t s_bar;
+    if (HOT) {
+        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t hot_bytes = P.hot_entries * 16u;
+            mbar_expect_tx(&s_bar, hot_bytes);
+            for (uint32_t off = 0; off < hot_bytes; off += 32768u)
+                tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_hot) + off, reinterpret_cast<const unsigned char*>(P.crec) + off,
+                             min(32768u, hot_bytes - off), &s_bar);
+        }
+    }
+    const StdEnv Ev0{P.crec, s_hot, smem_u32(s_hot), HOT ? P.hot_entries : 0u, P.opos_tab, P.text_end, P.text_lo, P.root_base, P.root_opos ? CF_OUT : 0u,
                      s_queue + threadIdx.x, blockDim.x, 0u, P.mapper, P.mapper_len, ld_u4(P.crec + D_ROOT)};
     StdEnv Ev1 = Ev0;
     Ev1.q = s_queue + (size_t)LANE_Q * blockDim.x + threadIdx.x;
@@ -224,6 +238,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_scan_duo(ScanParams P) {
     bool exhausted = false;
     const unsigned long long n_items = P.n_items_dev ? *P.n_items_dev : P.n_items;
     constexpr uint32_t WAIT = F_ACTIVE | F3_STOP;
+    if (HOT) mbar_wait(&s_bar, 0);
     for (;;) {
         // ---- service phase (the warp is converged here) ----
         if (L0.fl & F_ACTIVE) M::drain(L0, Ev0, P, E0);
@@ -733,6 +748,7 @@ struct dach_dev {
     int64_t opt_gather_ordered = 1;  // copy pool blocks in output order (sequential writes)
     int64_t opt_gather_u = 4;     // pooled blocks in flight per warp of k_gather (2, 4 or 8)
     int64_t opt_reserve_sms = 0;  // SMs left free for concurrent kernels
+    int64_t opt_smem_pad_kib = 0;  // lane machines: extra dynamic shared memory per CTA, i.e. that much less L1 (experiments)
     int64_t opt_seg_len = 0;  // 0: automatic; > 0: forced segment length; < 0: no segmentation
     int64_t opt_hot_records = 0;  // lane-per-haystack kernels: leading wide records staged in shared memory (-1 = as many as fit)
     int64_t opt_threads = 1024;
@@ -825,32 +841,33 @@ cudaError_t launch_std(int which, int mode, const ScanParams& P, int grid, int t
                  : launch_std_modes<StdMachine, LaneStd, 1024, 1, false>(mode, P, grid, threads, smem, st);
 }
 
-template <int MODE, int MAXT>
+template <int MODE, int MAXT, bool HOT>
 cudaError_t launch_duo_t(const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
     static bool attr_done[kMaxDevices] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= kMaxDevices || !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_scan_duo<MODE, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_scan_duo<MODE, MAXT, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < kMaxDevices) attr_done[dev] = true;
     }
-    k_scan_duo<MODE, MAXT><<<grid, threads, smem, st>>>(P);
+    k_scan_duo<MODE, MAXT, HOT><<<grid, threads, smem, st>>>(P);
     return cudaGetLastError();
+}
+template <int MAXT, bool HOT>
+cudaError_t launch_duo_m(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
+    switch (mode) {
+        case M_FIND: return launch_duo_t<M_FIND, MAXT, HOT>(P, grid, threads, smem, st);
+        case M_NO_SUFFIX: return launch_duo_t<M_NO_SUFFIX, MAXT, HOT>(P, grid, threads, smem, st);
+        case M_OVERLAPPING: return launch_duo_t<M_OVERLAPPING, MAXT, HOT>(P, grid, threads, smem, st);
+    }
+    return cudaErrorInvalidValue;
 }
 // two haystacks per lane (option kernel = 4): 1024 threads (64 registers) or up to 768 (85 registers)
 cudaError_t launch_duo(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
-    if (threads > 768) switch (mode) {
-            case M_FIND: return launch_duo_t<M_FIND, 1024>(P, grid, threads, smem, st);
-            case M_NO_SUFFIX: return launch_duo_t<M_NO_SUFFIX, 1024>(P, grid, threads, smem, st);
-            case M_OVERLAPPING: return launch_duo_t<M_OVERLAPPING, 1024>(P, grid, threads, smem, st);
-        }
-    switch (mode) {
-        case M_FIND: return launch_duo_t<M_FIND, 768>(P, grid, threads, smem, st);
-        case M_NO_SUFFIX: return launch_duo_t<M_NO_SUFFIX, 768>(P, grid, threads, smem, st);
-        case M_OVERLAPPING: return launch_duo_t<M_OVERLAPPING, 768>(P, grid, threads, smem, st);
-    }
-    return cudaErrorInvalidValue;
+    if (threads > 768)
+        return P.hot_entries ? launch_duo_m<1024, true>(mode, P, grid, threads, smem, st) : launch_duo_m<1024, false>(mode, P, grid, threads, smem, st);
+    return P.hot_entries ? launch_duo_m<768, true>(mode, P, grid, threads, smem, st) : launch_duo_m<768, false>(mode, P, grid, threads, smem, st);
 }
 
 cudaError_t launch_cw(int mode, const ScanParams& P, int grid, int threads, size_t smem, cudaStream_t st) {
@@ -948,8 +965,8 @@ int enqueue_scan(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, con
     const bool std3 = std2 && d->opt_kernel >= 3;
     const bool duo = std3 && d->opt_kernel >= 4 && ctas_per_sm == 1;
 
-    if (d_state_io && !std2) {
-        set_error("stream chunks need the bytewise Standard lane machine (find / find_overlapping, at most 2^24 states, "
+    if (d_state_io && !std2 && !cw_machine) {
+        set_error("stream chunks need a Standard lane machine (find / find_overlapping, at most 2^24 states, bytewise: "
                   "BASE(ROOT) != 0, no empty pattern for find)");
         return DACH_INVALID_ARGUMENT;
     }
@@ -1034,12 +1051,13 @@ int enqueue_scan(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, con
         const size_t queues = (size_t)LANE_Q * threads * sizeof(QEntry) * (duo ? 2 : 1);
         // StdMachine3: the front of the hot region next to the queues (whole 256-slot blocks)
         uint64_t want = 0;
-        if (std3 && !duo && d->opt_hot_entries != 0 && smem_budget > queues + 512) {
+        if (std3 && d->opt_hot_entries != 0 && smem_budget > queues + 512) {
             want = std::min<uint64_t>(d->hot_slots, (smem_budget - queues - 512) / 16);
             if (d->opt_hot_entries > 0) want = std::min<uint64_t>(want, (uint64_t)d->opt_hot_entries);
             want &= ~uint64_t(255);
         }
         smem = (size_t)want * 16 + queues;
+        if (d->opt_smem_pad_kib > 0) smem = std::min<size_t>(smem + ((size_t)d->opt_smem_pad_kib << 10), smem_budget);
         P.hot_n = 0;
         P.hot_entries = (uint32_t)want;
     } else {
@@ -1853,6 +1871,8 @@ int dach_dev_set_option(dach_dev* d, const char* name, int64_t value) {
         d->opt_gather_u = value;
     else if (k == "reserve_sms")
         d->opt_reserve_sms = value;
+    else if (k == "smem_pad_kib")
+        d->opt_smem_pad_kib = value;
     else if (k == "hot_entries")
         d->opt_hot_entries = value;
     else if (k == "l2_hints") {

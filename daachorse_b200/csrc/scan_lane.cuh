@@ -1154,7 +1154,11 @@ struct CwMachine {
     static constexpr bool LAZY = true;
     static constexpr bool LEAN = false;
     static constexpr uint32_t IDLE = 0;
-    static DACH_HD void finish_item(const LaneCw&, const ScanParams&) {}
+    // the item is complete: hand the state on to the next chunk of the stream (the charwise steppers,
+    // src/charwise/iter.rs:403-534; the charwise image keeps the crate's state ids)
+    static DACH_HD void finish_item(const LaneCw& L, const ScanParams& P) {
+        if (P.state_io) P.state_io[L.item] = L.cur;
+    }
     static constexpr bool LM = MODE == M_LEFTMOST;
     using Std = StdMachine<M_OVERLAPPING>;
 
@@ -1424,6 +1428,21 @@ struct CwMachine {
         L.it = (LM && (Ev.root_flags & CF_OUT)) ? IT_INIT : 0u;
         E.begin((uint32_t)item);
         restart(L, Ev, emu_lo, true);
+        if (!LM && P.state_io) {
+            // a chunk of a stream (whole chars): resume in the state the previous chunk ended in; the outputs of
+            // that state were reported with the previous chunk
+            const uint32_t st = P.state_io[item];
+            if (st != D_ROOT && st < P.n_slots) {
+                const uint4 x = ld_u4(Ev.glob + st);
+                L.cb = x.x >> 8;
+                L.sig = (x.x & 0xffu) | ((x.z & 0xffu) << 8);
+                L.nf = x.y;
+                L.nfb = x.z;
+                L.cur = st;
+                L.addr = st;
+            }
+            return;
+        }
         if (!LM && MODE != M_FIND && (Ev.root_flags & CF_OUT)) {  // ROOT's output list is pending at position 0
             QEntry e;
             e.end = 0;

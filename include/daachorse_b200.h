@@ -152,23 +152,24 @@ int dach_scan_batch_host(dach_dev *dev, int mode, const uint8_t *text, const uin
                          uint64_t *needed);
 
 /* Chunks of streams -- the batch form of the crate's steppers (FindStepper /
- * FindOverlappingStepper, src/bytewise/iter.rs:344-475, constructors src/bytewise.rs:627-729):
- * haystack i is the next chunk of stream i.  Bytewise Standard automata; mode is DACH_FIND
- * or DACH_FIND_OVERLAPPING.
+ * FindOverlappingStepper, src/bytewise/iter.rs:344-475, constructors src/bytewise.rs:627-729;
+ * charwise: src/charwise/iter.rs:403-534, constructors src/charwise.rs:638,734): haystack i is
+ * the next chunk of stream i.  Standard automata; mode is DACH_FIND or DACH_FIND_OVERLAPPING.
+ * A chunk of a charwise stream holds whole chars (the charwise steppers consume chars).
  *   d_state  device pointer, n u32, in/out: the stepper's state_id.  In: the state the
  *            previous chunk of the stream ended in (0 = ROOT for a new stream).  Out: the
- *            state after the chunk's last byte.  State ids are the crate's (the device image is
- *            renumbered hot-first; ids are translated at the boundary), so chunks may alternate
- *            between this library and the crate's own steppers.
+ *            state after the chunk's last byte.  State ids are the crate's (the bytewise device
+ *            image is renumbered hot-first; ids are translated at the boundary), so chunks may
+ *            alternate between this library and the crate's own steppers.
  *   d_pos    device pointer, n u32, or NULL: the stepper's pos at the chunk's first byte;
  *            it is added to start and end of the chunk's matches (stream coordinates,
  *            modulo 2^32).  NULL = positions relative to the chunk.
- * What is reported: for every byte of the chunk, consume(byte) followed by matches() -- the
+ * What is reported: for every byte (char) of the chunk, consume() followed by matches() -- the
  * matches() of the incoming state belong to the previous chunk and are not repeated.  All
  * other arguments, the output layout and the return codes are those of dach_dev_scan_batch;
  * on DACH_OUTPUT_OVERFLOW d_state has been advanced already (keep a copy to retry).
- * DACH_INVALID_ARGUMENT where the bytewise Standard lane machine does not apply (more than
- * 2^24 states, a ROOT without children, DACH_FIND with an empty pattern in the set). */
+ * DACH_INVALID_ARGUMENT where no Standard lane machine applies (more than 2^24 states; bytewise:
+ * a ROOT without children; DACH_FIND with an empty pattern in the set). */
 int dach_dev_scan_stream(dach_dev *dev, int mode, const uint8_t *d_text, const uint64_t *d_offs,
                          uint64_t n, uint64_t text_bytes, uint32_t *d_state, const uint32_t *d_pos,
                          dach_match *d_out, uint64_t out_cap, uint64_t *d_out_offs,

@@ -1,4 +1,4 @@
-//! `extern "C"` declarations of libdaachorse_b200 (include/daachorse_b200.h, ABI version 1).
+//! `extern "C"` declarations of libdaachorse_b200 (include/daachorse_b200.h, ABI version 2).
 //! Not compiled in this repository (no Rust toolchain in the build image).
 #![allow(non_camel_case_types)]
 use core::ffi::{c_char, c_void};
@@ -19,6 +19,15 @@ pub struct DachPma {
 pub struct DachDev {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct DachJob {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct DachGroup {
+    _private: [u8; 0],
+}
+pub const DACH_GROUP_HANDLE_BYTES: usize = 256;
 
 // status codes
 pub const DACH_OK: i32 = 0;
@@ -63,4 +72,23 @@ extern "C" {
     pub fn dach_dev_scan_stream(dev: *mut DachDev, mode: i32, d_text: *const u8, d_offs: *const u64, n: u64,
                                 text_bytes: u64, d_state: *mut u32, d_pos: *const u32, d_out: *mut DachMatch,
                                 out_cap: u64, d_out_offs: *mut u64, needed: *mut u64, stream: *mut c_void) -> i32;
+
+    /// Asynchronous two-phase scans with their own workspace: scan and place only enqueue, wait blocks.
+    pub fn dach_job_create(dev: *mut DachDev, out: *mut *mut DachJob) -> i32;
+    pub fn dach_job_free(job: *mut DachJob);
+    pub fn dach_job_scan(job: *mut DachJob, mode: i32, d_text: *const u8, d_offs: *const u64, n: u64, text_bytes: u64,
+                         cap_matches: u64, stream: *mut c_void) -> i32;
+    pub fn dach_job_place(job: *mut DachJob, d_out: *mut DachMatch, out_cap: u64, d_out_offs: *mut u64, d_base: *const u64,
+                          stream: *mut c_void) -> i32;
+    pub fn dach_job_wait(job: *mut DachJob, needed: *mut u64) -> i32;
+
+    /// Shard groups: every rank's placement stores its matches into rank 0's dense buffer over NVLink peer memory.
+    pub fn dach_group_create(rank: i32, world: i32, device: i32, match_cap: u64, n_haystacks_total: u64,
+                             out: *mut *mut DachGroup) -> i32;
+    pub fn dach_group_export(group: *const DachGroup, handle: *mut c_void) -> i32;
+    pub fn dach_group_connect(group: *mut DachGroup, handles: *const c_void) -> i32;
+    pub fn dach_group_place(group: *mut DachGroup, job: *mut DachJob, hay_base: u64, last: i32, stream: *mut c_void) -> i32;
+    pub fn dach_group_finish(group: *mut DachGroup, total: *mut u64, stream: *mut c_void) -> i32;
+    pub fn dach_group_result(group: *const DachGroup, d_out: *mut *mut DachMatch, d_offs: *mut *mut u64) -> i32;
+    pub fn dach_group_free(group: *mut DachGroup);
 }

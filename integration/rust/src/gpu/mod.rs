@@ -1,5 +1,6 @@
-//! GPU-backed twins of the crate's automata.  Construction stays in the crate; the serialized automaton
-//! crosses the FFI once; batches of haystacks are scanned by libdaachorse_b200 on a B200.
+//! `daachorse::gpu`: drop-in twins of the crate's automata whose scans run on a B200.  Same type names, same
+//! constructors (`new`, `with_values`), same iterator methods and `MatchKind` gating; construction stays in the crate,
+//! the serialized automaton crosses the FFI once, haystacks are scanned by libdaachorse_b200.
 //! Not compiled in this repository (no Rust toolchain in the build image).
 //!
 //! Needs two one-line accessors in the crate, `pub(crate) fn match_kind(&self) -> MatchKind { self.match_kind }`
@@ -7,7 +8,7 @@
 //! `MatchKind::is_standard / is_leftmost` are visible here because this module hangs off the crate root.
 pub mod ffi;
 
-use crate::{CharwiseDoubleArrayAhoCorasick, DoubleArrayAhoCorasick, Match, MatchKind};
+use crate::{Match, MatchKind};
 use core::ffi::CStr;
 
 #[derive(Debug)]
@@ -87,68 +88,159 @@ fn scan<P: AsRef<[u8]>>(dev: &Device, mode: i32, haystacks: &[P]) -> Result<Batc
     }
 }
 
-/// A `DoubleArrayAhoCorasick<u32>` whose scans run on a B200.
-pub struct GpuDoubleArrayAhoCorasick {
+/// Drop-in for `daachorse::DoubleArrayAhoCorasick<u32>`: same constructors, same iterator methods, same
+/// `MatchKind` gating -- `use daachorse::gpu::DoubleArrayAhoCorasick;` is the whole switch.  Construction runs the
+/// crate's own builder (src/bytewise/builder.rs) on the host; the serialized automaton crosses the FFI once.
+/// The iterator methods scan eagerly on the device and then yield the crate's `Match` sequence; the `*_batch`
+/// methods are the throughput interface (many haystacks per call).
+pub struct DoubleArrayAhoCorasick {
+    pma: crate::DoubleArrayAhoCorasick<u32>,
     dev: Device,
-    match_kind: MatchKind,
 }
 
-impl GpuDoubleArrayAhoCorasick {
-    /// Build with the crate (`DoubleArrayAhoCorasick::new`, builders: unchanged), hand the serialized
-    /// automaton over (src/bytewise.rs:801), upload once.
-    pub fn from_pma(pma: &DoubleArrayAhoCorasick<u32>, device: i32) -> Result<Self, GpuError> {
-        Ok(Self { dev: upload(&pma.serialize(), false, device)?, match_kind: pma.match_kind() })
+impl DoubleArrayAhoCorasick {
+    /// src/bytewise.rs:103
+    pub fn new<I, P>(patterns: I) -> crate::errors::Result<Self>
+    where
+        I: IntoIterator<Item = P>,
+        P: AsRef<[u8]>,
+    {
+        Self::from_pma(crate::DoubleArrayAhoCorasick::new(patterns)?, 0)
     }
-    /// Batch form of `find_iter` (src/bytewise.rs:190).
+    /// src/bytewise.rs:145
+    pub fn with_values<I, P>(patvals: I) -> crate::errors::Result<Self>
+    where
+        I: IntoIterator<Item = (P, u32)>,
+        P: AsRef<[u8]>,
+    {
+        Self::from_pma(crate::DoubleArrayAhoCorasick::with_values(patvals)?, 0)
+    }
+    /// From an automaton any builder of the crate made (`DoubleArrayAhoCorasickBuilder::new().match_kind(..)`),
+    /// on CUDA device `device`.
+    pub fn from_pma(pma: crate::DoubleArrayAhoCorasick<u32>, device: i32) -> crate::errors::Result<Self> {
+        let dev = upload(&pma.serialize(), false, device).map_err(|e| crate::errors::DaachorseError::invalid_argument("gpu", ">=", e.code as isize))?;
+        Ok(Self { pma, dev })
+    }
+    pub fn match_kind(&self) -> MatchKind {
+        self.pma.match_kind()
+    }
+    pub fn heap_bytes(&self) -> usize {
+        self.pma.heap_bytes()
+    }
+    pub fn num_states(&self) -> usize {
+        self.pma.num_states()
+    }
+
+    fn one<P: AsRef<[u8]>>(&self, mode: i32, haystack: P) -> std::vec::IntoIter<Match<u32>> {
+        scan(&self.dev, mode, &[haystack]).expect("GPU scan failed").matches.into_iter()
+    }
+    /// src/bytewise.rs:190
+    pub fn find_iter<P: AsRef<[u8]>>(&self, haystack: P) -> impl Iterator<Item = Match<u32>> {
+        assert!(self.match_kind().is_standard(), "Error: match_kind must be standard.");
+        self.one(ffi::DACH_FIND, haystack)
+    }
+    /// src/bytewise.rs:292
+    pub fn find_overlapping_iter<P: AsRef<[u8]>>(&self, haystack: P) -> impl Iterator<Item = Match<u32>> {
+        assert!(self.match_kind().is_standard(), "Error: match_kind must be standard.");
+        self.one(ffi::DACH_FIND_OVERLAPPING, haystack)
+    }
+    /// src/bytewise.rs:410
+    pub fn find_overlapping_no_suffix_iter<P: AsRef<[u8]>>(&self, haystack: P) -> impl Iterator<Item = Match<u32>> {
+        assert!(self.match_kind().is_standard(), "Error: match_kind must be standard.");
+        self.one(ffi::DACH_FIND_OVERLAPPING_NO_SUFFIX, haystack)
+    }
+    /// src/bytewise.rs:547
+    pub fn leftmost_find_iter<P: AsRef<[u8]>>(&self, haystack: P) -> impl Iterator<Item = Match<u32>> {
+        assert!(self.match_kind().is_leftmost(), "Error: match_kind must be leftmost.");
+        self.one(ffi::DACH_LEFTMOST_FIND, haystack)
+    }
+
+    /// Batch forms: haystack i's matches are `matches[offsets[i]..offsets[i + 1]]`, in iterator order.
     pub fn find_batch<P: AsRef<[u8]>>(&self, h: &[P]) -> Result<BatchMatches, GpuError> {
-        assert!(self.match_kind.is_standard(), "Error: match_kind must be standard.");
+        assert!(self.match_kind().is_standard(), "Error: match_kind must be standard.");
         scan(&self.dev, ffi::DACH_FIND, h)
     }
-    /// Batch form of `find_overlapping_iter` (src/bytewise.rs:292).
     pub fn find_overlapping_batch<P: AsRef<[u8]>>(&self, h: &[P]) -> Result<BatchMatches, GpuError> {
-        assert!(self.match_kind.is_standard(), "Error: match_kind must be standard.");
+        assert!(self.match_kind().is_standard(), "Error: match_kind must be standard.");
         scan(&self.dev, ffi::DACH_FIND_OVERLAPPING, h)
     }
-    /// Batch form of `find_overlapping_no_suffix_iter` (src/bytewise.rs:410).
     pub fn find_overlapping_no_suffix_batch<P: AsRef<[u8]>>(&self, h: &[P]) -> Result<BatchMatches, GpuError> {
-        assert!(self.match_kind.is_standard(), "Error: match_kind must be standard.");
+        assert!(self.match_kind().is_standard(), "Error: match_kind must be standard.");
         scan(&self.dev, ffi::DACH_FIND_OVERLAPPING_NO_SUFFIX, h)
     }
-    /// Batch form of `leftmost_find_iter` (src/bytewise.rs:547).
     pub fn leftmost_find_batch<P: AsRef<[u8]>>(&self, h: &[P]) -> Result<BatchMatches, GpuError> {
-        assert!(self.match_kind.is_leftmost(), "Error: match_kind must be leftmost.");
+        assert!(self.match_kind().is_leftmost(), "Error: match_kind must be leftmost.");
         scan(&self.dev, ffi::DACH_LEFTMOST_FIND, h)
     }
-    /// Drop-in for the lazy iterator on one haystack: scan eagerly, iterate the result.
-    pub fn find_overlapping_iter<P: AsRef<[u8]>>(&self, haystack: P) -> impl Iterator<Item = Match<u32>> {
-        self.find_overlapping_batch(&[haystack]).expect("GPU scan failed").matches.into_iter()
-    }
 }
 
-/// A `CharwiseDoubleArrayAhoCorasick<u32>` whose scans run on a B200 (haystacks are `&str`: valid UTF-8).
-pub struct GpuCharwiseDoubleArrayAhoCorasick {
+/// Drop-in for `daachorse::CharwiseDoubleArrayAhoCorasick<u32>` (haystacks are `&str`: valid UTF-8).
+pub struct CharwiseDoubleArrayAhoCorasick {
+    pma: crate::CharwiseDoubleArrayAhoCorasick<u32>,
     dev: Device,
-    match_kind: MatchKind,
 }
 
-impl GpuCharwiseDoubleArrayAhoCorasick {
-    pub fn from_pma(pma: &CharwiseDoubleArrayAhoCorasick<u32>, device: i32) -> Result<Self, GpuError> {
-        Ok(Self { dev: upload(&pma.serialize(), true, device)?, match_kind: pma.match_kind() })
+impl CharwiseDoubleArrayAhoCorasick {
+    /// src/charwise.rs:100
+    pub fn new<I, P>(patterns: I) -> crate::errors::Result<Self>
+    where
+        I: IntoIterator<Item = P>,
+        P: AsRef<str>,
+    {
+        Self::from_pma(crate::CharwiseDoubleArrayAhoCorasick::new(patterns)?, 0)
+    }
+    /// src/charwise.rs:139
+    pub fn with_values<I, P>(patvals: I) -> crate::errors::Result<Self>
+    where
+        I: IntoIterator<Item = (P, u32)>,
+        P: AsRef<str>,
+    {
+        Self::from_pma(crate::CharwiseDoubleArrayAhoCorasick::with_values(patvals)?, 0)
+    }
+    pub fn from_pma(pma: crate::CharwiseDoubleArrayAhoCorasick<u32>, device: i32) -> crate::errors::Result<Self> {
+        let dev = upload(&pma.serialize(), true, device).map_err(|e| crate::errors::DaachorseError::invalid_argument("gpu", ">=", e.code as isize))?;
+        Ok(Self { pma, dev })
+    }
+    pub fn match_kind(&self) -> MatchKind {
+        self.pma.match_kind()
+    }
+    fn one(&self, mode: i32, haystack: &str) -> std::vec::IntoIter<Match<u32>> {
+        scan(&self.dev, mode, &[haystack]).expect("GPU scan failed").matches.into_iter()
+    }
+    /// src/charwise.rs:184
+    pub fn find_iter<P: AsRef<str>>(&self, haystack: P) -> impl Iterator<Item = Match<u32>> {
+        assert!(self.match_kind().is_standard(), "Error: match_kind must be standard.");
+        self.one(ffi::DACH_FIND, haystack.as_ref())
+    }
+    /// src/charwise.rs:290
+    pub fn find_overlapping_iter<P: AsRef<str>>(&self, haystack: P) -> impl Iterator<Item = Match<u32>> {
+        assert!(self.match_kind().is_standard(), "Error: match_kind must be standard.");
+        self.one(ffi::DACH_FIND_OVERLAPPING, haystack.as_ref())
+    }
+    /// src/charwise.rs:412
+    pub fn find_overlapping_no_suffix_iter<P: AsRef<str>>(&self, haystack: P) -> impl Iterator<Item = Match<u32>> {
+        assert!(self.match_kind().is_standard(), "Error: match_kind must be standard.");
+        self.one(ffi::DACH_FIND_OVERLAPPING_NO_SUFFIX, haystack.as_ref())
+    }
+    /// src/charwise.rs:553
+    pub fn leftmost_find_iter<P: AsRef<str>>(&self, haystack: P) -> impl Iterator<Item = Match<u32>> {
+        assert!(self.match_kind().is_leftmost(), "Error: match_kind must be leftmost.");
+        self.one(ffi::DACH_LEFTMOST_FIND, haystack.as_ref())
     }
     pub fn find_batch(&self, h: &[&str]) -> Result<BatchMatches, GpuError> {
-        assert!(self.match_kind.is_standard(), "Error: match_kind must be standard.");
+        assert!(self.match_kind().is_standard(), "Error: match_kind must be standard.");
         scan(&self.dev, ffi::DACH_FIND, h)
     }
     pub fn find_overlapping_batch(&self, h: &[&str]) -> Result<BatchMatches, GpuError> {
-        assert!(self.match_kind.is_standard(), "Error: match_kind must be standard.");
+        assert!(self.match_kind().is_standard(), "Error: match_kind must be standard.");
         scan(&self.dev, ffi::DACH_FIND_OVERLAPPING, h)
     }
     pub fn find_overlapping_no_suffix_batch(&self, h: &[&str]) -> Result<BatchMatches, GpuError> {
-        assert!(self.match_kind.is_standard(), "Error: match_kind must be standard.");
+        assert!(self.match_kind().is_standard(), "Error: match_kind must be standard.");
         scan(&self.dev, ffi::DACH_FIND_OVERLAPPING_NO_SUFFIX, h)
     }
     pub fn leftmost_find_batch(&self, h: &[&str]) -> Result<BatchMatches, GpuError> {
-        assert!(self.match_kind.is_leftmost(), "Error: match_kind must be leftmost.");
+        assert!(self.match_kind().is_leftmost(), "Error: match_kind must be leftmost.");
         scan(&self.dev, ffi::DACH_LEFTMOST_FIND, h)
     }
 }
@@ -156,11 +248,11 @@ impl GpuCharwiseDoubleArrayAhoCorasick {
 /// Many streams scanned chunk after chunk: the batch form of `find_overlapping_stepper()`
 /// (src/bytewise.rs:660-729).  `state[i]` / `pos[i]` are stream i's `state_id` / `pos` and live in device
 /// memory (allocated by the caller's CUDA binding); each call consumes one chunk per stream.
-pub struct GpuStreamScanner<'a> {
-    pub pma: &'a GpuDoubleArrayAhoCorasick,
+pub struct StreamScanner<'a> {
+    pub pma: &'a DoubleArrayAhoCorasick,
 }
 
-impl GpuStreamScanner<'_> {
+impl StreamScanner<'_> {
     /// # Safety
     /// All pointers are device pointers of the sizes `dach_dev_scan_stream` documents.
     pub unsafe fn consume_chunks(&self, d_text: *const u8, d_offs: *const u64, n: u64, text_bytes: u64,

@@ -252,7 +252,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
 
     // segment table (mirrors k_seg_count / k_seg_fill in dev_scan.cu)
     const bool v1 = kernel_version >= 1 && !img.crec.empty() && !(mode == M_FIND && img.root_opos != 0);
-    if (g_state_io && !(v1 && !charwise && mode != M_LEFTMOST && kernel_version >= 2 && img.root_base != 0))
+    if (g_state_io && !(v1 && mode != M_LEFTMOST && (charwise || (kernel_version >= 2 && img.root_base != 0))))
         return DACH_INVALID_ARGUMENT;  // as scan_locked() in dev_scan.cu
     const bool seg = v1 && !charwise && !g_state_io && seg_len > 0 && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX);
     std::vector<uint32_t> item_hay, item_beg;
@@ -395,13 +395,15 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
 }
 
 // dach_dev_scan_stream: chunks of streams (state in/out per haystack, optional base position)
+static int g_stream_charwise = 0;
+extern "C" void emu_stream_charwise(int cw) { g_stream_charwise = cw; }
 extern "C" int emu_scan_stream_wire(const uint8_t* wire, size_t wire_len, int mode, const uint8_t* text, const uint64_t* offs,
                                     uint64_t n, uint32_t* state_io, const uint32_t* pos_in, uint32_t pool_blocks, dach_match* out,
                                     uint64_t out_cap, uint64_t* out_offs, uint64_t* needed) {
     if (mode != M_FIND && mode != M_OVERLAPPING) return DACH_INVALID_ARGUMENT;
     g_state_io = state_io;
     g_pos_in = pos_in;
-    const int rc = emu_scan_batch_wire(wire, wire_len, 0, mode, text, offs, n, g_stream_hot, g_stream_kernel, 0, 0, pool_blocks, out, out_cap, out_offs, needed);
+    const int rc = emu_scan_batch_wire(wire, wire_len, g_stream_charwise, mode, text, offs, n, g_stream_hot, g_stream_kernel, 0, 0, pool_blocks, out, out_cap, out_offs, needed);
     g_state_io = nullptr;
     g_pos_in = nullptr;
     return rc;

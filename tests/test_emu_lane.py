@@ -262,3 +262,47 @@ def test_hot_first_relayout_at_dictionary_shape(seed, hot_slots):
                     assert int(state[i]) == pma.state_after(h, find_mode=False)
     finally:
         E.lib().emu_set_hot_slots(65536)
+
+
+@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("mode", [0, 1])
+def test_charwise_stream_chunks_equal_the_stepper_over_the_whole_stream(seed, mode):
+    """The charwise steppers (src/charwise/iter.rs:403-534) as chunks of streams on CwMachine: streams of chars of
+    mixed byte widths cut at char boundaries into ragged chunks, state carried over."""
+    rng = np.random.default_rng(52000 + seed)
+    table = ["a", "b", "é", "あ", "𝄞", "z"]
+    alpha = int(rng.integers(2, 5))
+    pats = sorted({"".join(table[int(i)] for i in rng.integers(0, alpha, size=int(rng.integers(1, 6)))) for _ in range(int(rng.integers(1, 40)))})
+    streams = [[table[int(i)] for i in rng.integers(0, alpha + 1, size=int(rng.integers(0, 200)))] for _ in range(7)]
+    pma = O.OraclePma.build(pats, charwise=True)
+    wire = pma.serialize()
+    orc_mode = O.FIND_STEPPER if mode == 0 else O.FIND_OVERLAPPING_STEPPER
+    want = []
+    for chars in streams:
+        sb = "".join(chars).encode()
+        ref = pma.scan_batch(orc_mode, np.frombuffer(sb, dtype=np.uint8), np.array([0, len(sb)], dtype=np.uint64), want_matches=True)
+        want.append([x for x in triples(ref["matches"]) if x[1] != 0])
+    E.lib().emu_stream_charwise(1)
+    try:
+        state = np.zeros(len(streams), dtype=np.uint32)
+        pos = np.zeros(len(streams), dtype=np.uint32)
+        cur = [0] * len(streams)
+        got = [[] for _ in streams]
+        while any(cur[i] < len(s) for i, s in enumerate(streams)):
+            chunks = []
+            for i, s in enumerate(streams):
+                k = int(rng.integers(0, 25))
+                chunks.append("".join(s[cur[i]: cur[i] + k]).encode())
+                cur[i] += k
+            offs = np.zeros(len(streams) + 1, dtype=np.uint64)
+            offs[1:] = np.cumsum([len(c) for c in chunks])
+            text = np.frombuffer(b"".join(chunks), dtype=np.uint8)
+            rc, m, oo, need = E.scan_stream(wire, mode, text, offs, state, pos)
+            assert rc == 0
+            tr = triples(m)
+            for i in range(len(streams)):
+                got[i] += tr[int(oo[i]): int(oo[i + 1])]
+                pos[i] += len(chunks[i])
+        assert got == want
+    finally:
+        E.lib().emu_stream_charwise(0)

@@ -619,3 +619,59 @@ def test_bad_offsets_are_refused_on_both_paths():
         assert e.value.code == 1
     good = pma.scan_batch_device(D.FIND_OVERLAPPING, t, torch.tensor([0, 8, 8, 256], dtype=torch.int64, device=dev))
     assert good.matches.shape[0] == 4 + 4 + 124 + 124
+
+
+@pytest.mark.parametrize("mode", [D.FIND, D.FIND_OVERLAPPING])
+def test_charwise_stream_chunks_equal_the_stepper_over_the_whole_stream(mode):
+    """dach_dev_scan_stream on a charwise automaton (src/charwise/iter.rs:403-534): 2000 streams of CJK text cut at
+    char boundaries into ragged chunks, state and position carried from round to round."""
+    import torch
+
+    cfg = S.config("C4")
+    ps = S.make_patterns(cfg, n=5000)
+    pool, b = S.make_pool(cfg, ps, 4 << 20)
+    rng = np.random.default_rng(33)
+    n = 2000
+    bi = np.sort(rng.integers(0, len(b) - 400, size=n))
+    nt = rng.integers(0, 300, size=n)                      # tokens per stream
+    streams, cuts = [], []
+    for i in range(n):
+        lo = int(b[bi[i]]); hi = int(b[bi[i] + int(nt[i])])
+        streams.append(pool[lo:hi])
+        cuts.append((b[bi[i]: bi[i] + int(nt[i]) + 1] - lo).astype(np.int64))   # token starts: char boundaries
+    pma = D.CharwiseDoubleArrayAhoCorasick.new([p.decode() for p in ps.as_list()])
+    opma = O.OraclePma.build([p.decode() for p in ps.as_list()], charwise=True)
+    lens = np.array([len(x) for x in streams])
+    offs_all = np.zeros(n + 1, dtype=np.uint64)
+    offs_all[1:] = np.cumsum(lens)
+    whole = np.concatenate(streams)
+    ref = opma.scan_batch(O.FIND_STEPPER if mode == D.FIND else O.FIND_OVERLAPPING_STEPPER, whole, offs_all, nthreads=16, want_matches=True)
+    state = torch.zeros(n, dtype=torch.int32, device="cuda")
+    pos = np.zeros(n, dtype=np.int64)
+    tok = np.zeros(n, dtype=np.int64)
+    got = [[] for _ in range(n)]
+    while (pos < lens).any():
+        k = rng.integers(0, 60, size=n)
+        chunks = []
+        for i in range(n):
+            t1 = min(int(tok[i] + k[i]), len(cuts[i]) - 1)
+            chunks.append(streams[i][int(cuts[i][tok[i]]): int(cuts[i][t1])])
+            tok[i] = t1
+        offs = np.zeros(n + 1, dtype=np.int64)
+        offs[1:] = np.cumsum([len(c) for c in chunks])
+        text = np.concatenate(chunks) if offs[-1] else np.zeros(0, np.uint8)
+        t = torch.from_numpy(np.ascontiguousarray(text)).cuda() if len(text) else torch.zeros(16, dtype=torch.uint8, device="cuda")[:0]
+        r = pma.scan_stream_device(mode, t, torch.from_numpy(offs).cuda(), state, torch.from_numpy(pos.astype(np.int32)).cuda())
+        m = r.matches.cpu().numpy().view(np.uint32).reshape(-1, 3)
+        oo = r.offsets.cpu().numpy()
+        for i in range(n):
+            if oo[i + 1] > oo[i]:
+                got[i].append(m[oo[i]: oo[i + 1]])
+        pos += np.array([len(c) for c in chunks])
+    rm = ref["matches"]
+    ro = np.concatenate([[0], np.cumsum(ref["counts"])]).astype(np.int64)
+    for i in range(n):
+        want = np.stack([rm["start"][ro[i]: ro[i + 1]], rm["end"][ro[i]: ro[i + 1]], rm["value"][ro[i]: ro[i + 1]]], axis=1)
+        want = want[want[:, 1] != 0]
+        have = np.concatenate(got[i]) if got[i] else np.zeros((0, 3), np.uint32)
+        assert np.array_equal(have, want), i
