@@ -675,3 +675,31 @@ def test_charwise_stream_chunks_equal_the_stepper_over_the_whole_stream(mode):
         want = want[want[:, 1] != 0]
         have = np.concatenate(got[i]) if got[i] else np.zeros((0, 3), np.uint32)
         assert np.array_equal(have, want), i
+
+
+def test_python_daachorse_style_surface():
+    """daachorse_b200.pycompat.Automaton: the surface of the crate's Python wrapper (README.md:19) -- str patterns,
+    pattern indices as values, positions in characters."""
+    from daachorse_b200 import pycompat as P
+
+    pma = P.Automaton(["bcd", "ab", "a"])
+    assert pma.find_overlapping("abcd") == [(0, 1, 2), (0, 2, 1), (1, 4, 0)]           # README.md:57-71
+    ref = O.OraclePma.build(["bcd", "ab", "a"], charwise=True).scan_batch(
+        O.FIND_OVERLAPPING_NO_SUFFIX, np.frombuffer(b"abcd", dtype=np.uint8), np.array([0, 4], dtype=np.uint64), want_matches=True)["matches"]
+    assert pma.find_overlapping_no_suffix("abcd") == [(int(a), int(b), int(c)) for a, b, c in zip(ref["start"], ref["end"], ref["value"])]
+    assert pma.find("abcd") == [(0, 1, 2), (1, 4, 0)]                                  # README.md:82-94
+    pma = P.Automaton(["ab", "a", "abcd"], P.MATCH_KIND_LEFTMOST_LONGEST)
+    assert pma.leftmost_find("abcd") == [(0, 4, 2)]                                    # README.md:102-116
+    pma = P.Automaton(["ab", "a", "abcd"], P.MATCH_KIND_LEFTMOST_FIRST)
+    assert pma.leftmost_find("abcd") == [(0, 2, 0)]                                    # README.md:128-142
+    # positions are characters, not bytes
+    pats = ["全世界", "世界", "に"]
+    pma = P.Automaton(pats)
+    hay = "全世界中に"
+    got = pma.find_overlapping(hay)
+    want = sorted((i, i + len(p), k) for k, p in enumerate(pats) for i in range(len(hay)) if hay.startswith(p, i))
+    assert sorted(got) == want and pma.find_overlapping_as_strings(hay) == [hay[s:e] for s, e, _ in got]
+    rng = np.random.default_rng(3)
+    hays = ["".join(rng.choice(list("全世界中にab"), size=int(rng.integers(0, 40)))) for _ in range(50)]
+    for h, r in zip(hays, pma.find_overlapping_batch(hays)):
+        assert sorted(r) == sorted((i, i + len(p), k) for k, p in enumerate(pats) for i in range(len(h)) if h.startswith(p, i))
