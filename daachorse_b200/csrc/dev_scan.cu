@@ -424,6 +424,9 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const Scan
     const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
     // U blocks in flight per warp: the header -> (count, offset) -> data chains overlap
     for (uint64_t b0 = warp * U; b0 < used; b0 += n_warps * U) {
+        // output word k of a block = word k % 3 of match k / 3 = block word 4 * (1 + k / 3) + k % 3
+        const uint32_t k0 = lane, k1 = lane + 32;
+        const uint32_t s0 = BLK_SLOT_WORDS * (1 + k0 / 3) + k0 % 3, s1 = BLK_SLOT_WORDS * (1 + k1 / 3) + k1 % 3;
         const uint32_t* blk[U];
         uint32_t item[U], seq[U], w0[U], w1[U];
 #pragma unroll
@@ -433,8 +436,8 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const Scan
             blk[u] = pool + (blkmap ? (uint64_t)blkmap[bb] : bb) * BLK_WORDS;
             item[u] = blk[u][0];
             seq[u] = blk[u][1];
-            w0[u] = blk[u][2 + lane];
-            w1[u] = lane < 28 ? blk[u][2 + 32 + lane] : 0;
+            w0[u] = blk[u][s0];
+            w1[u] = k1 < BLK_MATCHES * 3 ? blk[u][s1] : 0;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -446,6 +449,32 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const Scan
             if (lane + 32 < nw) dst[lane + 32] = w1[u];
         }
     }
+}
+
+// The exchange step proper: `total` dense 12-byte tuples from local memory to out_words + 3 * base in (peer)
+// memory, as DESTINATION-ALIGNED 16-byte stores -- a warp store is 512 contiguous bytes, whole 128-byte lines on
+// NVLink.  (k_gather's own stores are 4 bytes per lane at the 4-byte alignment of a tuple array: as peer stores
+// they reach 350 GB/s into one GPU where the link takes 770, profiles/r2_multi_gpu.md.)
+__global__ void __launch_bounds__(256) k_push(const uint32_t* src, const unsigned long long* total_ptr, const unsigned long long* base,
+                                               unsigned long long out_cap, const ScanCtrl* ctrl, uint32_t* out_words) {
+    if (ctrl->overflow) return;
+    const unsigned long long b0 = base ? *base : 0ull, total = *total_ptr;
+    if (b0 + total > out_cap) return;
+    uint32_t* dst = out_words + b0 * 3ull;
+    const unsigned long long n_words = total * 3ull;
+    const unsigned long long head = min((unsigned long long)((4u - (uint32_t)(((uintptr_t)dst >> 2) & 3u)) & 3u), n_words);
+    const unsigned long long n_vec = (n_words - head) / 4ull;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long nth = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long v = tid; v < n_vec; v += nth) {
+        const uint32_t* s4 = src + head + 4ull * v;
+        uint4 x;
+        x.x = s4[0], x.y = s4[1], x.z = s4[2], x.w = s4[3];
+        *reinterpret_cast<uint4*>(dst + head + 4ull * v) = x;
+    }
+    const unsigned long long tail0 = head + 4ull * n_vec;
+    if (tid < head) dst[tid] = src[tid];
+    if (tid < n_words - tail0) dst[tail0 + tid] = src[tail0 + tid];
 }
 
 // per-haystack offsets of the caller: out_offs[h] = base + item_offs[first item of haystack h]; entry n (the
@@ -657,12 +686,14 @@ struct Workspace {
     DevBuf counts, tiles, ctrl, pool;
     DevBuf nseg, seg_first, item_hay, item_beg, item_offs, n_items_dev;  // segment table, per-item offsets
     DevBuf blk_first, blkmap, tiles2;  // pool blocks in output order (k_blk_index)
+    DevBuf stage;  // shard groups: the job's dense matches, pushed to the gathering rank by k_push
     HostPinned* pinned = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // pipeline start, scan end, pipeline end, scan start
     cudaEvent_t ev_scanned = nullptr, ev_placed = nullptr;
     // the scan in flight (phase 1 -> phase 2)
     uint64_t job_n = 0, job_items = 0;
     uint32_t job_pool_blocks = 0;
+    uint64_t job_cap = 0;
     bool job_seg = false, job_ordered = false, job_open = false;
     cudaStream_t job_stream = nullptr;
     // host-batch slices only: device staging and the slice's stream
@@ -683,7 +714,7 @@ struct Workspace {
     }
     void release() {
         for (DevBuf* b : {&counts, &tiles, &ctrl, &pool, &text, &offs, &out, &out_offs, &nseg, &seg_first, &item_hay, &item_beg,
-                          &item_offs, &n_items_dev, &blk_first, &blkmap, &tiles2})
+                          &item_offs, &n_items_dev, &blk_first, &blkmap, &tiles2, &stage})
             if (b->p) {
                 cudaFree(b->p);
                 b->p = nullptr;
@@ -935,6 +966,7 @@ int enqueue_scan(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, con
     // buffers are rewritten
     if (W.job_open) cudaStreamWaitEvent(st, W.ev_placed, 0);
     W.job_n = n;
+    W.job_cap = cap_matches;
     W.job_items = n;
     W.job_seg = false;
     W.job_ordered = false;
@@ -1133,7 +1165,8 @@ int enqueue_scan(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, con
 // d_out / d_out_offs may be peer-mapped memory of another GPU.  d_base (device pointer or nullptr): index of
 // this batch's first match in d_out, added to the offsets too; `last`: also write out_offs[n].
 int enqueue_place(dach_dev* d, Workspace& W, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs,
-                  const unsigned long long* d_base, bool last, cudaStream_t st, const uint32_t* d_pos_in = nullptr) {
+                  const unsigned long long* d_base, bool last, cudaStream_t st, const uint32_t* d_pos_in = nullptr,
+                  bool staged = false) {
     if (!W.job_open) {
         set_error("no scan to place");
         return DACH_INVALID_ARGUMENT;
@@ -1149,13 +1182,25 @@ int enqueue_place(dach_dev* d, Workspace& W, dach_match* d_out, uint64_t out_cap
         const uint32_t* counts = static_cast<const uint32_t*>(W.counts.p);
         const uint32_t* blkmap = W.job_ordered ? static_cast<const uint32_t*>(W.blkmap.p) : nullptr;
         uint32_t* out_words = reinterpret_cast<uint32_t*>(d_out);
+        const unsigned long long* g_base = d_base;
+        unsigned long long g_cap = out_cap;
+        if (staged) {  // peer destination: pack locally, then push with destination-aligned 16-byte stores
+            if (!ensure(W.stage, W.job_cap * sizeof(dach_match) + 64)) return DACH_CUDA_ERROR;
+            out_words = static_cast<uint32_t*>(W.stage.p);
+            g_base = nullptr;
+            g_cap = W.job_cap;
+        }
         if (d->opt_gather_u >= 8)
-            k_gather<8><<<gather_grid, 256, 0, st>>>(pool, ctrl, W.job_pool_blocks, counts, item_offs, n_items, out_cap, d_base, out_words, blkmap);
+            k_gather<8><<<gather_grid, 256, 0, st>>>(pool, ctrl, W.job_pool_blocks, counts, item_offs, n_items, g_cap, g_base, out_words, blkmap);
         else if (d->opt_gather_u <= 2)
-            k_gather<2><<<gather_grid, 256, 0, st>>>(pool, ctrl, W.job_pool_blocks, counts, item_offs, n_items, out_cap, d_base, out_words, blkmap);
+            k_gather<2><<<gather_grid, 256, 0, st>>>(pool, ctrl, W.job_pool_blocks, counts, item_offs, n_items, g_cap, g_base, out_words, blkmap);
         else
-            k_gather<4><<<gather_grid, 256, 0, st>>>(pool, ctrl, W.job_pool_blocks, counts, item_offs, n_items, out_cap, d_base, out_words, blkmap);
+            k_gather<4><<<gather_grid, 256, 0, st>>>(pool, ctrl, W.job_pool_blocks, counts, item_offs, n_items, g_cap, g_base, out_words, blkmap);
         ++d->launches;
+        if (staged) {
+            k_push<<<d->sm_count * 4, 256, 0, st>>>(out_words, item_offs + n_items, d_base, out_cap, ctrl, reinterpret_cast<uint32_t*>(d_out));
+            ++d->launches;
+        }
     }
     k_final_offsets<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(
         W.job_seg ? static_cast<const unsigned long long*>(W.seg_first.p) : nullptr, item_offs, n, d_base, last ? 1 : 0, offs64);
@@ -1782,7 +1827,8 @@ int dach_group_place(dach_group* G, dach_job* j, uint64_t hay_base, int last, vo
         k_group_wait_base<<<1, 1, 0, st>>>(G->ctl, G->rank, step);
         j->d->launches += 3;
         j->out_cap = G->match_cap;
-        const int rc = enqueue_place(j->d, W, G->out, G->match_cap, G->offs + hay_base, &G->ctl->base[step & 1], last != 0, st);
+        const int rc = enqueue_place(j->d, W, G->out, G->match_cap, G->offs + hay_base, &G->ctl->base[step & 1], last != 0, st, nullptr,
+                                     /*staged=*/G->rank != 0);
         if (rc) return rc;
         k_group_signal_done<<<1, 1, 0, st>>>(G->peers.ctl[0], G->rank, step);
         ++j->d->launches;

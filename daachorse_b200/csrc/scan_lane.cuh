@@ -76,10 +76,13 @@ constexpr uint32_t D_INVALID_CODE = 0xffffffffu;
 constexpr int M_FIND = 0, M_OVERLAPPING = 1, M_NO_SUFFIX = 2, M_LEFTMOST = 3;
 
 // Match staging: every lane appends its matches to 256-byte blocks taken from one pool with an
-// atomic bump allocator.  Block layout (64 words): [0] item id, [1] sequence number of the
-// block inside the item, [2..61] up to 20 matches (start, end, value), [62..63] unused.
+// atomic bump allocator.  Block layout: sixteen 16-byte slots -- slot 0 = {item id, sequence number of
+// the block inside the item, -, -}, slots 1..15 = one match each {start, end, value, -}: a match is ONE
+// 16-byte store (three 4-byte stores cost three L1 wavefronts each time: VERDICT r1 item 8); k_gather
+// packs them to the 12-byte tuples of the result.
 constexpr uint32_t BLK_WORDS = 64;
-constexpr uint32_t BLK_MATCHES = 20;
+constexpr uint32_t BLK_MATCHES = 15;
+constexpr uint32_t BLK_SLOT_WORDS = 4;
 
 struct ScanCtrl {
     unsigned long long next_item;  // dynamic work counter
@@ -161,11 +164,12 @@ DACH_HD uint32_t ld_u32(const uint32_t* p) {
 #endif
 }
 // match blocks: written once here, read once by k_gather
-DACH_HD void st_stream_u32(uint32_t* p, uint32_t v) {
+DACH_HD void st_stream_u4(uint32_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
 #if defined(__CUDA_ARCH__)
-    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(c_l2pol[2]) : "memory");
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "l"(c_l2pol[2])
+                 : "memory");
 #else
-    *p = v;
+    p[0] = a, p[1] = b, p[2] = c, p[3] = d;
 #endif
 }
 
@@ -258,18 +262,14 @@ struct Emitter {
             const uint32_t b = bump_u32(&P.ctrl->blk_cursor);
             if (b < P.pool_blocks) {
                 blk = P.pool + (size_t)b * BLK_WORDS;
-                st_stream_u32(blk + 0, item);
-                st_stream_u32(blk + 1, count / BLK_MATCHES);
+                st_stream_u4(blk, item, count / BLK_MATCHES, 0u, 0u);
             } else {
                 blk = nullptr;
                 P.ctrl->overflow = 1u;
             }
         }
         if (blk) {
-            uint32_t* q = blk + 2 + 3 * fill;
-            st_stream_u32(q + 0, start);
-            st_stream_u32(q + 1, end);
-            st_stream_u32(q + 2, value);
+            st_stream_u4(blk + BLK_SLOT_WORDS * (1 + fill), start, end, value, 0u);
         }
         fill = (fill + 1 == BLK_MATCHES) ? 0 : fill + 1;
         ++count;

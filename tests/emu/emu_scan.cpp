@@ -383,7 +383,7 @@ extern "C" int emu_scan_batch_wire(const uint8_t* wire, size_t wire_len, int cha
         uint32_t nm = counts[item] - first;
         if (nm > BLK_MATCHES) nm = BLK_MATCHES;
         uint32_t* dst = out_words + (item_offs[item] + first) * 3ull;
-        for (uint32_t w = 0; w < nm * 3; ++w) dst[w] = blk[2 + w];
+        for (uint32_t w = 0; w < nm * 3; ++w) dst[w] = blk[BLK_SLOT_WORDS * (1 + w / 3) + w % 3];
     }
     if (g_pos_in)  // k_add_base
         for (uint64_t h = 0; h < n; ++h)

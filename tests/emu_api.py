@@ -37,7 +37,7 @@ def scan(wire, charwise, mode, text, offs, hot_n=0, pool_blocks=None, out_cap=No
     cap = int(out_cap) if out_cap is not None else 1 << 16
     while True:
         n_items = n + (int(text.size) // seg_len + 1 if seg_len else 0)
-        pb = int(pool_blocks) if pool_blocks is not None else cap // 20 + n_items + 16
+        pb = int(pool_blocks) if pool_blocks is not None else cap // 15 + n_items + 16
         out = np.zeros(max(cap, 1), dtype=MATCH_DTYPE)
         oo = np.zeros(n + 1, dtype=np.uint64)
         need = C.c_uint64()
@@ -67,7 +67,7 @@ def scan_stream(wire, mode, text, offs, state, pos=None, out_cap=1 << 16):
         need = C.c_uint64()
         pad = text if text.size else np.zeros(16, dtype=np.uint8)
         rc = lib().emu_scan_stream_wire(wire_a.ctypes.data, wire_a.size, mode, pad.ctypes.data, offs.ctypes.data, n,
-                                        state.ctypes.data, pos.ctypes.data if pos is not None else None, cap // 20 + n + 16,
+                                        state.ctypes.data, pos.ctypes.data if pos is not None else None, cap // 15 + n + 16,
                                         out.ctypes.data, cap, oo.ctypes.data, C.byref(need))
         if rc == 6:
             state[:] = saved
