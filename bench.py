@@ -342,7 +342,7 @@ def main():
     st_scan = torch.cuda.Stream(dev, priority=-1)
     st_place = st_scan if args.no_overlap else torch.cuda.Stream(dev, priority=0)
     setup_s = time.time() - t_setup
-    kernel_ms = []
+    kernel_ms, push_ms = [], []
 
     def finish_prev(s):
         """everything of step s is in its final place (rank 0: from every rank); returns the step's match count"""
@@ -351,6 +351,7 @@ def main():
         else:
             tot = jobs[s % n_jobs].wait()
         kernel_ms.append(jobs[s % n_jobs].scan_kernel_ms())
+        push_ms.append(jobs[s % n_jobs].push_ms())
         return tot
 
     def run(steps, first):
@@ -383,6 +384,7 @@ def main():
     barrier()
     n_before = len(sampler.rows)
     kernel_ms.clear()
+    push_ms.clear()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches1 = pma.stats()["launches"]
     barrier()
@@ -403,6 +405,14 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    my_push = float(np.mean(push_ms)) if push_ms else 0.0
+    if world > 1:
+        t = torch.tensor([my_push], dtype=torch.float64, device=dev)
+        allp_ms = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allp_ms, t)
+        push_by_rank = [float(x.item()) for x in allp_ms]
+    else:
+        push_by_rank = []
     job_bytes = step_bytes * world
     value = job_bytes / (ms * 1e-3) / 1e9
     last_batch = (args.warmup + args.steps - 1) % len(batches)
@@ -563,6 +573,7 @@ def main():
                        "; every rank's placement kernel stores its matches into rank 0's dense buffer over NVLink peer memory "
                        "(dach_group_*), rank 0 holds the rebased %d-GPU result after every step" % world if world > 1 else ""),
                    "pipelining": "none (--no-overlap)" if args.no_overlap else "two jobs: the placement of step s runs beside the scan of step s+1",
+                   "peer_push_ms_by_rank": push_by_rank,
                    "options": args.option, "setup_s": setup_s},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches2 - launches1), "launches_per_step": (launches2 - launches1) / args.steps,

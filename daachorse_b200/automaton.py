@@ -436,6 +436,9 @@ class Job:
     def scan_kernel_ms(self):
         return _lib.load().dach_job_scan_kernel_ms(self._h)
 
+    def push_ms(self):
+        return _lib.load().dach_job_push_ms(self._h)
+
 
 def _current_device():
     try:

@@ -199,6 +199,7 @@ int dach_job_place(dach_job *job, dach_match *d_out, uint64_t out_cap, uint64_t 
                    const uint64_t *d_base, void *stream);
 int dach_job_wait(dach_job *job, uint64_t *needed);
 double dach_job_scan_kernel_ms(const dach_job *job); /* CUDA-event time of the job's last scan kernel */
+double dach_job_push_ms(const dach_job *job);        /* ... of its last peer push (dach_group_place), 0 if none */
 
 /* ---- shard groups: the exchange step of a batch sharded over the GPUs of one node ---------
  *
