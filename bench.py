@@ -515,8 +515,8 @@ def main():
     peak, peak_src = measured_peaks()
     k_ms = float(np.mean(kernel_ms))
     achieved = step_bytes / (k_ms * 1e-3) / 1e9
-    kname = {"C3": "k_scan_machine<StdMachine3<M_OVERLAPPING>, Lane3, 1024, 1, true>", "C3-find": "k_scan_machine<StdMachine3<M_FIND>, Lane3, 1024, 1, true>",
-             "C2": "k_scan_machine<StdMachine3<M_OVERLAPPING>, Lane3, 1024, 1, true>", "C5": "k_scan_machine<StdMachine3<M_OVERLAPPING>, Lane3, 1024, 1, true>",
+    kname = {"C3": "k_scan_machine<StdMachine3<M_OVERLAPPING>, Lane3, 1024, 1, false>", "C3-find": "k_scan_machine<StdMachine3<M_FIND>, Lane3, 1024, 1, false>",
+             "C2": "k_scan_machine<StdMachine3<M_OVERLAPPING>, Lane3, 1024, 1, false>", "C5": "k_scan_machine<StdMachine3<M_OVERLAPPING>, Lane3, 1024, 1, false>",
              "C4": "k_scan_machine<CwMachine<M_LEFTMOST>, LaneCw, 1024, 1, false>",
              "C4-bw": "k_scan_machine<LmMachine, LaneLm, 1024, 1, false>"}[args.config]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
