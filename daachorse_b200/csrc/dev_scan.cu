@@ -413,11 +413,14 @@ template <int U>
 __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const ScanCtrl* ctrl, uint32_t pool_blocks,
                                                  const uint32_t* counts, const unsigned long long* item_offs,
                                                  uint64_t n_items, unsigned long long out_cap, const unsigned long long* base,
-                                                 uint32_t* out_words, const uint32_t* blkmap) {
+                                                 uint32_t* out_words, const uint32_t* blkmap, const unsigned long long* pad_like) {
     if (ctrl->overflow) return;
     const unsigned long long b0m = base ? *base : 0ull;
     if (b0m + item_offs[n_items] > out_cap) return;
     out_words += b0m * 3ull;
+    // staged copy for k_push: start at the word offset (mod 4) the tuples will have at their final base, so that
+    // source and destination of the push are congruent modulo 16 bytes
+    if (pad_like) out_words += (*pad_like * 3ull) & 3ull;
     const uint32_t used = min(ctrl->blk_cursor, pool_blocks);
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -455,7 +458,7 @@ __global__ void __launch_bounds__(256) k_gather(const uint32_t* pool, const Scan
 // memory, as DESTINATION-ALIGNED 16-byte stores -- a warp store is 512 contiguous bytes, whole 128-byte lines on
 // NVLink.  (k_gather's own stores are 4 bytes per lane at the 4-byte alignment of a tuple array: as peer stores
 // they reach 350 GB/s into one GPU where the link takes 770, profiles/r2_multi_gpu.md.)
-// 128 threads x 40 registers: three CTAs fit into the registers an SM has left beside a resident scan CTA
+// 128 threads x at most 51 registers: two CTAs fit into the registers an SM has left beside a resident scan CTA
 // (1024 threads x 48), so the push of step s really runs while step s+1 is scanned.
 __global__ void __launch_bounds__(128, 10) k_push(const uint32_t* src, const unsigned long long* total_ptr, const unsigned long long* base,
                                                unsigned long long out_cap, const ScanCtrl* ctrl, uint32_t* out_words) {
@@ -463,30 +466,25 @@ __global__ void __launch_bounds__(128, 10) k_push(const uint32_t* src, const uns
     const unsigned long long b0 = base ? *base : 0ull, total = *total_ptr;
     if (b0 + total > out_cap) return;
     uint32_t* dst = out_words + b0 * 3ull;
+    src += (b0 * 3ull) & 3ull;  // the staged copy starts at the destination's word offset modulo 4 (k_gather, pad_like)
     const unsigned long long n_words = total * 3ull;
     const unsigned long long head = min((unsigned long long)((4u - (uint32_t)(((uintptr_t)dst >> 2) & 3u)) & 3u), n_words);
     const unsigned long long n_vec = (n_words - head) / 4ull;
     const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long nth = (unsigned long long)gridDim.x * blockDim.x;
-    const uint32_t* s1 = src + head;  // local, 4-byte aligned: four word loads make one destination-aligned 16-byte store
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);  // 16-byte aligned: congruent with dst + head
     uint4* d4 = reinterpret_cast<uint4*>(dst + head);
     unsigned long long v = tid;
 #pragma unroll 1
-    for (; v + nth < n_vec; v += 2ull * nth) {  // two 16-byte peer stores in flight per thread
-        const uint32_t* p = s1 + 4ull * v;
-        const uint32_t* q = s1 + 4ull * (v + nth);
-        uint4 a, b;
-        a.x = p[0], a.y = p[1], a.z = p[2], a.w = p[3];
-        b.x = q[0], b.y = q[1], b.z = q[2], b.w = q[3];
+    for (; v + 3ull * nth < n_vec; v += 4ull * nth) {  // four 16-byte loads, then four 16-byte peer stores in flight per thread
+        const uint4 a = s4[v], b = s4[v + nth], c = s4[v + 2ull * nth], e = s4[v + 3ull * nth];
         d4[v] = a;
         d4[v + nth] = b;
+        d4[v + 2ull * nth] = c;
+        d4[v + 3ull * nth] = e;
     }
-    if (v < n_vec) {
-        const uint32_t* p = s1 + 4ull * v;
-        uint4 a;
-        a.x = p[0], a.y = p[1], a.z = p[2], a.w = p[3];
-        d4[v] = a;
-    }
+#pragma unroll 1
+    for (; v < n_vec; v += nth) d4[v] = s4[v];
     const unsigned long long tail0 = head + 4ull * n_vec;
     if (tid < head) dst[tid] = src[tid];
     if (tid < n_words - tail0) dst[tail0 + tid] = src[tail0 + tid];
@@ -706,7 +704,6 @@ struct Workspace {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // pipeline start, scan end, pipeline end, scan start
     cudaEvent_t ev_scanned = nullptr, ev_placed = nullptr;
     cudaEvent_t ev_push[2] = {nullptr, nullptr};  // around k_push (shard groups)
-    cudaEvent_t ev_staged = nullptr;              // the packed copy of a staged placement is complete
     // the scan in flight (phase 1 -> phase 2)
     uint64_t job_n = 0, job_items = 0;
     uint32_t job_pool_blocks = 0;
@@ -727,7 +724,6 @@ struct Workspace {
         if (!ev_placed && !cuda_ok(cudaEventCreateWithFlags(&ev_placed, cudaEventDisableTiming), "cudaEventCreate")) return false;
         for (int i = 0; i < 2; ++i)
             if (!ev_push[i] && !cuda_ok(cudaEventCreate(&ev_push[i]), "cudaEventCreate")) return false;
-        if (!ev_staged && !cuda_ok(cudaEventCreateWithFlags(&ev_staged, cudaEventDisableTiming), "cudaEventCreate")) return false;
         if (with_stream && !stream && !cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate"))
             return false;
         return true;
@@ -755,8 +751,6 @@ struct Workspace {
                 cudaEventDestroy(ev_push[i]);
                 ev_push[i] = nullptr;
             }
-        if (ev_staged) cudaEventDestroy(ev_staged);
-        ev_staged = nullptr;
         if (ev_scanned) cudaEventDestroy(ev_scanned);
         if (ev_placed) cudaEventDestroy(ev_placed);
         ev_scanned = ev_placed = nullptr;
@@ -1217,24 +1211,17 @@ int enqueue_place(dach_dev* d, Workspace& W, dach_match* d_out, uint64_t out_cap
             g_base = nullptr;
             g_cap = W.job_cap;
         }
-        // The packing pass of a staged placement runs on the SCAN stream, right behind the scan: alone on the GPU it
-        // takes 0.5 ms per GiB scanned; beside the next scan (a fraction of the SMs' threads and registers, and the
-        // scan's fetches ahead of it in every queue) it takes many times that and would set the pace of the exchange.
-        cudaStream_t gs = staged ? W.job_stream : st;
+        const unsigned long long* pad_like = staged ? d_base : nullptr;
         if (d->opt_gather_u >= 8)
-            k_gather<8><<<gather_grid, 256, 0, gs>>>(pool, ctrl, W.job_pool_blocks, counts, item_offs, n_items, g_cap, g_base, out_words, blkmap);
+            k_gather<8><<<gather_grid, 256, 0, st>>>(pool, ctrl, W.job_pool_blocks, counts, item_offs, n_items, g_cap, g_base, out_words, blkmap, pad_like);
         else if (d->opt_gather_u <= 2)
-            k_gather<2><<<gather_grid, 256, 0, gs>>>(pool, ctrl, W.job_pool_blocks, counts, item_offs, n_items, g_cap, g_base, out_words, blkmap);
+            k_gather<2><<<gather_grid, 256, 0, st>>>(pool, ctrl, W.job_pool_blocks, counts, item_offs, n_items, g_cap, g_base, out_words, blkmap, pad_like);
         else
-            k_gather<4><<<gather_grid, 256, 0, gs>>>(pool, ctrl, W.job_pool_blocks, counts, item_offs, n_items, g_cap, g_base, out_words, blkmap);
+            k_gather<4><<<gather_grid, 256, 0, st>>>(pool, ctrl, W.job_pool_blocks, counts, item_offs, n_items, g_cap, g_base, out_words, blkmap, pad_like);
         ++d->launches;
         if (staged) {
-            if (gs != st) {
-                cudaEventRecord(W.ev_staged, gs);
-                cudaStreamWaitEvent(st, W.ev_staged, 0);
-            }
             cudaEventRecord(W.ev_push[0], st);
-            k_push<<<d->sm_count * 6, 128, 0, st>>>(out_words, item_offs + n_items, d_base, out_cap, ctrl, reinterpret_cast<uint32_t*>(d_out));
+            k_push<<<d->sm_count * 4, 128, 0, st>>>(out_words, item_offs + n_items, d_base, out_cap, ctrl, reinterpret_cast<uint32_t*>(d_out));
             cudaEventRecord(W.ev_push[1], st);
             ++d->launches;
         }
