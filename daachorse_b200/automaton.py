@@ -256,6 +256,12 @@ class _Automaton:
         text = np.ascontiguousarray(text, dtype=np.uint8)
         offs = np.ascontiguousarray(offs, dtype=np.uint64)
         n = len(offs) - 1
+        if n < 0 or (n > 0 and int(offs.max()) > text.size):
+            raise DaachorseError(_lib.INVALID_ARGUMENT, "offsets must hold n + 1 entries and stay inside the text")
+        if out is not None and (out.dtype != MATCH_DTYPE or not out.flags.c_contiguous):
+            raise DaachorseError(_lib.INVALID_ARGUMENT, "out must be a contiguous MATCH_DTYPE array")
+        if out_offs is not None and (out_offs.dtype != np.uint64 or not out_offs.flags.c_contiguous or len(out_offs) < n + 1):
+            raise DaachorseError(_lib.INVALID_ARGUMENT, "out_offs must be a contiguous uint64 array of n + 1 entries")
         if out is not None:
             cap = len(out)
         else:
@@ -287,6 +293,7 @@ class _Automaton:
         self._assert_mode(mode)
         L = _lib.load()
         dev = text.device.index if text.device.index is not None else torch.cuda.current_device()
+        _check_device_batch(text, offs, dev, out, out_offs)
         d = self.device_handle(dev)
         n = offs.numel() - 1
         if out_offs is None:
@@ -320,9 +327,9 @@ class _Automaton:
         self._assert_mode(mode)
         L = _lib.load()
         dev = text.device.index if text.device.index is not None else torch.cuda.current_device()
+        _check_device_batch(text, offs, dev, out, out_offs, state, pos)
         d = self.device_handle(dev)
         n = offs.numel() - 1
-        assert state.numel() == n and (pos is None or pos.numel() == n)
         if out_offs is None:
             out_offs = torch.empty(n + 1, dtype=torch.int64, device=text.device)
         cap = out.shape[0] if out is not None else max(1024, int(text.numel() // 8))
@@ -415,6 +422,7 @@ class Job:
     def scan(self, mode, text, offs, cap_matches, stream=None):
         """Enqueue the scan of ``text`` (uint8 CUDA tensor) / ``offs`` (int64, n+1) on ``stream``."""
         self._pma._assert_mode(mode)
+        _check_device_batch(text, offs, self._dev)
         self._keep = (text, offs)  # the kernels read them after this call returns
         _check(_lib.load().dach_job_scan(self._h, mode, C.c_void_p(text.data_ptr()), C.c_void_p(offs.data_ptr()),
                                          offs.numel() - 1, text.numel(), int(cap_matches), self._stream(stream, text.device)))
@@ -422,6 +430,9 @@ class Job:
     def place(self, out, out_offs, base=None, stream=None):
         """Enqueue the gather into ``out`` ((cap, 3) int32) / ``out_offs`` (int64, n+1); ``base``: optional
         1-element int64 CUDA tensor, index of the first match in ``out``."""
+        _check_device_batch(self._keep[0], self._keep[1], out.device.index, out, out_offs)
+        if base is not None and (not base.is_cuda or base.dtype not in (torch_int64(),) or base.numel() < 1):
+            raise DaachorseError(_lib.INVALID_ARGUMENT, "base must be a 1-element int64 CUDA tensor")
         self._out = (out, out_offs, base)
         _check(_lib.load().dach_job_place(self._h, C.c_void_p(out.data_ptr()), out.shape[0], C.c_void_p(out_offs.data_ptr()),
                                           C.c_void_p(base.data_ptr()) if base is not None else None,
@@ -438,6 +449,42 @@ class Job:
 
     def push_ms(self):
         return _lib.load().dach_job_push_ms(self._h)
+
+
+def torch_int64():
+    import torch
+
+    return torch.int64
+
+
+def _check_device_batch(text, offs, dev_index, out=None, out_offs=None, state=None, pos=None):
+    """Raw pointers cross the C ABI: a wrong dtype, stride or device would be silent garbage or a device fault."""
+    import torch
+
+    def bad(msg):
+        raise DaachorseError(_lib.INVALID_ARGUMENT, msg)
+
+    n = offs.numel() - 1
+    if n < 0:
+        bad("offs must hold n + 1 entries")
+    for name, t, dtypes in (("text", text, (torch.uint8,)), ("offs", offs, (torch.int64, torch.uint64)),
+                            ("out", out, (torch.int32, torch.uint32)), ("out_offs", out_offs, (torch.int64, torch.uint64)),
+                            ("state", state, (torch.int32, torch.uint32)), ("pos", pos, (torch.int32, torch.uint32))):
+        if t is None:
+            continue
+        if not t.is_cuda or t.device.index != dev_index:
+            bad("%s must be a CUDA tensor on cuda:%d" % (name, dev_index))
+        if t.dtype not in dtypes:
+            bad("%s has dtype %s, expected one of %s" % (name, t.dtype, dtypes))
+        if not t.is_contiguous():
+            bad("%s must be contiguous" % name)
+    if out is not None and (out.dim() != 2 or out.shape[1] != 3):
+        bad("out must have shape (capacity, 3)")
+    if out_offs is not None and out_offs.numel() < n + 1:
+        bad("out_offs must hold n + 1 entries")
+    for name, t in (("state", state), ("pos", pos)):
+        if t is not None and t.numel() != n:
+            bad("%s must hold n entries" % name)
 
 
 def _current_device():
