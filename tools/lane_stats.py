@@ -1,7 +1,6 @@
 #!/usr/bin/env python3
 """Per-byte event counts of the bytewise Standard lane machine on samples of the bench workloads, from
-the CPU emulation of the kernels' lane code (tests/emu, StdMachine with its DACH_STAT counters; the
-events -- probes, signature skips, misses, landings with output -- are the same for StdMachine2).
+the CPU emulation of the kernels' lane code (tests/emu, StdMachine3 with its DACH_STAT counters).
 No GPU needed.  Usage: python tools/lane_stats.py [C2|C3|C5 ...]"""
 import ctypes as C
 import os
@@ -34,9 +33,9 @@ def run(name, n_hay=256):
     text, offs = S.materialise_host(pool, starts, hay_len)
     buf = (C.c_ulonglong * len(NAMES))()
     lib = E.lib()
-    E.scan(wire, False, 1, text, offs, kernel=1, out_cap=1 << 24)  # sizes the output; counters reset below
+    E.scan(wire, False, 1, text, offs, kernel=3, out_cap=1 << 24)  # sizes the output; counters reset below
     lib.emu_stats(buf, 1)
-    rc, m, oo, need = E.scan(wire, False, 1, text, offs, kernel=1, out_cap=max(int(need_cap(text)), 1 << 16))
+    rc, m, oo, need = E.scan(wire, False, 1, text, offs, kernel=3, out_cap=max(int(need_cap(text)), 1 << 16))
     lib.emu_stats(buf, 1)
     nb = len(text)
     print("== %s: %d patterns, %d haystacks x %d B, %.4f matches/byte" % (name, len(ps), n_hay, hay_len, need / nb))
