@@ -342,7 +342,7 @@ def main():
     st_scan = torch.cuda.Stream(dev, priority=-1)
     st_place = st_scan if args.no_overlap else torch.cuda.Stream(dev, priority=0)
     setup_s = time.time() - t_setup
-    kernel_ms, push_ms = [], []
+    kernel_ms, push_ms, timeline = [], [], []
 
     def finish_prev(s):
         """everything of step s is in its final place (rank 0: from every rank); returns the step's match count"""
@@ -352,23 +352,37 @@ def main():
             tot = jobs[s % n_jobs].wait()
         kernel_ms.append(jobs[s % n_jobs].scan_kernel_ms())
         push_ms.append(jobs[s % n_jobs].push_ms())
+        timeline.append(jobs[s % n_jobs].times())
         return tot
 
     def run(steps, first):
-        """steps pipelined steps starting with batch index `first`; returns the last step's total"""
+        """steps pipelined steps starting with batch index `first`; returns the last step's total.
+        The scan of step s+1 is enqueued before step s is placed: a shard group's place() blocks until the rank's
+        host knows where its matches go (its own scan done, the lower ranks' counts published)."""
         tot = 0
+        if steps <= 0:
+            return tot
+
+        def scan(s):
+            t, o = batches[(first + s) % len(batches)]
+            jobs[s % n_jobs].scan(dmode, t, o, cap_local, stream=st_scan)
+
+        scan(0)
         for s in range(steps):
             j = jobs[s % n_jobs]
-            t, o = batches[(first + s) % len(batches)]
-            j.scan(dmode, t, o, cap_local, stream=st_scan)            # step s scans ...
-            if s > 0 and n_jobs > 1:
-                tot = finish_prev(s - 1)                                # ... while step s-1 lands; then consume it
+            if n_jobs > 1:
+                if s > 0:
+                    tot = finish_prev(s - 1)                            # step s-1 has landed: consume it ...
+                if s + 1 < steps:
+                    scan(s + 1)                                         # ... its job scans step s+1 ...
             if group is not None:
-                group.place(j, rank * n, rank == world - 1, stream=st_place)
+                group.place(j, rank * n, rank == world - 1, stream=st_place)   # ... while step s is exchanged
             else:
                 j.place(out_m, out_o, stream=st_place)
             if n_jobs == 1:
                 tot = finish_prev(s)
+                if s + 1 < steps:
+                    scan(s + 1)
         if n_jobs > 1:
             tot = finish_prev(steps - 1)
         return tot
@@ -385,6 +399,7 @@ def main():
     n_before = len(sampler.rows)
     kernel_ms.clear()
     push_ms.clear()
+    timeline.clear()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches1 = pma.stats()["launches"]
     barrier()
@@ -411,8 +426,18 @@ def main():
         allp_ms = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allp_ms, t)
         push_by_rank = [float(x.item()) for x in allp_ms]
+        tl = torch.tensor(timeline[-4:], dtype=torch.float64, device=dev).reshape(-1)
+        alltl = [torch.zeros_like(tl) for _ in range(world)]
+        dist.all_gather(alltl, tl)
+        # per rank, last four steps: ms of (scan start, scan end, push start, push end) relative to the rank's first
+        # timed scan start of those four (clocks of different GPUs are not comparable: per-rank offsets only)
+        timeline_by_rank = []
+        for x in alltl:
+            a = x.reshape(-1, 4).cpu().numpy()
+            timeline_by_rank.append([[round(float(v - a[0, 0]), 2) if v else None for v in row] for row in a])
     else:
         push_by_rank = []
+        timeline_by_rank = []
     job_bytes = step_bytes * world
     value = job_bytes / (ms * 1e-3) / 1e9
     last_batch = (args.warmup + args.steps - 1) % len(batches)
@@ -573,7 +598,7 @@ def main():
                        "; every rank's placement kernel stores its matches into rank 0's dense buffer over NVLink peer memory "
                        "(dach_group_*), rank 0 holds the rebased %d-GPU result after every step" % world if world > 1 else ""),
                    "pipelining": "none (--no-overlap)" if args.no_overlap else "two jobs: the placement of step s runs beside the scan of step s+1",
-                   "peer_push_ms_by_rank": push_by_rank,
+                   "peer_push_ms_by_rank": push_by_rank, "timeline_last4_by_rank": timeline_by_rank,
                    "options": args.option, "setup_s": setup_s},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches2 - launches1), "launches_per_step": (launches2 - launches1) / args.steps,

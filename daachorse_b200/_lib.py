@@ -21,7 +21,7 @@ SYMBOLS = [
     "dach_scan_batch_host", "dach_dev_kernel_launches", "dach_dev_last_scan_kernel_ms",
     "dach_dev_last_total_ms", "dach_dev_last_h2d_bytes", "dach_dev_last_d2h_bytes",
     "dach_dev_set_option", "dach_last_error", "dach_abi_version",
-    "dach_job_create", "dach_job_free", "dach_job_scan", "dach_job_place", "dach_job_wait", "dach_job_scan_kernel_ms", "dach_job_push_ms",
+    "dach_job_create", "dach_job_free", "dach_job_scan", "dach_job_place", "dach_job_wait", "dach_job_scan_kernel_ms", "dach_job_push_ms", "dach_job_times",
     "dach_group_create", "dach_group_export", "dach_group_connect", "dach_group_place", "dach_group_finish",
     "dach_group_result", "dach_group_free",
 ]
@@ -95,6 +95,8 @@ def load():
     L.dach_job_scan_kernel_ms.restype = C.c_double
     L.dach_job_push_ms.argtypes = [vp]
     L.dach_job_push_ms.restype = C.c_double
+    L.dach_job_times.argtypes = [vp, C.POINTER(C.c_double * 4)]
+    L.dach_job_times.restype = C.c_int
     L.dach_group_create.argtypes = [C.c_int, C.c_int, C.c_int, u64, u64, pp]
     L.dach_group_export.argtypes = [vp, vp]
     L.dach_group_connect.argtypes = [vp, vp]

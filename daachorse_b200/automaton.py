@@ -450,6 +450,12 @@ class Job:
     def push_ms(self):
         return _lib.load().dach_job_push_ms(self._h)
 
+    def times(self):
+        """ms since the automaton's first job scan on this device: (scan start, scan end, push start, push end)."""
+        buf = (C.c_double * 4)()
+        _check(_lib.load().dach_job_times(self._h, C.byref(buf)))
+        return tuple(float(x) for x in buf)
+
 
 def torch_int64():
     import torch

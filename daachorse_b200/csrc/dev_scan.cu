@@ -812,6 +812,7 @@ struct dach_dev {
                              // lane-per-haystack kernels
     // stats
     std::atomic<uint64_t> launches{0};
+    cudaEvent_t ev_ref = nullptr;  // time zero of dach_job_times (recorded at the first job scan)
     double last_scan_ms = 0, last_total_ms = 0;
     uint64_t last_h2d = 0, last_d2h = 0;
 };
@@ -1187,7 +1188,7 @@ int enqueue_scan(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, con
 // this batch's first match in d_out, added to the offsets too; `last`: also write out_offs[n].
 int enqueue_place(dach_dev* d, Workspace& W, dach_match* d_out, uint64_t out_cap, uint64_t* d_out_offs,
                   const unsigned long long* d_base, bool last, cudaStream_t st, const uint32_t* d_pos_in = nullptr,
-                  bool staged = false) {
+                  bool staged = false, bool dma = false, uint64_t h_base = 0, uint64_t h_total = 0) {
     if (!W.job_open) {
         set_error("no scan to place");
         return DACH_INVALID_ARGUMENT;
@@ -1221,9 +1222,19 @@ int enqueue_place(dach_dev* d, Workspace& W, dach_match* d_out, uint64_t out_cap
         ++d->launches;
         if (staged) {
             cudaEventRecord(W.ev_push[0], st);
-            k_push<<<d->sm_count * 4, 128, 0, st>>>(out_words, item_offs + n_items, d_base, out_cap, ctrl, reinterpret_cast<uint32_t*>(d_out));
+            if (dma) {
+                // base and count are known on the host: the packed tuples go out through a copy engine -- no SM, no
+                // LSU slot and no L1 line is taken from the scan that runs beside the exchange
+                if (h_total && h_base + h_total <= out_cap &&
+                    !cuda_ok(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(d_out) + h_base * 3ull, out_words + ((h_base * 3ull) & 3ull),
+                                             h_total * sizeof(dach_match), cudaMemcpyDefault, st),
+                             "peer copy"))
+                    return DACH_CUDA_ERROR;
+            } else {
+                k_push<<<d->sm_count * 4, 128, 0, st>>>(out_words, item_offs + n_items, d_base, out_cap, ctrl, reinterpret_cast<uint32_t*>(d_out));
+                ++d->launches;
+            }
             cudaEventRecord(W.ev_push[1], st);
-            ++d->launches;
         }
     }
     k_final_offsets<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(
@@ -1565,6 +1576,7 @@ void dach_dev_free(dach_dev* d) {
     if (!d) return;
     DeviceGuard g(d->device);
     cudaFree(d->image_base);
+    if (d->ev_ref) cudaEventDestroy(d->ev_ref);
     d->ws.release();
     for (Workspace& w : d->slot) w.release();
     delete d;
@@ -1655,6 +1667,10 @@ int dach_job_scan(dach_job* j, int mode, const uint8_t* d_text, const uint64_t* 
     return guarded([&]() -> int {
         DeviceGuard g(j->d->device);
         if (!g.ok) return DACH_CUDA_ERROR;
+        {
+            std::lock_guard<std::mutex> lk(j->d->mu);
+            if (!j->d->ev_ref && cudaEventCreate(&j->d->ev_ref) == cudaSuccess) cudaEventRecord(j->d->ev_ref, static_cast<cudaStream_t>(stream));
+        }
         return enqueue_scan(j->d, j->W, mode, d_text, d_text, d_text + text_bytes, text_bytes, d_offs, n, cap_matches,
                             static_cast<cudaStream_t>(stream));
     });
@@ -1690,6 +1706,19 @@ double dach_job_scan_kernel_ms(const dach_job* j) {
     return 0;
 }
 
+// ms since the handle's first job scan of {scan kernel start, scan kernel end, peer push start, peer push end} of the job's
+// last step (the last two are 0 without a peer push): the timeline of a pipelined run
+int dach_job_times(const dach_job* j, double out[4]) {
+    if (!j || !out || !j->d->ev_ref) return DACH_INVALID_ARGUMENT;
+    cudaEvent_t evs[4] = {j->W.ev[3], j->W.ev[1], j->W.ev_push[0], j->W.ev_push[1]};
+    for (int i = 0; i < 4; ++i) {
+        float ms = 0;
+        out[i] = cudaEventElapsedTime(&ms, j->d->ev_ref, evs[i]) == cudaSuccess ? ms : 0.0;
+    }
+    cudaGetLastError();
+    return DACH_OK;
+}
+
 double dach_job_push_ms(const dach_job* j) {
     float ms = 0;
     if (j && cudaEventElapsedTime(&ms, j->W.ev_push[0], j->W.ev_push[1]) == cudaSuccess) return ms;
@@ -1710,7 +1739,9 @@ struct dach_group {
     int n_ipc = 0;
     unsigned long long step = 0;
     GroupCtl* pinned = nullptr;    // host copy of the control block (finish)
+    unsigned long long* h_vals = nullptr;  // pinned: {base, total, overflow flag} of the step being placed
     bool connected = false;
+    bool push_dma = true;  // packed tuples leave through a copy engine (the rank's host learns base and count first)
 };
 
 namespace {
@@ -1742,7 +1773,9 @@ int dach_group_create(int rank, int world, int device, uint64_t match_cap, uint6
         memset(&G->peers, 0, sizeof(G->peers));
         bool ok = cuda_ok(cudaMalloc(reinterpret_cast<void**>(&G->ctl), sizeof(GroupCtl)), "cudaMalloc group control") &&
                   cuda_ok(cudaMemset(G->ctl, 0, sizeof(GroupCtl)), "memset group control") &&
-                  cuda_ok(cudaMallocHost(reinterpret_cast<void**>(&G->pinned), sizeof(GroupCtl)), "cudaMallocHost");
+                  cuda_ok(cudaMallocHost(reinterpret_cast<void**>(&G->pinned), sizeof(GroupCtl)), "cudaMallocHost") &&
+                  cuda_ok(cudaMallocHost(reinterpret_cast<void**>(&G->h_vals), 64), "cudaMallocHost");
+        if (const char* e = getenv("DACH_GROUP_PUSH")) G->push_dma = strcmp(e, "sm") != 0;  // "sm": k_push instead of the copy engine
         if (ok && rank == 0)
             ok = cuda_ok(cudaMalloc(reinterpret_cast<void**>(&G->out), std::max<uint64_t>(match_cap, 1) * sizeof(dach_match)), "cudaMalloc gathered matches") &&
                  cuda_ok(cudaMalloc(reinterpret_cast<void**>(&G->offs), (n_haystacks_total + 1) * 8), "cudaMalloc gathered offsets");
@@ -1859,8 +1892,21 @@ int dach_group_place(dach_group* G, dach_job* j, uint64_t hay_base, int last, vo
         k_group_wait_base<<<1, 1, 0, st>>>(G->ctl, G->rank, step);
         j->d->launches += 3;
         j->out_cap = G->match_cap;
+        const bool staged = G->rank != 0, dma = staged && G->push_dma;
+        uint64_t h_base = 0, h_total = 0;
+        if (dma) {
+            // The rank's host learns its base and count (blocks until the rank's scan is done, the lower ranks have
+            // published and rank 0 has released the previous result).  Callers that pipeline steps enqueue the next
+            // scan BEFORE this call so that the scan stream stays fed.
+            cudaMemcpyAsync(&G->h_vals[0], &G->ctl->base[step & 1], 8, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(&G->h_vals[1], total, 8, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(&G->h_vals[2], W.ctrl.p, sizeof(ScanCtrl), cudaMemcpyDeviceToHost, st);
+            if (!cuda_ok(cudaStreamSynchronize(st), "shard group: base")) return DACH_CUDA_ERROR;
+            h_base = G->h_vals[0];
+            h_total = reinterpret_cast<const ScanCtrl*>(&G->h_vals[2])->overflow ? 0 : G->h_vals[1];
+        }
         const int rc = enqueue_place(j->d, W, G->out, G->match_cap, G->offs + hay_base, &G->ctl->base[step & 1], last != 0, st, nullptr,
-                                     /*staged=*/G->rank != 0);
+                                     staged, dma, h_base, h_total);
         if (rc) return rc;
         k_group_signal_done<<<1, 1, 0, st>>>(G->peers.ctl[0], G->rank, step);
         ++j->d->launches;
@@ -1914,6 +1960,7 @@ void dach_group_free(dach_group* G) {
     }
     cudaFree(G->ctl);
     if (G->pinned) cudaFreeHost(G->pinned);
+    if (G->h_vals) cudaFreeHost(G->h_vals);
     delete G;
 }
 

@@ -200,6 +200,9 @@ int dach_job_place(dach_job *job, dach_match *d_out, uint64_t out_cap, uint64_t 
 int dach_job_wait(dach_job *job, uint64_t *needed);
 double dach_job_scan_kernel_ms(const dach_job *job); /* CUDA-event time of the job's last scan kernel */
 double dach_job_push_ms(const dach_job *job);        /* ... of its last peer push (dach_group_place), 0 if none */
+/* ms since the handle's first dach_job_scan of {scan kernel start, scan kernel end, peer push start, peer push end}
+ * of the job's last step: the timeline of a pipelined run (bench.py config.timeline) */
+int dach_job_times(const dach_job *job, double out[4]);
 
 /* ---- shard groups: the exchange step of a batch sharded over the GPUs of one node ---------
  *

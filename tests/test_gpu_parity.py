@@ -562,10 +562,14 @@ def _group_case(world, devices):
             jobs.append(pma.job(devices[r]))
             streams.append(torch.cuda.Stream(dev))
     for step in range(3):  # the buffers are reused step after step
-        order = range(world) if step % 2 == 0 else reversed(range(world))  # issue order must not matter
+        order = list(range(world)) if step % 2 == 0 else list(reversed(range(world)))  # scans may be issued in any order
         for r in order:
             with torch.cuda.device(devices[r]):
                 jobs[r].scan(D.FIND_OVERLAPPING, inputs[r][0], inputs[r][1], cap, stream=streams[r])
+        # place() blocks until the rank's host knows its base (the lower ranks' counts): one thread driving all ranks
+        # has to place them in rank order (one process or thread per rank has no such constraint)
+        for r in range(world):
+            with torch.cuda.device(devices[r]):
                 groups[r].place(jobs[r], bounds[r], r == world - 1, stream=streams[r])
         for r in reversed(range(1, world)):
             with torch.cuda.device(devices[r]):
