@@ -221,7 +221,14 @@ int dach_job_times(const dach_job *job, double out[4]);
  *            or handles inside one process (peer access).
  *   place    the exchange step of one job: hay_base = index of the shard's first haystack in the
  *            whole batch, last = this shard ends the batch (it also writes offsets[n_total]).
- *            Calling place for step s releases the result of step s-1 (rank 0).
+ *            Calling place for step s releases the result of step s-1 (rank 0).  On ranks other
+ *            than 0 the call BLOCKS until the rank's host knows where its matches go -- its own scan
+ *            is done, the lower ranks have published their counts, rank 0 has released the previous
+ *            result -- because the packed tuples then leave through a copy engine (no SM, LSU slot or
+ *            L1 line is taken from the scan running beside the exchange).  Pipelining callers enqueue
+ *            the next dach_job_scan before they call place; one thread driving several ranks places
+ *            them in rank order.  (Environment DACH_GROUP_PUSH=sm keeps everything on the device:
+ *            k_push, destination-aligned 16-byte peer stores, no host round trip.)
  *   finish   rank 0: enqueues the wait for all ranks on `stream`, synchronises it, reports the total
  *            (DACH_OUTPUT_OVERFLOW if it exceeds match_cap); other ranks: synchronise `stream`.
  *   result   rank 0's device pointers. */
