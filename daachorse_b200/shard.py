@@ -52,7 +52,9 @@ class PeerGroup:
         self._check(self._L.dach_group_connect(self._h, b"".join(blobs)))
 
     def place(self, job, hay_base, last, stream=None):
-        """The exchange step of ``job`` (a daachorse_b200.Job that has scanned this rank's shard)."""
+        """The exchange step of ``job`` (a daachorse_b200.Job that has scanned this rank's shard).  On ranks other than
+        0 the call blocks until the rank's scan is done and the lower ranks' counts are in (its matches then leave
+        through a copy engine): enqueue the next scan first; one thread driving several ranks places in rank order."""
         st = job._stream(stream, self.device)
         self._check(self._L.dach_group_place(self._h, job._h, int(hay_base), 1 if last else 0, st))
 
