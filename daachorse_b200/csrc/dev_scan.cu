@@ -1,17 +1,29 @@
 // CUDA kernels (sm_100a) and the device half of the C ABI of libdaachorse_b200.
 //
-// Pipeline of one dach_dev_scan_batch():
-//   1. k_scan_machine<M, LANE>  persistent grid (CTAs = SMs x ctas_per_sm); warps of 32 independent
-//                               walkers pull items (haystacks or segments) from one atomic counter
-//                               and step them in lock step through the automaton image -- one record
-//                               fetch per lane per iteration (scan_lane.cuh: StdMachine2, LmMachine,
-//                               CwMachine); matches go to pooled 256-byte blocks.
-//      k_scan<CHARWISE, MODE>   lane per haystack, reference-shaped loop: automata above 2^24 slots,
-//                               find_iter with an empty pattern, and option kernel=0.
-//   2. k_offsets_*              exclusive scan of the per-item match counts -> d_out_offs (u64).
-//   3. k_blk_index + k_gather   copy every pooled block to its final place (in output order for large
-//                               batches), which makes the output dense and ordered exactly like the
-//                               crate's iterators.
+// One scan is two phases that only enqueue work (enqueue_scan / enqueue_place; dach_dev_scan_batch runs them back to
+// back on one stream, dach_job_* exposes them, dach_group_* makes the second one the exchange step of a sharded batch):
+//   phase 1
+//     k_check_offsets           the caller's offsets: ascending, inside the text, no haystack of 4 GiB or more
+//     k_seg_*                   (find_overlapping / no_suffix) cut haystacks into segments with a warm-up
+//     k_scan_machine<M, LANE>   persistent grid (CTAs = SMs x ctas_per_sm); warps of 32 independent walkers pull
+//                               items from one atomic counter and step them in lock step through the automaton
+//                               image -- one record fetch per lane per iteration (scan_lane.cuh: StdMachine3,
+//                               LmMachine, CwMachine); matches go to pooled 256-byte blocks.
+//       k_scan_duo<MODE>        StdMachine3 with two haystacks per lane (option kernel = 4; measured slower)
+//       k_scan<CHARWISE, MODE>  lane per haystack, reference-shaped loop: automata above 2^24 slots, find_iter with
+//                               an empty pattern, and option kernel = 0
+//     k_offsets_*               exclusive scan of the per-item match counts
+//     k_blk_index               pool blocks listed in output order (large batches)
+//   phase 2
+//     k_gather                  every pooled block to its final place: dense, ordered exactly like the crate's
+//                               iterators, at a device-side base, into any buffer (the caller's, a job's packed copy)
+//     k_final_offsets           the caller's per-haystack offsets (+ base)
+//     k_add_base                stream chunks: positions in stream coordinates
+//   shard groups (dach_group_place)
+//     k_group_publish / k_group_wait_base / k_group_signal_done / k_group_wait_all / k_group_release
+//                               counts published into every rank's control block, bases derived from them, done
+//                               flags -- system-scope releases, local polling; the packed matches go to rank 0 through
+//                               a copy engine (or k_push: destination-aligned 16-byte peer stores)
 // No CPU fallback exists: every entry point here fails with DACH_CUDA_ERROR without a device.
 #include <cuda_runtime.h>
 

@@ -8,11 +8,14 @@
 // Contents, in file order:
 //   - wide records + the lane-per-haystack loops (scan_standard / scan_leftmost): the reference's control
 //     flow as written; used by k_scan for automata above 2^24 slots, find_iter with an empty pattern, kernel=0
-//   - StdMachine   bytewise Standard lane machine, first cut (kernel=1; optional shared-memory state cache)
+//   - StdMachine   bytewise Standard lane machine, first cut (kernel=1)
 //   - LmMachine    bytewise leftmost_find_iter on the lane machine
-//   - CwMachine    the four charwise iterators on the lane machine
-//   - StdMachine2  bytewise Standard lane machine, the default (three phases, ROOT in registers, text shift
-//                  register); also serves stream chunks (state carried in and out)
+//   - CwMachine    the four charwise iterators on the lane machine; also the charwise stream chunks
+//   - StdMachine2  bytewise Standard lane machine, round 1's default (kernel=2: three phases, ROOT in registers,
+//                  text shift register)
+//   - StdMachine3  the default (kernel=3): no probe-state flags, one stop bit, cursor = address word, records from
+//                  the hot-first image (optionally its front from shared memory); probe / resolve are separate so
+//                  that k_scan_duo can keep two fetches in flight; serves stream chunks
 //
 // Device image (built by dev_image.cpp from the validated host automaton):
 //   wide bytewise record  uint4 {base, efail, fbase, opos<<8 | check}      16 B / slot
