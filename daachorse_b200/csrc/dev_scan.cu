@@ -720,7 +720,7 @@ struct Workspace {
     uint64_t job_n = 0, job_items = 0;
     uint32_t job_pool_blocks = 0;
     uint64_t job_cap = 0;
-    bool job_seg = false, job_ordered = false, job_open = false;
+    bool job_seg = false, job_ordered = false, job_open = false, job_placed = false;
     cudaStream_t job_stream = nullptr;
     // host-batch slices only: device staging and the slice's stream
     DevBuf text, offs, out, out_offs;
@@ -1261,6 +1261,7 @@ int enqueue_place(dach_dev* d, Workspace& W, dach_match* d_out, uint64_t out_cap
     cudaMemcpyAsync(&W.pinned->total, item_offs + n_items, 8, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&W.pinned->ctrl, W.ctrl.p, sizeof(ScanCtrl), cudaMemcpyDeviceToHost, st);
     cudaEventRecord(W.ev_placed, st);
+    W.job_placed = true;
     return DACH_OK;
 }
 
@@ -1704,6 +1705,10 @@ int dach_job_place(dach_job* j, dach_match* d_out, uint64_t out_cap, uint64_t* d
 
 int dach_job_wait(dach_job* j, uint64_t* needed) {
     if (!j) return DACH_INVALID_ARGUMENT;
+    if (!j->W.job_placed) {
+        set_error("dach_job_wait: nothing has been placed yet");
+        return DACH_INVALID_ARGUMENT;
+    }
     return guarded([&]() -> int {
         DeviceGuard g(j->d->device);
         if (!g.ok) return DACH_CUDA_ERROR;
@@ -1906,6 +1911,7 @@ int dach_group_place(dach_group* G, dach_job* j, uint64_t hay_base, int last, vo
         j->out_cap = G->match_cap;
         const bool staged = G->rank != 0, dma = staged && G->push_dma;
         uint64_t h_base = 0, h_total = 0;
+        bool over = false;
         if (dma) {
             // The rank's host learns its base and count (blocks until the rank's scan is done, the lower ranks have
             // published and rank 0 has released the previous result).  Callers that pipeline steps enqueue the next
@@ -1915,7 +1921,11 @@ int dach_group_place(dach_group* G, dach_job* j, uint64_t hay_base, int last, vo
             cudaMemcpyAsync(&G->h_vals[2], W.ctrl.p, sizeof(ScanCtrl), cudaMemcpyDeviceToHost, st);
             if (!cuda_ok(cudaStreamSynchronize(st), "shard group: base")) return DACH_CUDA_ERROR;
             h_base = G->h_vals[0];
-            h_total = reinterpret_cast<const ScanCtrl*>(&G->h_vals[2])->overflow ? 0 : G->h_vals[1];
+            h_total = G->h_vals[1];
+            // the job's pool or its packed copy was too small for this shard: nothing valid to send (the rank's count
+            // is published all the same, so the other ranks' bases stay right and nobody waits for this one)
+            over = reinterpret_cast<const ScanCtrl*>(&G->h_vals[2])->overflow != 0 || h_total > W.job_cap;
+            if (over) h_total = 0;
         }
         const int rc = enqueue_place(j->d, W, G->out, G->match_cap, G->offs + hay_base, &G->ctl->base[step & 1], last != 0, st, nullptr,
                                      staged, dma, h_base, h_total);
@@ -1924,6 +1934,13 @@ int dach_group_place(dach_group* G, dach_job* j, uint64_t hay_base, int last, vo
         ++j->d->launches;
         if (!cuda_ok(cudaGetLastError(), "shard group kernels")) return DACH_CUDA_ERROR;
         cudaEventRecord(W.ev_placed, st);  // the job's buffers are free once the done signal is out
+        if (over) {
+            char buf[200];
+            snprintf(buf, sizeof(buf), "shard group: the job's capacity (%llu matches) is too small for this shard (needed %llu)",
+                     (unsigned long long)W.job_cap, (unsigned long long)G->h_vals[1]);
+            set_error(buf);
+            return DACH_OUTPUT_OVERFLOW;
+        }
         return DACH_OK;
     });
 }
