@@ -171,6 +171,32 @@ class Workload:
         return D.DoubleArrayAhoCorasickBuilder.new().match_kind(self.match_kind).build(self.ps.as_list())
 
 
+def run_pipeline(steps, n_jobs, scan, place, finish):
+    """The order in which a run issues its steps (callbacks take the step index; `finish` returns the step's total).
+    With two jobs the scan of step s+1 is enqueued before step s is placed -- a shard group's place() blocks until
+    the rank's host knows where its matches go (its own scan done, the lower ranks' counts published) -- and only
+    after step s-1 has been finished, because it reuses that step's job."""
+    tot = 0
+    if steps <= 0:
+        return tot
+    scan(0)
+    for s in range(steps):
+        if n_jobs > 1:
+            if s > 0:
+                tot = finish(s - 1)      # step s-1 has landed: consume it ...
+            if s + 1 < steps:
+                scan(s + 1)              # ... its job scans step s+1 ...
+            place(s)                     # ... while step s is exchanged
+        else:
+            place(s)
+            tot = finish(s)
+            if s + 1 < steps:
+                scan(s + 1)
+    if n_jobs > 1:
+        tot = finish(steps - 1)
+    return tot
+
+
 def mode_ids(mode_name):
     import daachorse_b200 as D
     import oracle_api as O
@@ -356,36 +382,19 @@ def main():
         return tot
 
     def run(steps, first):
-        """steps pipelined steps starting with batch index `first`; returns the last step's total.
-        The scan of step s+1 is enqueued before step s is placed: a shard group's place() blocks until the rank's
-        host knows where its matches go (its own scan done, the lower ranks' counts published)."""
-        tot = 0
-        if steps <= 0:
-            return tot
-
+        """steps pipelined steps starting with batch index `first`; returns the last step's total"""
         def scan(s):
             t, o = batches[(first + s) % len(batches)]
             jobs[s % n_jobs].scan(dmode, t, o, cap_local, stream=st_scan)
 
-        scan(0)
-        for s in range(steps):
+        def place(s):
             j = jobs[s % n_jobs]
-            if n_jobs > 1:
-                if s > 0:
-                    tot = finish_prev(s - 1)                            # step s-1 has landed: consume it ...
-                if s + 1 < steps:
-                    scan(s + 1)                                         # ... its job scans step s+1 ...
             if group is not None:
-                group.place(j, rank * n, rank == world - 1, stream=st_place)   # ... while step s is exchanged
+                group.place(j, rank * n, rank == world - 1, stream=st_place)
             else:
                 j.place(out_m, out_o, stream=st_place)
-            if n_jobs == 1:
-                tot = finish_prev(s)
-                if s + 1 < steps:
-                    scan(s + 1)
-        if n_jobs > 1:
-            tot = finish_prev(steps - 1)
-        return tot
+
+        return run_pipeline(steps, n_jobs, scan, place, finish_prev)
 
     def barrier():
         if world > 1:
