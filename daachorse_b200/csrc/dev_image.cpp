@@ -288,6 +288,14 @@ int build_image(const dach_pma* p, HostImage* img) {
             }
             for (uint32_t v = 0; v < H; ++v)  // slots of the region no state occupies
                 if (R.vacant_check[v] && v != kRoot && v != kDead) img->crec[size_t(v) * 4] = R.vacant_check[v] & 0xffu;
+            // Slots a moved state left behind (ROOT's and DEAD's old places included) keep its CHECK byte: the
+            // shifted part is then probe for probe the crate's array, and the only BASE a moved child's byte
+            // could answer to is its parent's old one, which moved with the family and is unique.  (An all-zero
+            // record would answer label 0 to whichever state's BASE equals the slot: a wrong transition on a
+            // NUL byte.)
+            if (H)
+                for (size_t s = 0; s < n; ++s)
+                    if (R.new_of_old[s] < H) img->crec[(s + H) * 4] = p->opos_ch[s] & 0xffu;
         }
     } else {
         for (size_t s = 0; s < n; ++s) {

@@ -408,3 +408,110 @@ extern "C" int emu_scan_stream_wire(const uint8_t* wire, size_t wire_len, int mo
     g_pos_in = nullptr;
     return rc;
 }
+
+// Exhaustive check of the compact bytewise image against the crate's transition function: for every state s of
+// the host automaton and every byte c, following the image's records (signature, BASE ^ c with CHECK, efail /
+// fbase chain, the flags CF_FROOT / CF_F2ROOT / CF_F2DEAD) from new_of_old[s] must end in new_of_old[delta(s, c)].
+// Returns the number of mismatches (0 = the relayout and every derived field are consistent), -1 on a bad automaton.
+extern "C" long long emu_check_image_transitions(const uint8_t* wire, size_t wire_len, uint32_t want_hot_slots,
+                                                 uint32_t* hot_slots_out, uint32_t* hot_used_out) {
+    dach_pma* pma = nullptr;
+    size_t used = 0;
+    if (wire_read(wire, wire_len, false, &pma, &used)) return -1;
+    HostImage img;
+    img.want_hot_slots = want_hot_slots;
+    if (build_image(pma, &img) || img.crec.empty()) {
+        delete pma;
+        return -1;
+    }
+    const bool lm = is_leftmost(pma->match_kind);
+    const size_t n = pma->slots();
+    const uint32_t N = img.n_cslots;
+    auto rec = [&](uint32_t slot) { return &img.crec[(size_t)slot * 4]; };
+    auto nid = [&](uint32_t s) { return img.hot_slots ? img.new_of_old[s] : s; };
+    // reachable states of the host automaton
+    std::vector<uint8_t> live(n, 0);
+    std::vector<uint32_t> q{kRoot};
+    live[kRoot] = 1;
+    for (size_t h = 0; h < q.size(); ++h) {
+        const uint32_t s = q[h], b = pma->base[s];
+        if (!b) continue;
+        for (uint32_t c = 0; c < 256; ++c) {
+            const uint32_t ci = b ^ c;
+            if (ci < n && (pma->opos_ch[ci] & 0xffu) == c && !live[ci]) live[ci] = 1, q.push_back(ci);
+        }
+    }
+    long long bad = 0;
+    uint32_t hot_used = 0;
+    for (uint32_t s : q) {
+        if (nid(s) < img.hot_slots) ++hot_used;
+        for (uint32_t c = 0; c < 256; ++c) {
+            // the crate (src/bytewise.rs:1063-1088 / :1094-1128)
+            uint32_t t = s;
+            for (;;) {
+                const uint32_t b = pma->base[t];
+                if (b) {
+                    const uint32_t ci = b ^ c;
+                    if (ci < n && (pma->opos_ch[ci] & 0xffu) == c) {
+                        t = ci;
+                        break;
+                    }
+                }
+                if (t == kRoot) break;
+                const uint32_t f = pma->fail[t];
+                if (lm && f == kDead) {
+                    t = kRoot;
+                    break;
+                }
+                t = f;
+            }
+            // the image, field by field as the lane machines read it (scan_lane.cuh, StdMachine3 / LmMachine)
+            auto child = [&](uint32_t base, uint32_t* out) {
+                if (!base) return false;
+                const uint32_t a = base ^ c;
+                if (a >= N || (rec(a)[0] & 0xffu) != c) return false;
+                *out = a;
+                return true;
+            };
+            uint32_t cur = nid(s), got = kRoot;
+            bool done = child(rec(cur)[0] >> 8, &got);
+            if (done && !((rec(cur)[3] >> (c & 31u)) & 1u)) ++bad;  // the signature must never hide a child
+            if (!done && cur != kRoot) {
+                for (int guard = 0; guard < 1 << 20 && !done; ++guard) {
+                    const uint32_t nf = rec(cur)[1], f = nf >> 8, fbase = rec(cur)[2] >> 8;
+                    if (f == kRoot) {
+                        if (!lm && (!(nf & 8u) || fbase != img.root_base)) ++bad;  // CF_FROOT, pre-resolved base
+                        if (!child(img.root_base, &got)) got = kRoot;
+                        break;
+                    }
+                    if (lm && f == kDead) {
+                        got = kRoot;
+                        break;
+                    }
+                    if (fbase != (rec(f)[0] >> 8)) ++bad;  // fbase is the failure state's BASE
+                    if (child(fbase, &got)) break;
+                    const uint32_t f2 = rec(f)[1] >> 8;
+                    if (((nf & 2u) != 0) != (f2 == kRoot)) ++bad;  // CF_F2ROOT
+                    if (lm && ((nf & 4u) != 0) != (f2 == kDead)) ++bad;  // CF_F2DEAD
+                    if (nf & 2u) {
+                        if (!child(img.root_base, &got)) got = kRoot;
+                        break;
+                    }
+                    if (lm && (nf & 4u)) {
+                        got = kRoot;
+                        break;
+                    }
+                    cur = f;  // its children were just probed through fbase: go on with ITS failure fields
+                }
+            }
+            if (got != nid(t)) {
+                if (getenv("EMU_DBG") && bad < 10) fprintf(stderr, "s=%u(new %u) c=%u crate->%u(new %u) image->%u base=%u\n", s, nid(s), c, t, nid(t), got, rec(nid(s))[0]>>8);
+                ++bad;
+            }
+        }
+    }
+    if (hot_slots_out) *hot_slots_out = img.hot_slots;
+    if (hot_used_out) *hot_used_out = hot_used;
+    delete pma;
+    return bad;
+}

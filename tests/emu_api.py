@@ -25,7 +25,19 @@ def lib():
         _lib.emu_scan_stream_wire.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                               C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
         _lib.emu_scan_stream_wire.restype = C.c_int
+        _lib.emu_check_image_transitions.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_uint32),
+                                                     C.POINTER(C.c_uint32)]
+        _lib.emu_check_image_transitions.restype = C.c_longlong
     return _lib
+
+
+def check_image_transitions(wire, want_hot_slots):
+    """Every (state, byte) transition of the compact bytewise device image against the crate's transition
+    function.  Returns (mismatches, hot_slots, states placed in the hot region)."""
+    wire_a = np.frombuffer(wire, dtype=np.uint8)
+    hs, hu = C.c_uint32(), C.c_uint32()
+    bad = lib().emu_check_image_transitions(wire_a.ctypes.data, wire_a.size, int(want_hot_slots), C.byref(hs), C.byref(hu))
+    return int(bad), int(hs.value), int(hu.value)
 
 
 def scan(wire, charwise, mode, text, offs, hot_n=0, pool_blocks=None, out_cap=None, kernel=3, seg_len=0, seg_from=0):

@@ -228,6 +228,61 @@ def test_stream_chunks_equal_the_stepper_over_the_whole_stream(seed, mode, kerne
         assert int(state[i]) == pma.state_after(s, find_mode=(mode == 0))
 
 
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("hot_slots", [0, 256, 4096, 65536])
+def test_device_image_transition_function_is_the_crates(kind, hot_slots):
+    """Exhaustive, scan-independent check of the compact bytewise image (dev_image.cpp): for EVERY state and
+    byte, walking the records the way the lane machines do -- child signature, BASE ^ c with CHECK, the
+    pre-resolved failure base, CF_FROOT / CF_F2ROOT / CF_F2DEAD -- lands where the crate's next_state
+    (src/bytewise.rs:1063-1128) lands, for every size of the hot region (none, one block, some, all)."""
+    rng = np.random.default_rng(4200 + kind)
+    for pats in (sorted(set(rand_patterns(rng, 2500, 5, 10))), [b"a"], [b"ab", b"b", bytes(range(256))],
+                 sorted(set(bytes(rng.integers(0, 256, size=int(rng.integers(1, 6))).tolist()) for _ in range(3000)))):
+        pma = O.OraclePma.build(pats, match_kind=kind)
+        bad, hs, used = E.check_image_transitions(pma.serialize(), hot_slots)
+        assert bad == 0, (kind, hot_slots, len(pats))
+        assert hs <= hot_slots and hs % 256 == 0
+        if hot_slots and len(pats) > 1000:
+            assert used > 2  # more than ROOT and DEAD live in the region
+
+
+def test_device_image_transitions_with_the_default_region_on_a_large_automaton():
+    """The default region (65536 slots) in front of an automaton several times that size: most states stay in
+    the shifted part and many families leave holes behind there."""
+    rng = np.random.default_rng(99)
+    pats = sorted(set(bytes(rng.integers(0, 256, size=int(rng.integers(2, 7))).tolist()) for _ in range(60000)))
+    for kind in (0, 1):
+        pma = O.OraclePma.build(pats, match_kind=kind)
+        bad, hs, used = E.check_image_transitions(pma.serialize(), 65536)
+        assert bad == 0 and hs == 65536 and used > 30000
+
+
+@pytest.mark.parametrize("hot_slots", [256, 1024])
+def test_nul_bytes_do_not_land_in_slots_a_moved_family_left_behind(hot_slots):
+    """Regression: a state whose BASE equals a slot that a re-placed family vacated must not take label 0x00 as
+    a child there.  Binary patterns and texts full of NUL bytes, a region much smaller than the automaton."""
+    rng = np.random.default_rng(31337)
+    pats = sorted(set(bytes(rng.choice([0, 0, 1, 2, 3, 255], size=int(rng.integers(1, 9))).tolist()) for _ in range(4000)))
+    E.lib().emu_set_hot_slots(hot_slots)
+    try:
+        for kind in (0, 1):
+            pma = O.OraclePma.build(pats, match_kind=kind)
+            wire = pma.serialize()
+            n = 16
+            hays = [bytes(rng.choice([0, 0, 0, 1, 2, 3, 255], size=int(rng.integers(0, 900))).tolist()) for _ in range(n)]
+            offs = np.zeros(n + 1, dtype=np.uint64)
+            offs[1:] = np.cumsum([len(h) for h in hays])
+            text = np.frombuffer(b"".join(hays), dtype=np.uint8)
+            for mode in ([3] if kind else [0, 1, 2]):
+                ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
+                for kernel in (1, 2, 3, 4):
+                    rc, m, oo, need = E.scan(wire, False, mode, text, offs, kernel=kernel)
+                    assert rc == 0 and need == ref["total"], (kind, mode, kernel)
+                    assert m.tobytes() == ref["matches"].tobytes(), (kind, mode, kernel)
+    finally:
+        E.lib().emu_set_hot_slots(65536)
+
+
 @pytest.mark.parametrize("seed", range(4))
 @pytest.mark.parametrize("hot_slots", [0, 256, 1024, 65536])
 def test_hot_first_relayout_at_dictionary_shape(seed, hot_slots):

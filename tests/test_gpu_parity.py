@@ -303,6 +303,27 @@ def test_bytewise_leftmost_lane_machine(kind):
     assert np.array_equal(r0.offsets, r1.offsets) and np.array_equal(r2.offsets, r1.offsets)
 
 
+@pytest.mark.parametrize("kind", [0, 1])
+def test_binary_text_full_of_nul_bytes_on_a_relaid_out_automaton(kind):
+    """Binary patterns and haystacks made mostly of 0x00, an automaton several times the hot region (the
+    shifted part keeps the holes re-placed families leave behind): label 0 must never be taken for a child
+    in such a hole (dev_image.cpp); every lane-machine kernel against the oracle."""
+    rng = np.random.default_rng(31337 + kind)
+    pats = sorted(set(bytes(rng.choice([0, 0, 1, 2, 3, 255], size=int(rng.integers(1, 12))).tolist())
+                      for _ in range(120000)))
+    n = 3000
+    lens = rng.integers(0, 1500, size=n)
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    text = rng.choice(np.array([0, 0, 0, 1, 2, 3, 255], dtype=np.uint8), size=int(offs[-1]))
+    pma = D.DoubleArrayAhoCorasickBuilder.new().match_kind(kind).build(pats)
+    opma = O.OraclePma.build(pats, match_kind=kind)
+    for mode in ([D.LEFTMOST_FIND] if kind else [D.FIND, D.FIND_OVERLAPPING, D.FIND_OVERLAPPING_NO_SUFFIX]):
+        for kernel in (DEFAULT_KERNEL, 2, 1):
+            pma.set_option("kernel", kernel)
+            check_batch(pma, opma, mode, text, offs)
+
+
 def test_full_size_properties_c3():
     """Size-independent properties at a larger batch (1 GiB of the C3 workload, device resident):
     (1) find_iter output == greedy filter of the find_overlapping_iter output (SURVEY C.2);
