@@ -445,6 +445,11 @@ extern "C" long long emu_check_image_transitions(const uint8_t* wire, size_t wir
     uint32_t hot_used = 0;
     for (uint32_t s : q) {
         if (nid(s) < img.hot_slots) ++hot_used;
+        {  // output position and CF_OUT travel with the state; stream state ids map back
+            const uint32_t op = pma->opos_ch[s] >> 8;
+            if (img.opos_tab[nid(s)] != op || ((rec(nid(s))[1] & 1u) != 0) != (op != 0)) ++bad;
+            if (img.hot_slots && img.old_of_new[nid(s)] != s) ++bad;
+        }
         for (uint32_t c = 0; c < 256; ++c) {
             // the crate (src/bytewise.rs:1063-1088 / :1094-1128)
             uint32_t t = s;
@@ -512,6 +517,96 @@ extern "C" long long emu_check_image_transitions(const uint8_t* wire, size_t wir
     }
     if (hot_slots_out) *hot_slots_out = img.hot_slots;
     if (hot_used_out) *hot_used_out = hot_used;
+    delete pma;
+    return bad;
+}
+
+// The same for the charwise compact image (CwMachine): every reachable state x every mapped code.  Records are
+// {BASE << 8 | sig lo, efail << 8 | flags, fbase << 8 | sig hi, parent << 8}; a child of `cur` for code k is
+// the slot BASE ^ k whose parent field is `cur` (src/charwise.rs:1008-1060, child_index / next_state).
+extern "C" long long emu_check_image_transitions_charwise(const uint8_t* wire, size_t wire_len) {
+    dach_pma* pma = nullptr;
+    size_t used = 0;
+    if (wire_read(wire, wire_len, true, &pma, &used)) return -1;
+    HostImage img;
+    if (build_image(pma, &img) || img.crec.empty()) {
+        delete pma;
+        return -1;
+    }
+    const bool lm = is_leftmost(pma->match_kind);
+    const uint32_t n = uint32_t(pma->slots()), A = pma->alphabet_size;
+    auto rec = [&](uint32_t slot) { return &img.crec[(size_t)slot * 4]; };
+    auto crate_child = [&](uint32_t s, uint32_t k, uint32_t* out) {
+        const uint32_t b = pma->base[s];
+        if (!b) return false;
+        const uint32_t ci = b ^ k;
+        if (ci >= n || pma->check[ci] != s) return false;
+        *out = ci;
+        return true;
+    };
+    std::vector<uint8_t> live(n, 0);
+    std::vector<uint32_t> q{kRoot};
+    live[kRoot] = 1;
+    for (size_t h = 0; h < q.size(); ++h)
+        for (uint32_t k = 0; k < A; ++k) {
+            uint32_t ci;
+            if (crate_child(q[h], k, &ci) && !live[ci]) live[ci] = 1, q.push_back(ci);
+        }
+    long long bad = 0;
+    for (uint32_t s : q) {
+        if (img.opos_tab[s] != pma->output_pos[s] || ((rec(s)[1] & 1u) != 0) != (pma->output_pos[s] != 0)) ++bad;
+        for (uint32_t k = 0; k < A; ++k) {
+            uint32_t t = s;
+            for (;;) {  // the crate
+                if (crate_child(t, k, &t)) break;
+                if (t == kRoot) break;
+                const uint32_t f = pma->fail[t];
+                if (lm && f == kDead) {
+                    t = kRoot;
+                    break;
+                }
+                t = f;
+            }
+            auto child = [&](uint32_t par, uint32_t base, uint32_t* out) {  // the image
+                if (!base) return false;
+                const uint32_t a = base ^ k;
+                if (a >= n || (rec(a)[3] >> 8) != par) return false;
+                *out = a;
+                return true;
+            };
+            uint32_t cur = s, got = kRoot;
+            bool done = child(cur, rec(cur)[0] >> 8, &got);
+            const uint32_t sig = (rec(cur)[0] & 0xffu) | ((rec(cur)[2] & 0xffu) << 8);
+            if (done && !((sig >> (k & 15u)) & 1u)) ++bad;
+            if (!done && cur != kRoot) {
+                for (int guard = 0; guard < 1 << 20; ++guard) {
+                    const uint32_t nf = rec(cur)[1], f = nf >> 8, fbase = rec(cur)[2] >> 8;
+                    if (f == kRoot) {
+                        if (!child(kRoot, img.root_base, &got)) got = kRoot;
+                        break;
+                    }
+                    if (f == kDead) {
+                        got = kRoot;
+                        break;
+                    }
+                    if (fbase != (rec(f)[0] >> 8)) ++bad;
+                    if (child(f, fbase, &got)) break;
+                    const uint32_t f2 = rec(f)[1] >> 8;
+                    if (((nf & 2u) != 0) != (f2 == kRoot) || ((nf & 4u) != 0) != (f2 == kDead)) ++bad;
+                    if (nf & 2u) {
+                        if (!child(kRoot, img.root_base, &got)) got = kRoot;
+                        break;
+                    }
+                    if (nf & 4u) {
+                        got = kRoot;
+                        break;
+                    }
+                    cur = f;
+                }
+            }
+            if (got != t) ++bad;
+        }
+    }
     delete pma;
     return bad;
 }

@@ -28,7 +28,15 @@ def lib():
         _lib.emu_check_image_transitions.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_uint32),
                                                      C.POINTER(C.c_uint32)]
         _lib.emu_check_image_transitions.restype = C.c_longlong
+        _lib.emu_check_image_transitions_charwise.argtypes = [C.c_void_p, C.c_size_t]
+        _lib.emu_check_image_transitions_charwise.restype = C.c_longlong
     return _lib
+
+
+def check_image_transitions_charwise(wire):
+    """The charwise compact image: every (state, mapped code) transition against the crate's; mismatches."""
+    wire_a = np.frombuffer(wire, dtype=np.uint8)
+    return int(lib().emu_check_image_transitions_charwise(wire_a.ctypes.data, wire_a.size))
 
 
 def check_image_transitions(wire, want_hot_slots):

@@ -246,6 +246,19 @@ def test_device_image_transition_function_is_the_crates(kind, hot_slots):
             assert used > 2  # more than ROOT and DEAD live in the region
 
 
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_charwise_device_image_transition_function_is_the_crates(kind):
+    """The same exhaustive check for the charwise compact image (CwMachine): every reachable state x every mapped
+    code, plus output positions and the 16-bit child signature (src/charwise.rs:1008-1060)."""
+    rng = np.random.default_rng(4300 + kind)
+    cps = [0x61, 0x62, 0x63, 0xE6, 0x3042, 0x3044, 0x4E00, 0x1F600] + list(range(0x4E10, 0x4E60))
+    for npat, alpha in ((3000, 8), (3000, len(cps)), (1, 3)):
+        pats = sorted(set("".join(chr(cps[int(i)]) for i in rng.integers(0, alpha, size=int(rng.integers(1, 8))))
+                          for _ in range(npat)))
+        pma = O.OraclePma.build([p.encode("utf-8") for p in pats], charwise=True, match_kind=kind)
+        assert E.check_image_transitions_charwise(pma.serialize()) == 0, (kind, npat, alpha)
+
+
 def test_device_image_transitions_with_the_default_region_on_a_large_automaton():
     """The default region (65536 slots) in front of an automaton several times that size: most states stay in
     the shifted part and many families leave holes behind there."""
