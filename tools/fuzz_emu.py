@@ -1,0 +1,94 @@
+"""Randomised differential run of the emulated lane logic (tests/emu: scan_lane.cuh + dev_image.cpp compiled for
+the CPU) against the oracle: binary and text alphabets, every match kind and iterator, every lane-machine kernel,
+hot regions smaller than the automaton, segmented scans.  Not part of the test suite; run it for as long as you like:
+
+    python tools/fuzz_emu.py --seconds 600 --seed 1
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
+import emu_api as E  # noqa: E402
+import oracle_api as O  # noqa: E402
+
+ORC_MODE = {0: O.FIND, 1: O.FIND_OVERLAPPING, 2: O.FIND_OVERLAPPING_NO_SUFFIX, 3: O.LEFTMOST_FIND}
+
+
+def one_case(rng):
+    cw = bool(rng.integers(0, 4) == 0)
+    kind = int(rng.integers(0, 3))
+    style = int(rng.integers(0, 4))
+    if cw:
+        cps = [0x61, 0x62, 0x63, 0x64, 0xE6, 0x3042, 0x3044, 0x4E00, 0x1F600, 0x7F, 0x80, 0x7FF, 0x800, 0xFFFF, 0x10000]
+        alpha = int(rng.integers(2, len(cps) + 1))
+        sym = lambda k: "".join(chr(cps[int(i)]) for i in rng.integers(0, alpha, size=k)).encode("utf-8")  # noqa: E731
+    else:
+        if style == 0:
+            pool = np.array([0, 0, 1, 2, 255], dtype=np.uint8)
+        elif style == 1:
+            pool = np.arange(256, dtype=np.uint8)
+        else:
+            pool = np.arange(97, 97 + int(rng.integers(2, 9)), dtype=np.uint8)
+        sym = lambda k: bytes(rng.choice(pool, size=k).tolist())  # noqa: E731
+    npat = int(rng.choice([1, 5, 60, 800, 6000]))
+    maxlen = int(rng.integers(1, 14))
+    allow_empty = kind != 0 and rng.integers(0, 3) == 0
+    pats = sorted(set(sym(int(rng.integers(0 if allow_empty else 1, maxlen + 1))) for _ in range(npat)))
+    pats = [p for p in pats if p or allow_empty] or [sym(1)]
+    n = int(rng.integers(1, 40))
+    hays = [sym(int(rng.integers(0, int(rng.choice([4, 60, 700, 5000]))))) for _ in range(n)]
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(h) for h in hays])
+    text = np.frombuffer(b"".join(hays), dtype=np.uint8) if offs[-1] else np.zeros(0, dtype=np.uint8)
+    hot_slots = int(rng.choice([0, 256, 512, 4096, 65536]))
+    return cw, kind, pats, text, offs, hot_slots
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=60)
+    ap.add_argument("--seed", type=int, default=0)
+    a = ap.parse_args()
+    rng = np.random.default_rng(a.seed)
+    t0, cases, scans = time.time(), 0, 0
+    while time.time() - t0 < a.seconds:
+        cw, kind, pats, text, offs, hot_slots = one_case(rng)
+        try:
+            pma = O.OraclePma.build(pats, charwise=cw, match_kind=kind)
+        except O.OracleError:
+            continue
+        wire = pma.serialize()
+        E.lib().emu_set_hot_slots(hot_slots)
+        if not cw:
+            bad = E.check_image_transitions(wire, hot_slots)[0]
+        else:
+            bad = E.check_image_transitions_charwise(wire)
+        assert bad == 0, ("image", a.seed, cases, cw, kind, hot_slots)
+        for mode in ([3] if kind else [0, 1, 2]):
+            ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
+            kernels = (1,) if cw else ((1, 2) if kind else (1, 2, 3, 4))
+            for kernel in kernels:
+                segs = [(0, 0)]
+                if not cw and mode in (0, 1) and kernel != 4 and rng.integers(0, 2):
+                    segs.append((int(rng.choice([64, 256, 1024])), int(rng.integers(0, len(offs)))))
+                for seg_len, seg_from in segs:
+                    hot_n = int(rng.choice([0, 256])) if kernel == 3 else 0
+                    rc, m, oo, need = E.scan(wire, cw, mode, text, offs, kernel=kernel, seg_len=seg_len, seg_from=seg_from, hot_n=hot_n)
+                    ctx = (a.seed, cases, cw, kind, mode, kernel, seg_len, seg_from, hot_slots, hot_n)
+                    assert rc == 0 and need == ref["total"], ctx
+                    assert m.tobytes() == ref["matches"].tobytes(), ctx
+                    assert np.array_equal(np.diff(oo.astype(np.int64)), ref["counts"].astype(np.int64)), ctx
+                    scans += 1
+        cases += 1
+    E.lib().emu_set_hot_slots(65536)
+    print(f"fuzz_emu: seed {a.seed}: {cases} cases, {scans} scans, all equal to the oracle")
+
+
+if __name__ == "__main__":
+    main()
