@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import emu_api as E
-from cases import mixed_width_case
+from cases import mixed_width_case, nul_heavy_case
 import oracle_api as O
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -268,6 +268,23 @@ def test_device_image_transitions_with_the_default_region_on_a_large_automaton()
         pma = O.OraclePma.build(pats, match_kind=kind)
         bad, hs, used = E.check_image_transitions(pma.serialize(), 65536)
         assert bad == 0 and hs == 65536 and used > 30000
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_nul_heavy_case_of_the_gpu_suite_on_the_emulated_lanes(kind):
+    """tests/test_gpu_parity.py::test_binary_text_full_of_nul_bytes_on_a_relaid_out_automaton, same data, default
+    region, on the CPU (fewer haystacks: the emulation is slow)."""
+    pats, text, offs = nul_heavy_case(kind, n_hay=150)
+    pma = O.OraclePma.build(pats, match_kind=kind)
+    wire = pma.serialize()
+    assert E.check_image_transitions(wire, 65536)[:2] == (0, 65536)
+    for mode in ([3] if kind else [0, 1, 2]):
+        ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
+        assert ref["total"] > 1000
+        for kernel in (3, 1):
+            rc, m, oo, need = E.scan(wire, False, mode, text, offs, kernel=kernel)
+            assert rc == 0 and need == ref["total"]
+            assert m.tobytes() == ref["matches"].tobytes(), (kind, mode, kernel)
 
 
 @pytest.mark.parametrize("hot_slots", [256, 1024])
