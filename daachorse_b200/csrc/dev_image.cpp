@@ -52,6 +52,8 @@ struct Relayout {
     std::vector<uint32_t> new_base;     // BASE of every (old) slot in the compact image's numbering
     std::vector<uint32_t> sig;          // child signature per (old) slot
     std::vector<uint32_t> vacant_check; // per region slot: 0x100 | CHECK for slots no state occupies (and ROOT, DEAD)
+    bool textbook = false;              // Standard automata: the trie and its failure links are Aho-Corasick's (see below)
+    uint32_t max_depth = 0;             // depth of the deepest trie state
 };
 
 constexpr uint32_t kNone = 0xffffffffu;
@@ -59,6 +61,8 @@ constexpr uint32_t kNone = 0xffffffffu;
 void relayout_bytewise(const dach_pma* p, uint32_t want_hot_slots, Relayout* R) {
     const size_t n = p->slots();
     R->hot_slots = 0;
+    R->textbook = false;
+    R->max_depth = 0;
     R->new_of_old.resize(n);
     R->new_base.assign(p->base.begin(), p->base.end());
     R->sig.assign(n, 0);
@@ -92,7 +96,10 @@ void relayout_bytewise(const dach_pma* p, uint32_t want_hot_slots, Relayout* R) 
         R->sig[s] = sig;
         nchild[s] = k;
     }
-    // slots the walk did not reach (vacant, or garbage of a hand-made automaton) still get their signature
+    // Slots the walk did not reach still get their signature.  In an automaton the builders made these are
+    // vacant and have no BASE.  A hand-made one may hold states there that only failure links lead to; if such
+    // a state answers to children, they are some trie state's children as well (or garbage), and moving that
+    // family away would change what the failure walk finds: the layout is then left alone.
     for (size_t s = 0; s < n; ++s) {
         if (parent[s] != kNone || p->base[s] == 0) continue;
         uint32_t sig = 0;
@@ -101,6 +108,33 @@ void relayout_bytewise(const dach_pma* p, uint32_t want_hot_slots, Relayout* R) 
             if (ci < n && (p->opos_ch[ci] & 0xffu) == c) sig |= 1u << (c & 31);
         }
         R->sig[s] = sig;
+        if (sig) tree = false;
+    }
+    // Is this the automaton Aho and Corasick describe -- every state with children a trie state, every failure
+    // link the state of the longest proper suffix?  Always, for what the builders make (src/nfa_builder.rs).  A
+    // hand-made blob can pass the crate's validation without it; then the state after a text is no longer a
+    // function of the text's last bytes, which cutting long haystacks into segments relies on (dev_scan.cu).
+    if (tree && !is_leftmost(p->match_kind)) {
+        bool ok = true;
+        for (size_t h = 1; h < bfs.size() && ok; ++h) {
+            const uint32_t s = bfs[h], par = parent[s], c = p->opos_ch[s] & 0xffu;
+            if (depth[s] > R->max_depth) R->max_depth = depth[s];
+            uint32_t t = kRoot;
+            if (par != kRoot) {
+                t = p->fail[par];
+                for (;;) {  // the crate's transition from the parent's failure state (src/bytewise.rs:1063-1088)
+                    const uint32_t b = p->base[t], ci = b ^ c;
+                    if (b != 0 && ci < n && (p->opos_ch[ci] & 0xffu) == c) {
+                        t = ci;
+                        break;
+                    }
+                    if (t == kRoot) break;
+                    t = p->fail[t];
+                }
+            }
+            ok = p->fail[s] == t;
+        }
+        R->textbook = ok;
     }
     uint64_t H64 = std::min<uint64_t>(want_hot_slots, (uint64_t(n) + 255) & ~uint64_t(255));
     H64 &= ~uint64_t(255);
@@ -250,6 +284,7 @@ int build_image(const dach_pma* p, HostImage* img) {
         if (n <= (size_t(1) << 24) && p->outputs.size() < (size_t(1) << 24)) {
             Relayout R;
             relayout_bytewise(p, img->want_hot_slots, &R);
+            img->segmentable = R.textbook && R.max_depth <= img->max_pattern_len;
             const uint32_t H = R.hot_slots;
             const size_t N = n + H;
             img->hot_slots = H;

@@ -28,6 +28,11 @@ struct HostImage {
     std::vector<uint32_t> new_of_old;  // crate slot -> compact slot (stream chunks take and return crate state ids)
     std::vector<uint32_t> old_of_new;  // compact slot -> crate slot
     std::vector<uint32_t> mapper;      // charwise code table
+    // bytewise Standard, compact image: the automaton is Aho-Corasick's in the textbook sense (a trie whose failure
+    // links lead to the longest proper suffix, no state deeper than the longest pattern), as everything the
+    // builders make is.  Only then may a long haystack be cut into segments with a warm-up of max_pattern_len - 1
+    // bytes; a hand-made blob that merely passes validation is scanned whole.
+    bool segmentable = false;
 };
 
 // Returns DACH_OK or DACH_INVALID_AUTOMATON (a failure chain that never reaches ROOT would

@@ -778,6 +778,7 @@ struct dach_dev {
     bool charwise = false;
     uint8_t match_kind = 0;
     uint32_t n_slots = 0, root_opos = 0, mapper_len = 0, max_pattern_len = 0;
+    bool segmentable = false;  // HostImage::segmentable: long haystacks may be cut into segments
     size_t image_bytes = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
@@ -1041,7 +1042,7 @@ int enqueue_scan(dach_dev* d, Workspace& W, int mode, const uint8_t* d_text, con
     // (L-1)-byte warm-up) so that small batches and long haystacks still
     // fill the machine; everything else works on whole haystacks.
     // (a chunk of a stream resumes in a given state: it stays one item)
-    bool seg = v1 && !d->charwise && !d_state_io && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX) && d->opt_seg_len >= 0;
+    bool seg = v1 && !d->charwise && !d_state_io && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX) && d->opt_seg_len >= 0 && d->segmentable;
     uint32_t seg_len = 0, seg_from = 0;
     uint64_t n_items_max = n;
     if (seg) {
@@ -1341,7 +1342,7 @@ int scan_batch_host_impl(dach_dev* d, int mode, const uint8_t* text, const uint6
     {
         // find_iter / leftmost_find_iter / charwise work on whole haystacks: a slice should bring at least one
         // haystack per lane (find_overlapping slices are cut into segments on the device instead)
-        const bool segmentable = !d->charwise && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX) && d->d_crec && d->opt_seg_len >= 0;
+        const bool segmentable = !d->charwise && (mode == M_OVERLAPPING || mode == M_NO_SUFFIX) && d->d_crec && d->opt_seg_len >= 0 && d->segmentable;
         const uint64_t lanes = (uint64_t)d->sm_count * 1024, avg = (offs[n] - offs[0]) / n + 1;
         if (!segmentable) slice_bytes = std::min<uint64_t>(std::max(slice_bytes, lanes * avg), 1ull << 30);
     }
@@ -1536,6 +1537,7 @@ int dach_dev_upload(const dach_pma* pma, int device, dach_dev** out) {
         d->n_slots = img.n_slots;
         d->root_opos = img.root_opos;
         d->max_pattern_len = img.max_pattern_len;
+        d->segmentable = img.segmentable;
         d->mapper_len = (uint32_t)img.mapper.size();
         cudaDeviceProp prop;
         if (!cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return DACH_CUDA_ERROR;

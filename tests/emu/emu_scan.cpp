@@ -429,21 +429,15 @@ extern "C" long long emu_check_image_transitions(const uint8_t* wire, size_t wir
     const uint32_t N = img.n_cslots;
     auto rec = [&](uint32_t slot) { return &img.crec[(size_t)slot * 4]; };
     auto nid = [&](uint32_t s) { return img.hot_slots ? img.new_of_old[s] : s; };
-    // reachable states of the host automaton
+    // states a scan can be in: the closure of ROOT under the crate's transition function (for an automaton the
+    // builders made that is the trie; a hand-made one may have states only failure links lead to)
     std::vector<uint8_t> live(n, 0);
     std::vector<uint32_t> q{kRoot};
     live[kRoot] = 1;
-    for (size_t h = 0; h < q.size(); ++h) {
-        const uint32_t s = q[h], b = pma->base[s];
-        if (!b) continue;
-        for (uint32_t c = 0; c < 256; ++c) {
-            const uint32_t ci = b ^ c;
-            if (ci < n && (pma->opos_ch[ci] & 0xffu) == c && !live[ci]) live[ci] = 1, q.push_back(ci);
-        }
-    }
     long long bad = 0;
     uint32_t hot_used = 0;
-    for (uint32_t s : q) {
+    for (size_t h = 0; h < q.size(); ++h) {
+        const uint32_t s = q[h];
         if (nid(s) < img.hot_slots) ++hot_used;
         {  // output position and CF_OUT travel with the state; stream state ids map back
             const uint32_t op = pma->opos_ch[s] >> 8;
@@ -470,6 +464,7 @@ extern "C" long long emu_check_image_transitions(const uint8_t* wire, size_t wir
                 }
                 t = f;
             }
+            if (!live[t]) live[t] = 1, q.push_back(t);
             // the image, field by field as the lane machines read it (scan_lane.cuh, StdMachine3 / LmMachine)
             auto child = [&](uint32_t base, uint32_t* out) {
                 if (!base) return false;
@@ -523,7 +518,8 @@ extern "C" long long emu_check_image_transitions(const uint8_t* wire, size_t wir
 
 // The same for the charwise compact image (CwMachine): every reachable state x every mapped code.  Records are
 // {BASE << 8 | sig lo, efail << 8 | flags, fbase << 8 | sig hi, parent << 8}; a child of `cur` for code k is
-// the slot BASE ^ k whose parent field is `cur` (src/charwise.rs:1008-1060, child_index / next_state).
+// the slot BASE ^ k whose parent field is `cur` (src/charwise.rs:1022-1095, next_state_id(_leftmost)_unchecked).
+// Returns the mismatches, -1 for a refused automaton, -2 where the crate's own walk would not terminate.
 extern "C" long long emu_check_image_transitions_charwise(const uint8_t* wire, size_t wire_len) {
     dach_pma* pma = nullptr;
     size_t used = 0;
@@ -547,13 +543,9 @@ extern "C" long long emu_check_image_transitions_charwise(const uint8_t* wire, s
     std::vector<uint8_t> live(n, 0);
     std::vector<uint32_t> q{kRoot};
     live[kRoot] = 1;
-    for (size_t h = 0; h < q.size(); ++h)
-        for (uint32_t k = 0; k < A; ++k) {
-            uint32_t ci;
-            if (crate_child(q[h], k, &ci) && !live[ci]) live[ci] = 1, q.push_back(ci);
-        }
     long long bad = 0;
-    for (uint32_t s : q) {
+    for (size_t h = 0; h < q.size(); ++h) {  // closure of ROOT under the crate's transition function
+        const uint32_t s = q[h];
         if (img.opos_tab[s] != pma->output_pos[s] || ((rec(s)[1] & 1u) != 0) != (pma->output_pos[s] != 0)) ++bad;
         for (uint32_t k = 0; k < A; ++k) {
             uint32_t t = s;
@@ -561,12 +553,17 @@ extern "C" long long emu_check_image_transitions_charwise(const uint8_t* wire, s
                 if (crate_child(t, k, &t)) break;
                 if (t == kRoot) break;
                 const uint32_t f = pma->fail[t];
-                if (lm && f == kDead) {
+                if (f == kDead) {
+                    if (!lm) {  // DEAD fails to itself: the crate's standard walk would never return (hand-made
+                        delete pma;  // automata only; DESIGN.md section 1 lists it as a deliberate divergence)
+                        return -2;
+                    }
                     t = kRoot;
                     break;
                 }
                 t = f;
             }
+            if (!live[t]) live[t] = 1, q.push_back(t);
             auto child = [&](uint32_t par, uint32_t base, uint32_t* out) {  // the image
                 if (!base) return false;
                 const uint32_t a = base ^ k;
@@ -609,4 +606,15 @@ extern "C" long long emu_check_image_transitions_charwise(const uint8_t* wire, s
     }
     delete pma;
     return bad;
+}
+
+// HostImage::segmentable of a serialized bytewise automaton: 1 / 0, -1 for a refused one.
+extern "C" int emu_image_segmentable(const uint8_t* wire, size_t wire_len) {
+    dach_pma* pma = nullptr;
+    size_t used = 0;
+    if (wire_read(wire, wire_len, false, &pma, &used)) return -1;
+    HostImage img;
+    const int rc = build_image(pma, &img);
+    delete pma;
+    return rc ? -1 : (img.segmentable ? 1 : 0);
 }

@@ -33,6 +33,13 @@ def lib():
     return _lib
 
 
+def image_segmentable(wire):
+    """HostImage::segmentable of a serialized bytewise automaton (1 / 0; -1: refused)."""
+    wire_a = np.frombuffer(wire, dtype=np.uint8)
+    lib().emu_image_segmentable.argtypes = [C.c_void_p, C.c_size_t]
+    return int(lib().emu_image_segmentable(wire_a.ctypes.data, wire_a.size))
+
+
 def check_image_transitions_charwise(wire):
     """The charwise compact image: every (state, mapped code) transition against the crate's; mismatches."""
     wire_a = np.frombuffer(wire, dtype=np.uint8)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import emu_api as E
-from cases import mixed_width_case, nul_heavy_case
+from cases import damage_standard_wire, hand_made_case, mixed_width_case, nul_heavy_case
 import oracle_api as O
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -257,6 +257,54 @@ def test_charwise_device_image_transition_function_is_the_crates(kind):
                           for _ in range(npat)))
         pma = O.OraclePma.build([p.encode("utf-8") for p in pats], charwise=True, match_kind=kind)
         assert E.check_image_transitions_charwise(pma.serialize()) == 0, (kind, npat, alpha)
+
+
+def test_hand_made_automata_keep_the_crates_numbering_and_are_scanned_whole():
+    """What the builders make is Aho-Corasick's automaton: it may be relaid out and long haystacks may be cut into
+    segments.  A hand-made blob that passes the crate's validation need not be one -- a state only failure links
+    lead to that shares a BASE with a trie state, a failure link to some other state: the image must still scan
+    like the crate's loops (exhaustive check), keeps the crate's layout, and is not segmentable."""
+    rng = np.random.default_rng(8)
+    pats = sorted(set(rand_patterns(rng, 400, 4, 7)))
+    pma = O.OraclePma.build(pats)
+    wire = pma.serialize()
+    assert E.image_segmentable(wire) == 1 and E.check_image_transitions(wire, 256)[:2] == (0, 256)
+    _, a = damage_standard_wire(wire, [])
+    n = len(a)
+    inner = [s for s in range(2, n) if a[s, 0] != 0 and a[s, 1] != 0]          # trie states with children, depth > 1
+    vacant = [s for s in range(2, n) if a[s, 0] == 0 and a[s, 1] == 0 and (a[s, 2] >> 8) == 0]
+    leafish = [s for s in range(2, n) if a[s, 0] == 0 and a[s, 1] != 0]
+    assert inner and leafish
+    # (a) a failure link that is not the longest proper suffix: still a valid automaton for the crate
+    w1, _ = damage_standard_wire(wire, [(inner[0], 1, 0)])
+    bad, hs, _ = E.check_image_transitions(w1, 256)
+    assert bad == 0 and E.image_segmentable(w1) == 0
+    # (b) a childless state gets the BASE of a trie state and a trie state fails to it: reachable by failure links only
+    w2, _ = damage_standard_wire(wire, [(leafish[0], 0, int(a[inner[0], 0])), (inner[-1], 1, leafish[0])])
+    bad, hs, _ = E.check_image_transitions(w2, 256)
+    assert bad == 0 and hs == 0 and E.image_segmentable(w2) == 0
+    # (c) damage in slots no scan can reach changes nothing
+    if vacant:
+        w3, _ = damage_standard_wire(wire, [(vacant[0], 1, 5)])
+        assert E.check_image_transitions(w3, 256)[0] == 0 and E.image_segmentable(w3) == 1
+
+
+def test_hand_made_case_of_the_gpu_suite_on_the_emulated_lanes():
+    """tests/test_gpu_parity.py::test_hand_made_automaton_with_long_haystacks_is_scanned_whole on the CPU: whole
+    haystacks equal the oracle; forcing segments anyway is wrong, which is why the product does not."""
+    wire, text, offs = hand_made_case()
+    pma, _ = O.OraclePma.deserialize(wire)
+    assert E.image_segmentable(wire) == 0
+    differs = False
+    for mode in (1, 2):
+        ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
+        assert ref["total"] > 100
+        for kernel in (3, 1):
+            rc, m, oo, need = E.scan(wire, False, mode, text, offs, kernel=kernel)
+            assert rc == 0 and m.tobytes() == ref["matches"].tobytes()
+        rc, m, oo, need = E.scan(wire, False, mode, text, offs, kernel=3, seg_len=256)
+        differs |= rc != 0 or need != ref["total"] or m.tobytes() != ref["matches"].tobytes()
+    assert differs
 
 
 def test_device_image_transitions_with_the_default_region_on_a_large_automaton():

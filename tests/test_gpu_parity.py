@@ -9,7 +9,7 @@ import pytest
 
 import daachorse_b200 as D
 import oracle_api as O
-from cases import mixed_width_case, nul_heavy_case
+from cases import hand_made_case, mixed_width_case, nul_heavy_case
 from daachorse_b200 import synth as S
 
 pytestmark = pytest.mark.gpu
@@ -316,6 +316,19 @@ def test_binary_text_full_of_nul_bytes_on_a_relaid_out_automaton(kind):
         for kernel in ((DEFAULT_KERNEL, 1) if kind else (DEFAULT_KERNEL, 2, 1)):
             pma.set_option("kernel", kernel)
             check_batch(pma, opma, mode, text, offs)
+
+
+def test_hand_made_automaton_with_long_haystacks_is_scanned_whole():
+    """A blob that passes the crate's validation but is not Aho-Corasick's automaton (failure links rewired by
+    hand): the state after a text is not a function of its last bytes, so the device path must not cut the long
+    haystacks into segments (HostImage::segmentable) -- results as the crate's loops give them.  The emulated
+    lanes run the same case, and show that forcing segments would be wrong (tests/test_emu_lane.py)."""
+    wire, text, offs = hand_made_case()
+    pma, rest = D.DoubleArrayAhoCorasick.deserialize(wire)
+    assert len(rest) == 0
+    opma, _ = O.OraclePma.deserialize(wire)
+    for mode in (D.FIND_OVERLAPPING, D.FIND_OVERLAPPING_NO_SUFFIX, D.FIND):
+        check_batch(pma, opma, mode, text, offs)
 
 
 def test_full_size_properties_c3():

@@ -1,8 +1,10 @@
 """Randomised differential run of the emulated lane logic (tests/emu: scan_lane.cuh + dev_image.cpp compiled for
 the CPU) against the oracle: binary and text alphabets, every match kind and iterator, every lane-machine kernel,
-hot regions smaller than the automaton, segmented scans.  Not part of the test suite; run it for as long as you like:
+hot regions smaller than the automaton, segmented scans.  With --mutate the serialized automaton is damaged first
+(random BASE / CHECK / failure fields, the way a hand-made blob handed to deserialize might look): whatever still
+passes validation must scan like the crate's loops do.  Not part of the test suite; run it for as long as you like:
 
-    python tools/fuzz_emu.py --seconds 600 --seed 1
+    python tools/fuzz_emu.py --seconds 600 --seed 1 [--mutate]
 """
 import argparse
 import os
@@ -50,13 +52,48 @@ def one_case(rng):
     return cw, kind, pats, text, offs, hot_slots
 
 
+def mutate(rng, wire, cw, kind):
+    """Random field damage in the crate's wire format (src/bytewise.rs:801-820, src/charwise.rs:831-848)."""
+    w = bytearray(wire)
+    u32 = lambda off: int(np.frombuffer(w, dtype="<u4", count=1, offset=off)[0])  # noqa: E731
+    if cw:
+        n = u32(0)
+        a = np.frombuffer(w, dtype="<u4", count=n * 4, offset=4).reshape(n, 4)  # base, check, fail, output_pos
+        cols = {"base": a[:, 0], "check": a[:, 1], "fail": a[:, 2]}
+    elif kind == 0:
+        n = u32(0)
+        a = np.frombuffer(w, dtype="<u4", count=n * 3, offset=4).reshape(n, 3)  # base, fail, output_pos << 8 | check
+        cols = {"base": a[:, 0], "fail": a[:, 1], "opos_ch": a[:, 2]}
+    else:
+        assert u32(0) == 0
+        n = u32(4)
+        a = np.frombuffer(w, dtype="<u4", count=n * 2, offset=8).reshape(n, 2)  # base, output_pos << 8 | check
+        assert u32(8 + 8 * n) == n
+        f = np.frombuffer(w, dtype="<u4", count=n, offset=12 + 8 * n)
+        cols = {"base": a[:, 0], "opos_ch": a[:, 1], "fail": f}
+    for _ in range(int(rng.integers(1, 6))):
+        s, what = int(rng.integers(0, n)), int(rng.integers(0, 4))
+        if what == 0:
+            cols["base"][s] = int(rng.integers(0, n))
+        elif what == 1:
+            cols["fail"][s] = int(rng.integers(0, n))
+        elif what == 2 and cw:
+            cols["check"][s] = int(rng.integers(0, n))
+        elif what == 2:
+            cols["opos_ch"][s] = (int(cols["opos_ch"][s]) & ~0xFF) | int(rng.integers(0, 256))
+        else:
+            cols["base"][s] = 0
+    return bytes(w)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=60)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--mutate", action="store_true")
     a = ap.parse_args()
     rng = np.random.default_rng(a.seed)
-    t0, cases, scans = time.time(), 0, 0
+    t0, cases, scans, rejected = time.time(), 0, 0, 0
     while time.time() - t0 < a.seconds:
         cw, kind, pats, text, offs, hot_slots = one_case(rng)
         try:
@@ -64,18 +101,29 @@ def main():
         except O.OracleError:
             continue
         wire = pma.serialize()
+        if a.mutate:
+            wire = mutate(rng, wire, cw, kind)
         E.lib().emu_set_hot_slots(hot_slots)
         if not cw:
             bad = E.check_image_transitions(wire, hot_slots)[0]
         else:
             bad = E.check_image_transitions_charwise(wire)
+        if a.mutate and bad < 0:  # refused (validation, or failure links that never reach the root)
+            rejected += 1
+            continue
         assert bad == 0, ("image", a.seed, cases, cw, kind, hot_slots)
+        if a.mutate:
+            try:
+                pma, _ = O.OraclePma.deserialize(wire, charwise=cw)
+            except O.OracleError:
+                rejected += 1
+                continue
         for mode in ([3] if kind else [0, 1, 2]):
             ref = pma.scan_batch(ORC_MODE[mode], text, offs, want_matches=True)
             kernels = (1,) if cw else ((1, 2) if kind else (1, 2, 3, 4))
             for kernel in kernels:
                 segs = [(0, 0)]
-                if not cw and mode in (0, 1) and kernel != 4 and rng.integers(0, 2):
+                if not cw and mode in (1, 2) and kernel != 4 and rng.integers(0, 2) and E.image_segmentable(wire) == 1:
                     segs.append((int(rng.choice([64, 256, 1024])), int(rng.integers(0, len(offs)))))
                 for seg_len, seg_from in segs:
                     hot_n = int(rng.choice([0, 256])) if kernel == 3 else 0
@@ -87,7 +135,7 @@ def main():
                     scans += 1
         cases += 1
     E.lib().emu_set_hot_slots(65536)
-    print(f"fuzz_emu: seed {a.seed}: {cases} cases, {scans} scans, all equal to the oracle")
+    print(f"fuzz_emu: seed {a.seed}{' mutated' if a.mutate else ''}: {cases} cases ({rejected} refused), {scans} scans, all equal to the oracle")
 
 
 if __name__ == "__main__":
