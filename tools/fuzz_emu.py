@@ -53,7 +53,9 @@ def one_case(rng):
 
 
 def mutate(rng, wire, cw, kind):
-    """Random field damage in the crate's wire format (src/bytewise.rs:801-820, src/charwise.rs:831-848)."""
+    """Random field damage in the crate's wire format (src/bytewise.rs:801-820, src/charwise.rs:831-848): BASE,
+    CHECK and failure fields.  Output lists are left alone: a length larger than the depth of its state makes the
+    crate compute `end - length` below zero (a panic in debug builds), there is no behaviour to match."""
     w = bytearray(wire)
     u32 = lambda off: int(np.frombuffer(w, dtype="<u4", count=1, offset=off)[0])  # noqa: E731
     if cw:
