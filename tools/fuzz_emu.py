@@ -88,6 +88,56 @@ def mutate(rng, wire, cw, kind):
     return bytes(w)
 
 
+def stream_rounds(rng, pma, wire, cw, text, offs, ctx, mutated):
+    """dach_dev_scan_stream: the haystacks as streams, fed in ragged chunks (cut at char boundaries for charwise)
+    with the state carried over, against the crate's steppers over the whole stream."""
+    n = len(offs) - 1
+    streams = [bytes(text[int(offs[i]): int(offs[i + 1])]) for i in range(n)]
+    rounds = 0
+    E.lib().emu_stream_charwise(1 if cw else 0)
+    try:
+        for mode in (0, 1):
+            if not cw:
+                E.lib().emu_stream_config(int(rng.choice([2, 3, 4])), int(rng.choice([0, 256])))
+            orc_mode = O.FIND_STEPPER if mode == 0 else O.FIND_OVERLAPPING_STEPPER
+            want = []
+            for sb in streams:
+                ref = pma.scan_batch(orc_mode, np.frombuffer(sb, dtype=np.uint8), np.array([0, len(sb)], dtype=np.uint64),
+                                     want_matches=True)
+                mm = ref["matches"]
+                want.append([(int(x["start"]), int(x["end"]), int(x["value"])) for x in mm if int(x["end"]) != 0])
+            state = np.zeros(n, dtype=np.uint32)
+            pos = np.zeros(n, dtype=np.uint32)
+            got = [[] for _ in streams]
+            step = int(rng.choice([3, 40, 700]))
+            while any(int(pos[i]) < len(sb) for i, sb in enumerate(streams)):
+                chunks = []
+                for i, sb in enumerate(streams):
+                    e = min(len(sb), int(pos[i]) + int(rng.integers(0, step)))
+                    while cw and e < len(sb) and (sb[e] & 0xC0) == 0x80:
+                        e += 1
+                    chunks.append(sb[int(pos[i]): e])
+                co = np.zeros(n + 1, dtype=np.uint64)
+                co[1:] = np.cumsum([len(c) for c in chunks])
+                ct = np.frombuffer(b"".join(chunks), dtype=np.uint8) if co[-1] else np.zeros(0, dtype=np.uint8)
+                rc, m, oo, need = E.scan_stream(wire, mode, ct, co, state, pos)
+                if rc == 1 and mutated and rounds == 0:
+                    return 0  # BASE(ROOT) damaged to 0: stream chunks are refused (documented in the header)
+                assert rc == 0, ("stream rc", ctx, mode, rc)
+                for i in range(n):
+                    got[i] += [(int(x["start"]), int(x["end"]), int(x["value"])) for x in m[int(oo[i]): int(oo[i + 1])]]
+                    pos[i] += len(chunks[i])
+                rounds += 1
+            assert got == want, ("stream", ctx, mode)
+            for i, sb in enumerate(streams[:3]):  # the carried state is the crate's state id (pure-Python walk: a few only)
+                if not cw:
+                    assert int(state[i]) == pma.state_after(sb, find_mode=(mode == 0)), ("stream state", ctx, mode, i)
+    finally:
+        E.lib().emu_stream_charwise(0)
+        E.lib().emu_stream_config(3, 0)
+    return rounds
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=60)
@@ -135,6 +185,17 @@ def main():
                     assert m.tobytes() == ref["matches"].tobytes(), ctx
                     assert np.array_equal(np.diff(oo.astype(np.int64)), ref["counts"].astype(np.int64)), ctx
                     scans += 1
+                if ref["total"] > 1 and rng.integers(0, 4) == 0:  # the overflow protocol: the count is still exact
+                    cap = int(rng.integers(0, ref["total"]))
+                    rc, m, oo, need = E.scan(wire, cw, mode, text, offs, kernel=kernel, out_cap=cap)
+                    assert rc == 6 and need == ref["total"], ("cap", a.seed, cases, cw, kind, mode, kernel, cap)
+                    rc, m, oo, need = E.scan(wire, cw, mode, text, offs, kernel=kernel, out_cap=ref["total"],
+                                             pool_blocks=int(rng.integers(1, 4)))
+                    assert (rc == 6 and need == ref["total"]) or (rc == 0 and m.tobytes() == ref["matches"].tobytes()), \
+                        ("pool", a.seed, cases, cw, kind, mode, kernel)
+                    scans += 2
+        if kind == 0 and not any(len(p) == 0 for p in pats) and rng.integers(0, 3) == 0:
+            scans += stream_rounds(rng, pma, wire, cw, text, offs, (a.seed, cases, cw, hot_slots), a.mutate)
         cases += 1
     E.lib().emu_set_hot_slots(65536)
     print(f"fuzz_emu: seed {a.seed}{' mutated' if a.mutate else ''}: {cases} cases ({rejected} refused), {scans} scans, all equal to the oracle")
